@@ -1,0 +1,200 @@
+/*
+ * b200arrays.h — C ABI of libb200arrays.so: B200 (sm_100a) reduce / scan / sort
+ * primitives for CUDA.jl's CuArray hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces ONE reference
+ * interface (paths relative to the JuliaGPU/CUDA.jl v6.3.0 tree):
+ *
+ *   b200_reduce            GPUArrays.mapreducedim!(f, op, R::AnyCuArray, A; init)
+ *                          CUDACore/src/mapreduce.jl:168-301 (kernels :90-157)
+ *   b200_scan              CUDACore.scan!(f, output, input; dims, init, neutral)
+ *                          CUDACore/src/accumulate.jl:135-199 (kernels :15-131)
+ *   b200_sort_keys         Base.sort!(c::AnyCuArray; rev, dims)  -> bitonic_sort!(c)
+ *                          CUDACore/src/sorting.jl:1003-1009, :909-974
+ *   b200_sortperm          Base.sortperm!(ix, A; rev) / Base.sortperm(c)
+ *                          CUDACore/src/sorting.jl:1051-1070 (bitonic_sort!((A, ix)))
+ *   b200_sort_pairs        (key, payload) variant used by the multi-GPU sample sort
+ *   b200_select_flagged    findall(::CuArray{Bool}) = cumsum + scatter
+ *                          CUDACore/src/indexing.jl:26-66   ("next")
+ *
+ * Conventions (mirroring how lib/curand binds libcurand,
+ * lib/curand/src/libcurand.jl:166-215):
+ *   - plain C symbols, no C++ types, no exceptions; int32 status return, 0 = OK.
+ *   - device pointers are raw `void*` (CuPtr{T} is ABI-identical to Ptr,
+ *     CUDACore/src/pointer.jl:13-28); the caller's stream (CUstream ==
+ *     cudaStream_t, CUDACore/lib/cudadrv/stream.jl:78) is explicit in every call.
+ *   - the library allocates NOTHING on the device and keeps no device state:
+ *     temporaries come from the caller (CUDA.jl's stream-ordered pool through
+ *     with_workspace, CUDACore/src/utils/call.jl:23-103).  Two-phase protocol:
+ *     `*_workspace_bytes` first, then the call proper with a buffer of at least
+ *     that many bytes (256-byte aligned).  The workspace may be uninitialised;
+ *     all control words are (re)initialised on `stream` inside the call.
+ *   - no cudaSetDevice / cudaDeviceSynchronize / cudaStreamSynchronize inside:
+ *     calls are asynchronous on `stream`, re-entrant, thread-safe and
+ *     CUDA-graph capturable.
+ *   - arrays are dense and column-major.  An N-d array reduced / scanned /
+ *     sorted along one dimension (or one contiguous group of dimensions) is
+ *     passed as its (pre, n, post) factorisation:
+ *         element (i, r, j) lives at  i + pre * (r + n * j),
+ *     i in [0,pre), r in [0,n) along the processed dimension, j in [0,post).
+ */
+#ifndef B200ARRAYS_H
+#define B200ARRAYS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+/* Opaque here so that the header needs no CUDA headers; this is CUstream. */
+typedef struct CUstream_st *b200_stream_t;
+
+typedef enum {
+    B200_OK = 0,
+    B200_INVALID_VALUE = 1,        /* bad pointer / negative size / bad enum        */
+    B200_UNSUPPORTED = 2,          /* (dtype, op) combination outside the graft     */
+    B200_WORKSPACE_TOO_SMALL = 3,
+    B200_LAUNCH_FAILURE = 4,       /* cudaError of the failing call: b200_last_cuda_error() */
+    B200_WRONG_DEVICE = 5          /* not an sm_100 device                           */
+} b200_status_t;
+
+/* Element types (Julia names in comments). Bool is one byte holding 0 or 1. */
+typedef enum {
+    B200_F16 = 0,   /* Float16  */
+    B200_BF16 = 1,  /* BFloat16 (BFloat16s.jl) */
+    B200_F32 = 2,   /* Float32  */
+    B200_F64 = 3,   /* Float64  */
+    B200_I32 = 4,   /* Int32    */
+    B200_I64 = 5,   /* Int64    */
+    B200_U32 = 6,   /* UInt32   */
+    B200_U64 = 7,   /* UInt64   */
+    B200_BOOL = 8,  /* Bool     */
+    B200_I8 = 9,    /* Int8   (sort only) */
+    B200_U8 = 10,   /* UInt8  (sort only) */
+    B200_I16 = 11,  /* Int16  (sort only) */
+    B200_U16 = 12,  /* UInt16 (sort only) */
+    B200_DTYPE_COUNT = 13
+} b200_dtype_t;
+
+/* Binary reduction / scan operators.  ADD covers both `+` and Base.add_sum, MUL
+ * both `*` and Base.mul_prod: the widening those imply (Int32 -> Int64, Bool ->
+ * Int64 ...) is expressed by the caller through dtype_out, exactly as GPUArrays
+ * expresses it through eltype(R).  MAX / MIN follow IEEE-754-2019 maximum /
+ * minimum for floats (NaN-propagating, -0.0 < +0.0), as the reference's device
+ * overrides do (CUDACore/src/device/intrinsics/math.jl:458-487).
+ * EXTREMA is Base.ExtremaMap / Base._extrema_rf: the output holds (min, max)
+ * pairs of dtype_out, i.e. 2 elements per reduced slice. */
+typedef enum {
+    B200_OP_ADD = 0,
+    B200_OP_MUL = 1,
+    B200_OP_MAX = 2,
+    B200_OP_MIN = 3,
+    B200_OP_AND = 4,
+    B200_OP_OR = 5,
+    B200_OP_EXTREMA = 6,   /* reduce only */
+    B200_OP_COUNT = 7
+} b200_op_t;
+
+/* Element map applied before the operator (the `f` of mapreduce). */
+typedef enum {
+    B200_MAP_IDENTITY = 0,
+    B200_MAP_ABS2 = 1,     /* integers: x*x wrapping in the input type; floats: x*x */
+    B200_MAP_COUNT = 2
+} b200_map_t;
+
+/* How the prior contents of the output are treated (the `init` kwarg of
+ * mapreducedim!, mapreduce.jl:108-112,142-146). */
+typedef enum {
+    B200_INIT_NEUTRAL = 0,   /* init === neutral_element(op, T): out is overwritten      */
+    B200_INIT_FROM_OUT = 1   /* init === nothing: out = op(out_before, reduction), folded once */
+} b200_init_t;
+
+/* ---- library ----------------------------------------------------------- */
+int32_t b200_version(void);                       /* major*10000 + minor*100 + patch */
+const char *b200_status_string(int32_t status);
+int32_t b200_last_cuda_error(void);               /* thread-local cudaError_t of the last LAUNCH_FAILURE */
+/* 0 when the current device is compute capability 10.x, B200_WRONG_DEVICE otherwise. */
+int32_t b200_check_device(void);
+/* Number of kernels launched by this thread through the library since the last
+ * reset (bench.py's gpu_launches).  Host-side counter only. */
+int64_t b200_launch_count(void);
+void b200_reset_launch_count(void);
+
+/* ---- reduce: GPUArrays.mapreducedim! (mapreduce.jl:168) ----------------- */
+/* out[i, 0, j] = op over r of map(in[i, r, j]);  in: pre*red*post elements of
+ * dtype_in, out: pre*post elements of dtype_out (2x for EXTREMA).
+ * Accumulation happens in dtype_out (Float16/BFloat16: in Float32, rounded once).
+ * When pre*post >= 1024 * #SM and pre > 1 (the reference's serial-kernel
+ * regime, mapreduce.jl:162-166,203) each output is accumulated sequentially in
+ * index order, which the reference's own tests pin (test/core/array.jl:771-773).
+ * red == 0 or pre*post == 0: returns OK without touching out (mapreduce.jl:175). */
+int32_t b200_reduce_workspace_bytes(int32_t dtype_in, int32_t dtype_out, int32_t op, int32_t map,
+                                    int64_t pre, int64_t red, int64_t post, size_t *bytes);
+int32_t b200_reduce(void *workspace, size_t workspace_bytes,
+                    const void *in, void *out,
+                    int32_t dtype_in, int32_t dtype_out, int32_t op, int32_t map,
+                    int64_t pre, int64_t red, int64_t post,
+                    int32_t init_mode, b200_stream_t stream);
+
+/* ---- scan: CUDACore.scan! (accumulate.jl:135) --------------------------- */
+/* Inclusive (exclusive != 0: exclusive) prefix-op along n.  `init` is a HOST
+ * pointer to one dtype_out value (the x of Some(x)) folded into every output,
+ * or NULL (accumulate.jl:90-92,123-125).  Exclusive scans start from init (or
+ * the operator's neutral element).  in == out (exact aliasing) is allowed.
+ * Ops: ADD, MUL, MAX, MIN, AND, OR. */
+int32_t b200_scan_workspace_bytes(int32_t dtype_in, int32_t dtype_out, int32_t op,
+                                  int64_t pre, int64_t n, int64_t post, size_t *bytes);
+int32_t b200_scan(void *workspace, size_t workspace_bytes,
+                  const void *in, void *out,
+                  int32_t dtype_in, int32_t dtype_out, int32_t op, int32_t exclusive,
+                  int64_t pre, int64_t n, int64_t post,
+                  const void *init_host, b200_stream_t stream);
+
+/* ---- sort: Base.sort! / sortperm! hooks (sorting.jl:1003-1070) ---------- */
+/* Order is Julia's `isless`: -Inf < ... < -0.0 < +0.0 < ... < +Inf < NaN (all
+ * NaNs equal, last), two's-complement order for signed ints; `descending` is
+ * `rev=true` (stable: ties keep ascending index, sorting.jl:582-592).
+ * Stable LSD radix sort.  Segments: `nseg` independent contiguous vectors of
+ * `n` keys each (sort!(A; dims=1) of an n x nseg matrix); nseg = 1 for vectors. */
+int32_t b200_sort_workspace_bytes(int32_t dtype_key, int32_t dtype_payload /* -1: keys only */,
+                                  int64_t n, int64_t nseg, size_t *bytes);
+/* In place. */
+int32_t b200_sort_keys(void *workspace, size_t workspace_bytes,
+                       void *keys, int32_t dtype_key, int64_t n, int64_t nseg,
+                       int32_t descending, b200_stream_t stream);
+/* perm[k] = 1-based index (within its segment when `linear` == 0, else the
+ * 1-based linear index into the whole array, sorting.jl:1067-1070) of the k-th
+ * smallest key; keys are not modified (sorting.jl:857-858).  dtype_index is any
+ * of I32/I64/U32/U64 (test/core/sorting.jl:395-403). */
+int32_t b200_sortperm(void *workspace, size_t workspace_bytes,
+                      const void *keys, void *perm,
+                      int32_t dtype_key, int32_t dtype_index, int64_t n, int64_t nseg,
+                      int32_t descending, int32_t linear, b200_stream_t stream);
+/* Sorts keys in place and permutes `payload` (4- or 8-byte elements, dtype
+ * I32/U32/I64/U64/F32/F64 treated as raw bits) along with them. */
+int32_t b200_sort_pairs(void *workspace, size_t workspace_bytes,
+                        void *keys, void *payload,
+                        int32_t dtype_key, int32_t dtype_payload, int64_t n,
+                        int32_t descending, b200_stream_t stream);
+
+/* ---- select: findall(::CuArray{Bool}) (indexing.jl:26-66) --------------- */
+/* Writes the 1-based linear indices (dtype_index I32/I64) of the non-zero flags
+ * to `indices` in order and the number found to *count_dev (device int64).
+ * One pass: scan and scatter are fused.  `indices` must hold n entries. */
+int32_t b200_select_workspace_bytes(int64_t n, size_t *bytes);
+int32_t b200_select_flagged(void *workspace, size_t workspace_bytes,
+                            const void *flags_bool, void *indices, int32_t dtype_index,
+                            void *count_dev, int64_t n, b200_stream_t stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ARRAYS_H */
