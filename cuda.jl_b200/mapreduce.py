@@ -6,6 +6,7 @@ that reach it (SURVEY §3.1, §8 a1/a1').
 calling it: output eltype, neutral `init`, reduced output shape, scalar read-back
 for `dims=:`.  All device work goes through libb200arrays' `b200_reduce`.
 """
+import builtins as _bi
 import ctypes
 
 import numpy as np
@@ -76,7 +77,7 @@ def _factor(adims, rdims):
     for d in range(nd):
         if rdims[d] != adims[d] and rdims[d] != 1:
             raise DimensionMismatch(f"cannot reduce {adims} into {rdims}")  # Base.check_reducedims
-    if any(r != 1 for r in rdims[nd:]):
+    if _bi.any(r != 1 for r in rdims[nd:]):
         raise DimensionMismatch(f"cannot reduce {adims} into {rdims}")
     reduced = [d for d in range(nd) if rdims[d] == 1 and adims[d] != 1]
     if not reduced:
