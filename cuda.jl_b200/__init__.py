@@ -11,6 +11,7 @@ from .cuarray import CuArray, Array
 from .mapreduce import (identity, abs2, add_sum, mul_prod, add, mul, max_, min_, and_, or_, extrema_rf,
                         neutral_element, mapreducedim_, mapreduce, reduce, sum, prod, maximum, minimum,
                         extrema, count, any, all, sum_, prod_, maximum_, minimum_)
+from .accumulate import scan_, accumulate_, accumulate, cumsum, cumprod, cumsum_, cumprod_
 from . import _lib
 
 __all__ = [n for n in dir() if not n.startswith("_")]

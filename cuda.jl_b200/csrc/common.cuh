@@ -139,6 +139,31 @@ template <class T> __device__ __forceinline__ T ldg_stream(const T *p) {
     }
 }
 
+// Coherent streaming loads (no .nc): used where input and output may alias exactly
+// (accumulate!(op, x, x)), each address being read before the same CTA overwrites it.
+__device__ __forceinline__ Vec16 ld_coh16(const void *p) {
+    Vec16 v;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p) : "memory");
+    return v;
+}
+template <class T> __device__ __forceinline__ T ld_coh(const T *p) {
+    if constexpr (sizeof(T) == 1) {
+        uint16_t r; asm volatile("ld.global.L1::no_allocate.u8 %0, [%1];" : "=h"(r) : "l"(p) : "memory");
+        uint8_t b = (uint8_t)r; T t; memcpy(&t, &b, 1); return t;
+    } else if constexpr (sizeof(T) == 2) {
+        uint16_t r; asm volatile("ld.global.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p) : "memory");
+        T t; memcpy(&t, &r, 2); return t;
+    } else if constexpr (sizeof(T) == 4) {
+        uint32_t r; asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+        T t; memcpy(&t, &r, 4); return t;
+    } else {
+        static_assert(sizeof(T) == 8, "unsupported element size");
+        uint64_t r; asm volatile("ld.global.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
+        T t; memcpy(&t, &r, 8); return t;
+    }
+}
+
 __device__ __forceinline__ void stg_stream16(void *p, const Vec16 &v) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]) : "memory");

@@ -1,0 +1,652 @@
+// scan.cuh — single-pass prefix scan (decoupled look-back) for sm_100a.
+//
+// Replaces partial_scan + aggregate_partial_scan + the recursive host glue of
+// CUDACore/src/accumulate.jl:15-131,166-196 (>= 4 launches per level and ~4N
+// traffic) with ONE kernel that reads every element once and writes it once.
+//
+// Layout: (pre, n, post) view of a dense column-major array, scanned along n.
+//   contig  (pre == 1): `post` independent chains.  A tile is 256 threads x K
+//           chunks; chunks are WARP-STRIPED (chunk c of a warp = row k, lane l,
+//           c = k*32 + l) so every load/store instruction of a warp covers one
+//           contiguous 512-byte span: fully coalesced with no shared-memory
+//           transpose.  Per tile: chunk-serial scan, K warp scans, one block scan,
+//           then Merrill-Garland decoupled look-back over the per-tile status words.
+//   strided (pre > 1): one thread per column marching along n (coalesced across
+//           columns).  [SURVEY §8 f2: look-back chains for strided scans are "next".]
+//
+// Tile status words live in the caller's workspace: {flag:32 | payload:32} packed in
+// one 64-bit word per 32 bits of the accumulator, written/read with relaxed
+// gpu-scope 64-bit accesses (single-copy atomic), so no fences are needed; a
+// reader of a 64-bit accumulator retries until both halves carry the same flag.
+// Tiles take their index from an atomic ticket, so a tile's predecessors are always
+// resident or finished (forward progress without relying on block scheduling order).
+#pragma once
+#include "ops.cuh"
+
+namespace b200 {
+
+constexpr int SC_THREADS = 256;
+constexpr int SC_WARPS = SC_THREADS / 32;
+constexpr uint32_t SC_INVALID = 0, SC_PARTIAL = 1, SC_INCLUSIVE = 2;
+constexpr int SC_LOOK = 4;        // predecessors inspected per lane per look-back round trip
+
+struct ScanParams {
+    const void *in;
+    void *out;
+    uint64_t *status;              // [post * tiles_per_seg * NW]
+    unsigned long long *ticket;    // [1]
+    int64_t pre, n, post;
+    int64_t tiles_per_seg;
+    int32_t exclusive;
+    int32_t has_init;
+    uint64_t init_bits;            // the Some(x) value, bit pattern of the accumulator type
+};
+
+__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <class A> struct StatusWords { static constexpr int NW = sizeof(A) > 4 ? 2 : 1; };
+
+template <class A> __device__ __forceinline__ void publish(uint64_t *slot, uint32_t flag, A value) {
+    constexpr int NW = StatusWords<A>::NW;
+    uint32_t w[NW] = {};
+    memcpy(w, &value, sizeof(A));
+#pragma unroll
+    for (int k = 0; k < NW; ++k) st_relaxed_u64(slot + k, ((uint64_t)flag << 32) | w[k]);
+}
+
+// Spins until the slot is valid; returns its flag and value.
+template <class A> __device__ __forceinline__ uint32_t wait_slot(const uint64_t *slot, A &value) {
+    constexpr int NW = StatusWords<A>::NW;
+    uint32_t w[NW];
+    uint32_t flag;
+    while (true) {
+        uint64_t r[NW];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) r[k] = ld_relaxed_u64(slot + k);
+        flag = (uint32_t)(r[0] >> 32);
+        bool ok = flag != SC_INVALID;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) { ok = ok && ((uint32_t)(r[k] >> 32) == flag); w[k] = (uint32_t)r[k]; }
+        if (ok) break;
+    }
+    memcpy(&value, w, sizeof(A));
+    return flag;
+}
+
+// One attempt: returns SC_INVALID when the slot is empty or its halves disagree.
+template <class A> __device__ __forceinline__ uint32_t peek_slot(const uint64_t *slot, A &value) {
+    constexpr int NW = StatusWords<A>::NW;
+    uint64_t r[NW];
+    if constexpr (NW == 2) {
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(r[0]), "=l"(r[1]) : "l"(slot) : "memory");
+    } else {
+        r[0] = ld_relaxed_u64(slot);
+    }
+    uint32_t w[NW];
+    uint32_t flag = (uint32_t)(r[0] >> 32);
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+        if ((uint32_t)(r[k] >> 32) != flag) flag = SC_INVALID;
+        w[k] = (uint32_t)r[k];
+    }
+    memcpy(&value, w, sizeof(A));
+    return flag;
+}
+
+template <class A> __device__ __forceinline__ A bits_to_acc(uint64_t bits) {
+    A a;
+    memcpy(&a, &bits, sizeof(A));
+    return a;
+}
+
+// Decoupled look-back, executed by one full warp.  Publishes this tile's aggregate,
+// walks back over predecessor status words until an inclusive prefix is found,
+// publishes this tile's inclusive prefix and returns its exclusive prefix.
+// Wide window: every lane inspects SC_LOOK consecutive predecessors per round trip
+// (32*SC_LOOK tiles per window).
+template <class Op>
+__device__ __forceinline__ typename Op::acc_t tile_lookback(const ScanParams &p, int64_t seg, int64_t t, int lane,
+                                                            typename Op::acc_t tile_agg) {
+    using A = typename Op::acc_t;
+    constexpr int NW = StatusWords<A>::NW;
+    uint64_t *slots = p.status + seg * p.tiles_per_seg * NW;
+    A prefix;
+    if (t == 0) {
+        prefix = p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity();
+        if (lane == 0 && p.tiles_per_seg > 1) publish<A>(slots, SC_INCLUSIVE, Op::apply(prefix, tile_agg));
+        return prefix;
+    }
+    if (lane == 0) publish<A>(slots + t * NW, SC_PARTIAL, tile_agg);
+    prefix = Op::identity();
+    int64_t look = t - 1;
+    while (true) {
+        const int64_t first = look - (int64_t)lane * SC_LOOK;   // nearest predecessor of this lane
+        A vals[SC_LOOK];
+        uint32_t flags[SC_LOOK];
+        while (true) {
+            bool all_valid = true;
+#pragma unroll
+            for (int w = 0; w < SC_LOOK; ++w) {
+                const int64_t idx = first - w;
+                flags[w] = SC_INCLUSIVE;
+                vals[w] = Op::identity();
+                if (idx >= 0) flags[w] = peek_slot<A>(slots + idx * NW, vals[w]);
+                all_valid = all_valid && (flags[w] != SC_INVALID);
+            }
+            if (all_valid) break;
+        }
+        A val = Op::identity();
+        bool lane_incl = false;
+#pragma unroll
+        for (int w = 0; w < SC_LOOK; ++w) {
+            if (!lane_incl) {
+                val = Op::apply(vals[w], val);
+                lane_incl = flags[w] == SC_INCLUSIVE;
+            }
+        }
+        const uint32_t incl = __ballot_sync(0xffffffffu, lane_incl);
+        const int nearest = __ffs(incl) - 1;          // closest lane holding an inclusive prefix
+        if (incl && lane > nearest) val = Op::identity();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val = Op::apply(val, shfl_xor_any(val, o));
+        prefix = Op::apply(val, prefix);
+        if (incl) break;
+        look -= 32 * SC_LOOK;
+    }
+    if (lane == 0) publish<A>(slots + t * NW, SC_INCLUSIVE, Op::apply(prefix, tile_agg));
+    return prefix;
+}
+
+// Loads EPC consecutive elements starting at element offset `off` of the tile;
+// elements at or beyond `valid` are replaced by the operator's identity.
+template <class Tin, class A, class Op, int EPC>
+__device__ __forceinline__ void load_chunk(const Tin *tile, int64_t off, int64_t valid, A (&v)[EPC]) {
+    if (off + EPC <= valid) {
+        using LoadT = typename std::conditional<(EPC * sizeof(Tin) == 16), Vec16,
+                      typename std::conditional<(EPC * sizeof(Tin) == 8), uint64_t,
+                      typename std::conditional<(EPC * sizeof(Tin) == 4), uint32_t,
+                      typename std::conditional<(EPC * sizeof(Tin) == 2), uint16_t, uint8_t>::type>::type>::type>::type;
+        static_assert(sizeof(LoadT) == EPC * sizeof(Tin), "chunk size must be 1,2,4,8 or 16 bytes");
+        LoadT raw;
+        if constexpr (sizeof(LoadT) == 16) raw = ld_coh16(tile + off);
+        else raw = ld_coh(reinterpret_cast<const LoadT *>(tile + off));
+        Tin e[EPC];
+        memcpy(e, &raw, sizeof(LoadT));
+#pragma unroll
+        for (int k = 0; k < EPC; ++k) v[k] = cvt<A>(e[k]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < EPC; ++k) v[k] = (off + k < valid) ? cvt<A>(ld_coh(tile + off + k)) : Op::identity();
+    }
+}
+
+template <class Tout, class A, int EPC>
+__device__ __forceinline__ void store_chunk(Tout *tile, int64_t off, int64_t valid, const A (&v)[EPC]) {
+    if (off + EPC <= valid) {
+        Tout e[EPC];
+#pragma unroll
+        for (int k = 0; k < EPC; ++k) e[k] = cvt<Tout>(v[k]);
+        if constexpr (EPC * sizeof(Tout) == 16) {
+            Vec16 raw;
+            memcpy(&raw, e, 16);
+            *reinterpret_cast<Vec16 *>(tile + off) = raw;
+        } else if constexpr (EPC * sizeof(Tout) == 32) {
+            Vec16 raw[2];
+            memcpy(raw, e, 32);
+            *reinterpret_cast<Vec16 *>(tile + off) = raw[0];
+            *(reinterpret_cast<Vec16 *>(tile + off) + 1) = raw[1];
+        } else if constexpr (EPC * sizeof(Tout) == 8) {
+            uint64_t raw; memcpy(&raw, e, 8);
+            *reinterpret_cast<uint64_t *>(tile + off) = raw;
+        } else if constexpr (EPC * sizeof(Tout) == 4) {
+            uint32_t raw; memcpy(&raw, e, 4);
+            *reinterpret_cast<uint32_t *>(tile + off) = raw;
+        } else if constexpr (EPC * sizeof(Tout) == 2) {
+            uint16_t raw; memcpy(&raw, e, 2);
+            *reinterpret_cast<uint16_t *>(tile + off) = raw;
+        } else {
+#pragma unroll
+            for (int k = 0; k < EPC; ++k) tile[off + k] = e[k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < EPC; ++k)
+            if (off + k < valid) tile[off + k] = cvt<Tout>(v[k]);
+    }
+}
+
+// One tile per CTA.  EPC = elements per chunk, K = chunk rows per warp.
+template <class Tin, class Tout, class Op, int EPC, int K>
+__global__ void __launch_bounds__(SC_THREADS) scan_contig_kernel(ScanParams p) {
+    using A = typename Op::acc_t;
+    constexpr int WARP_ELEMS = 32 * EPC * K;
+    constexpr int TILE = SC_WARPS * WARP_ELEMS;
+    __shared__ A s_warp[SC_WARPS];
+    __shared__ A s_tile_prefix;
+    __shared__ unsigned long long s_ticket;
+
+    if (threadIdx.x == 0) s_ticket = atomicAdd(p.ticket, 1ull);
+    __syncthreads();
+    const int64_t g = (int64_t)s_ticket;
+    const int64_t seg = g / p.tiles_per_seg;
+    const int64_t t = g - seg * p.tiles_per_seg;
+    const int64_t tile_off = seg * p.n + t * TILE;
+    int64_t valid = p.n - t * TILE;
+    if (valid > TILE) valid = TILE;
+    const Tin *tin = static_cast<const Tin *>(p.in) + tile_off;
+    Tout *tout = static_cast<Tout *>(p.out) + tile_off;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // ---- load (warp-striped chunks) and scan inside each chunk
+    A v[K][EPC];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+        load_chunk<Tin, A, Op, EPC>(tin, (int64_t)warp * WARP_ELEMS + (k * 32 + lane) * EPC, valid, v[k]);
+    A csum[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int e = 1; e < EPC; ++e) v[k][e] = Op::apply(v[k][e - 1], v[k][e]);
+        csum[k] = v[k][EPC - 1];
+    }
+    // ---- K interleaved warp scans over the chunk sums
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            A up = shfl_up_any(csum[k], d);
+            if (lane >= d) csum[k] = Op::apply(up, csum[k]);
+        }
+    }
+    // chunk-exclusive prefix within the warp: earlier rows, then earlier lanes of this row
+    A cpre[K];
+    A run = Op::identity();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        A excl = shfl_up_any(csum[k], 1);
+        A rtot = shfl_idx_any(csum[k], 31);
+        cpre[k] = lane == 0 ? run : Op::apply(run, excl);
+        run = Op::apply(run, rtot);
+    }
+    if (lane == 0) s_warp[warp] = run;  // warp aggregate
+    __syncthreads();
+
+    // ---- warp 0: scan of warp aggregates + decoupled look-back
+    if (warp == 0) {
+        A wagg = lane < SC_WARPS ? s_warp[lane] : Op::identity();
+        A wincl = wagg;
+#pragma unroll
+        for (int d = 1; d < SC_WARPS; d <<= 1) {
+            A up = shfl_up_any(wincl, d);
+            if (lane >= d) wincl = Op::apply(up, wincl);
+        }
+        const A tile_agg = shfl_idx_any(wincl, SC_WARPS - 1);
+        A wexcl = shfl_up_any(wincl, 1);
+        if (lane == 0) wexcl = Op::identity();
+
+        const A prefix = tile_lookback<Op>(p, seg, t, lane, tile_agg);
+        if (lane == 0) s_tile_prefix = prefix;
+        if (lane < SC_WARPS) s_warp[lane] = wexcl;
+    }
+    __syncthreads();
+    const A base = Op::apply(s_tile_prefix, s_warp[warp]);
+
+    // ---- apply prefixes and store
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const A pre = Op::apply(base, cpre[k]);
+        A o[EPC];
+        if (!p.exclusive) {
+#pragma unroll
+            for (int e = 0; e < EPC; ++e) o[e] = Op::apply(pre, v[k][e]);
+        } else {
+            o[0] = pre;
+#pragma unroll
+            for (int e = 1; e < EPC; ++e) o[e] = Op::apply(pre, v[k][e - 1]);
+        }
+        store_chunk<Tout, A, EPC>(tout, (int64_t)warp * WARP_ELEMS + (k * 32 + lane) * EPC, valid, o);
+    }
+}
+
+
+// ------------------------------------------------------------------ TMA tile kernel
+// Same tiling, but the tile travels global -> shared -> global through the TMA unit
+// (cp.async.bulk, SASS UBLKCP): the bulk data never enters the SM's LSU / L1TEX
+// queue, so the look-back's status-word loads see plain L2 latency instead of
+// queueing behind ~100 KB of streaming loads per SM (measured: ~2 us per status
+// round trip when the data moves through LDG, which capped the scan at 2.5 TB/s).
+// Registers only hold the K chunk sums between the two passes over shared memory.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <class T, int N> __device__ __forceinline__ void lds_chunk(const T *sm, T (&e)[N]) {
+    if constexpr (N * sizeof(T) == 16) {
+        Vec16 raw = *reinterpret_cast<const Vec16 *>(sm);
+        memcpy(e, &raw, 16);
+    } else if constexpr (N * sizeof(T) == 32) {
+        Vec16 raw[2];
+        raw[0] = *reinterpret_cast<const Vec16 *>(sm);
+        raw[1] = *(reinterpret_cast<const Vec16 *>(sm) + 1);
+        memcpy(e, raw, 32);
+    } else if constexpr (N * sizeof(T) == 8) {
+        uint64_t raw = *reinterpret_cast<const uint64_t *>(sm);
+        memcpy(e, &raw, 8);
+    } else if constexpr (N * sizeof(T) == 4) {
+        uint32_t raw = *reinterpret_cast<const uint32_t *>(sm);
+        memcpy(e, &raw, 4);
+    } else if constexpr (N * sizeof(T) == 2) {
+        uint16_t raw = *reinterpret_cast<const uint16_t *>(sm);
+        memcpy(e, &raw, 2);
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) e[k] = sm[k];
+    }
+}
+template <class T, int N> __device__ __forceinline__ void sts_chunk(T *sm, const T (&e)[N]) {
+    if constexpr (N * sizeof(T) == 16) {
+        Vec16 raw; memcpy(&raw, e, 16);
+        *reinterpret_cast<Vec16 *>(sm) = raw;
+    } else if constexpr (N * sizeof(T) == 32) {
+        Vec16 raw[2]; memcpy(raw, e, 32);
+        *reinterpret_cast<Vec16 *>(sm) = raw[0];
+        *(reinterpret_cast<Vec16 *>(sm) + 1) = raw[1];
+    } else if constexpr (N * sizeof(T) == 8) {
+        uint64_t raw; memcpy(&raw, e, 8);
+        *reinterpret_cast<uint64_t *>(sm) = raw;
+    } else if constexpr (N * sizeof(T) == 4) {
+        uint32_t raw; memcpy(&raw, e, 4);
+        *reinterpret_cast<uint32_t *>(sm) = raw;
+    } else if constexpr (N * sizeof(T) == 2) {
+        uint16_t raw; memcpy(&raw, e, 2);
+        *reinterpret_cast<uint16_t *>(sm) = raw;
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) sm[k] = e[k];
+    }
+}
+
+template <class Tin, class Tout, class Op, int EPC, int K>
+__global__ void __launch_bounds__(SC_THREADS) scan_tma_kernel(ScanParams p) {
+    using A = typename Op::acc_t;
+    constexpr int WARP_ELEMS = 32 * EPC * K;
+    constexpr int TILE = SC_WARPS * WARP_ELEMS;
+    constexpr bool IN_PLACE = sizeof(Tin) == sizeof(Tout);
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    Tin *s_in = reinterpret_cast<Tin *>(s_dyn);
+    Tout *s_out = IN_PLACE ? reinterpret_cast<Tout *>(s_dyn) : reinterpret_cast<Tout *>(s_dyn + TILE * sizeof(Tin));
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ A s_warp[SC_WARPS];
+    __shared__ A s_tile_prefix;
+    __shared__ unsigned long long s_ticket;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t g = 0, seg = 0, t = 0, valid = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        fence_proxy_async_smem();
+        g = (int64_t)atomicAdd(p.ticket, 1ull);
+        s_ticket = (unsigned long long)g;
+        seg = g / p.tiles_per_seg;
+        t = g - seg * p.tiles_per_seg;
+        valid = p.n - t * TILE;
+        if (valid >= TILE) {
+            // full tile: one bulk copy, completion counted in bytes on the mbarrier
+            mbar_expect_tx(&s_bar, TILE * sizeof(Tin));
+            tma_load_1d(s_in, static_cast<const Tin *>(p.in) + seg * p.n + t * TILE, TILE * sizeof(Tin), &s_bar);
+        }
+    }
+    __syncthreads();
+    g = (int64_t)s_ticket;
+    seg = g / p.tiles_per_seg;
+    t = g - seg * p.tiles_per_seg;
+    const int64_t tile_off = seg * p.n + t * TILE;
+    valid = p.n - t * TILE;
+    const bool full = valid >= TILE;
+    if (valid > TILE) valid = TILE;
+    const Tin *tin = static_cast<const Tin *>(p.in) + tile_off;
+    Tout *tout = static_cast<Tout *>(p.out) + tile_off;
+    const int64_t wbase = (int64_t)warp * WARP_ELEMS;
+
+    // ---- pass 1: chunk sums (from shared memory for full tiles, from global for the ragged tail)
+    A csum[K];
+    if (full) {
+        mbar_wait(&s_bar, 0);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            Tin e[EPC];
+            lds_chunk<Tin, EPC>(s_in + wbase + (k * 32 + lane) * EPC, e);
+            A acc = cvt<A>(e[0]);
+#pragma unroll
+            for (int q = 1; q < EPC; ++q) acc = Op::apply(acc, cvt<A>(e[q]));
+            csum[k] = acc;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            A v[EPC];
+            load_chunk<Tin, A, Op, EPC>(tin, wbase + (k * 32 + lane) * EPC, valid, v);
+            Tin e[EPC];
+            A acc = v[0];
+            e[0] = cvt<Tin>(v[0]);
+#pragma unroll
+            for (int q = 1; q < EPC; ++q) { acc = Op::apply(acc, v[q]); e[q] = cvt<Tin>(v[q]); }
+            csum[k] = acc;
+            sts_chunk<Tin, EPC>(s_in + wbase + (k * 32 + lane) * EPC, e);   // own chunk only: no sync needed
+        }
+    }
+    // ---- K interleaved warp scans over the chunk sums
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            A up = shfl_up_any(csum[k], d);
+            if (lane >= d) csum[k] = Op::apply(up, csum[k]);
+        }
+    }
+    A cpre[K];
+    A run = Op::identity();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        A excl = shfl_up_any(csum[k], 1);
+        A rtot = shfl_idx_any(csum[k], 31);
+        cpre[k] = lane == 0 ? run : Op::apply(run, excl);
+        run = Op::apply(run, rtot);
+    }
+    if (lane == 0) s_warp[warp] = run;
+    __syncthreads();
+
+    if (warp == 0) {
+        A wagg = lane < SC_WARPS ? s_warp[lane] : Op::identity();
+        A wincl = wagg;
+#pragma unroll
+        for (int d = 1; d < SC_WARPS; d <<= 1) {
+            A up = shfl_up_any(wincl, d);
+            if (lane >= d) wincl = Op::apply(up, wincl);
+        }
+        const A tile_agg = shfl_idx_any(wincl, SC_WARPS - 1);
+        A wexcl = shfl_up_any(wincl, 1);
+        if (lane == 0) wexcl = Op::identity();
+        const A prefix = tile_lookback<Op>(p, seg, t, lane, tile_agg);
+        if (lane == 0) s_tile_prefix = prefix;
+        if (lane < SC_WARPS) s_warp[lane] = wexcl;
+    }
+    __syncthreads();
+    const A base = Op::apply(s_tile_prefix, s_warp[warp]);
+
+    // ---- pass 2: re-read the chunk, apply the prefix, write the result back to shared memory
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        Tin e[EPC];
+        lds_chunk<Tin, EPC>(s_in + wbase + (k * 32 + lane) * EPC, e);
+        A run2 = Op::apply(base, cpre[k]);
+        Tout o[EPC];
+#pragma unroll
+        for (int q = 0; q < EPC; ++q) {
+            const A nxt = Op::apply(run2, cvt<A>(e[q]));
+            o[q] = cvt<Tout>(p.exclusive ? run2 : nxt);
+            run2 = nxt;
+        }
+        if (full) {
+            sts_chunk<Tout, EPC>(s_out + wbase + (k * 32 + lane) * EPC, o);
+        } else {
+            const int64_t off = wbase + (k * 32 + lane) * EPC;
+#pragma unroll
+            for (int q = 0; q < EPC; ++q)
+                if (off + q < valid) tout[off + q] = o[q];
+        }
+    }
+    if (full) {
+        fence_proxy_async_smem();      // make this thread's shared-memory writes visible to the TMA unit
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tma_store_1d(tout, s_out, TILE * sizeof(Tout));
+            tma_store_wait_read();      // shared memory must outlive the bulk read
+        }
+    }
+}
+
+// One thread per (i, j) column, marching along n.
+template <class Tin, class Tout, class Op>
+__global__ void __launch_bounds__(256) scan_strided_kernel(ScanParams p) {
+    using A = typename Op::acc_t;
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= p.pre * p.post) return;
+    const int64_t j = o / p.pre, i = o - j * p.pre;
+    const Tin *in = static_cast<const Tin *>(p.in) + i + p.pre * p.n * j;
+    Tout *out = static_cast<Tout *>(p.out) + i + p.pre * p.n * j;
+    A acc = p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity();
+    constexpr int U = 8;
+    int64_t r = 0;
+    for (; r + U <= p.n; r += U) {
+        Tin x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) x[u] = ld_coh(in + p.pre * (r + u));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const A nxt = Op::apply(acc, cvt<A>(x[u]));
+            out[p.pre * (r + u)] = cvt<Tout>(p.exclusive ? acc : nxt);
+            acc = nxt;
+        }
+    }
+    for (; r < p.n; ++r) {
+        const A nxt = Op::apply(acc, cvt<A>(ld_coh(in + p.pre * r)));
+        out[p.pre * r] = cvt<Tout>(p.exclusive ? acc : nxt);
+        acc = nxt;
+    }
+}
+
+// ------------------------------------------------------------------ host
+template <class Tin, class Tout> struct ScanShape {
+    static constexpr int WIDE = sizeof(Tin) > sizeof(Tout) ? sizeof(Tin) : sizeof(Tout);
+    static constexpr int EPC = 16 / WIDE;                       // elements per 16-byte chunk of the wider type
+    static constexpr int K = 8;
+    static constexpr int TILE_VEC = SC_THREADS * EPC * K;
+    static constexpr int K1 = 8;                                // scalar-chunk fallback
+    static constexpr int TILE_SCALAR = SC_THREADS * K1;
+};
+
+template <class Tin, class Tout, class Op>
+int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_t pre, int64_t n, int64_t post,
+                    int exclusive, const void *init_host, cudaStream_t stream, size_t *query_bytes) {
+    using A = typename Op::acc_t;
+    using S = ScanShape<Tin, Tout>;
+    constexpr int NW = StatusWords<A>::NW;
+    ScanParams p{};
+    p.in = in; p.out = out; p.pre = pre; p.n = n; p.post = post; p.exclusive = exclusive;
+    p.has_init = init_host != nullptr;
+    if (init_host) {
+        // init arrives as a value of the OUTPUT element type; convert to the accumulator
+        Tout iv;
+        memcpy(&iv, init_host, sizeof(Tout));
+        A a = cvt<A>(iv);
+        memcpy(&p.init_bits, &a, sizeof(A));
+    }
+    if (pre > 1) {
+        if (query_bytes) { *query_bytes = 0; return B200_OK; }
+        const int64_t cols = pre * post;
+        const int64_t grid = cdiv(cols, 256);
+        if (grid > 2147483647LL) return B200_INVALID_VALUE;
+        scan_strided_kernel<Tin, Tout, Op><<<(unsigned int)grid, 256, 0, stream>>>(p);
+        B200_CHECK_LAUNCH();
+        return B200_OK;
+    }
+    // contig: vector chunks need both pointers 16-byte-chunk aligned and, with several
+    // segments, every segment start aligned too
+    const bool query = query_bytes != nullptr;
+    const bool seg_ok = post == 1 || (n % S::EPC == 0);
+    const bool aligned = query || ((reinterpret_cast<uintptr_t>(in) % (S::EPC * sizeof(Tin))) == 0 &&
+                                   (reinterpret_cast<uintptr_t>(out) % (S::EPC * sizeof(Tout))) == 0);
+    const bool vec = seg_ok && aligned && S::EPC > 1;
+    // workspace is sized for the scalar tiling (smaller tiles => more status words) so that
+    // the query does not depend on pointer alignment
+    const int64_t tps_max = cdiv(n, (int64_t)(S::TILE_SCALAR < S::TILE_VEC ? S::TILE_SCALAR : S::TILE_VEC));
+    Carver c(ws);
+    unsigned long long *ticket = c.take<unsigned long long>(1);
+    uint64_t *status = c.take<uint64_t>((size_t)(post * tps_max * NW));
+    if (query) { *query_bytes = c.bytes(); return B200_OK; }
+    if (c.bytes() > ws_bytes) return B200_WORKSPACE_TOO_SMALL;
+    if (ws == nullptr) return B200_INVALID_VALUE;
+    const int64_t tile = vec ? S::TILE_VEC : S::TILE_SCALAR;
+    p.tiles_per_seg = cdiv(n, tile);
+    p.status = status; p.ticket = ticket;
+    const int64_t grid = p.tiles_per_seg * post;
+    if (grid > 2147483647LL) return B200_INVALID_VALUE;
+    // one memset node clears the ticket and every status word (ticket and status are adjacent)
+    const size_t clear = (size_t)((char *)(status + post * p.tiles_per_seg * NW) - (char *)ticket);
+    B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, clear, stream));
+    if (vec) {
+        constexpr size_t smem = (size_t)S::TILE_VEC * (sizeof(Tin) == sizeof(Tout) ? sizeof(Tin) : sizeof(Tin) + sizeof(Tout));
+        auto kern = scan_tma_kernel<Tin, Tout, Op, S::EPC, S::K>;
+        static thread_local int attr_dev_mask[64];  // cudaFuncSetAttribute once per (thread, device, instantiation)
+        int dev = 0;
+        B200_CUDA_TRY(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && !attr_dev_mask[dev]) {
+            B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_dev_mask[dev] = 1;
+        }
+        kern<<<(unsigned int)grid, SC_THREADS, smem, stream>>>(p);
+    }
+    else scan_contig_kernel<Tin, Tout, Op, 1, S::K1><<<(unsigned int)grid, SC_THREADS, 0, stream>>>(p);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
+}  // namespace b200
