@@ -12,6 +12,7 @@ from .mapreduce import (identity, abs2, add_sum, mul_prod, add, mul, max_, min_,
                         neutral_element, mapreducedim_, mapreduce, reduce, sum, prod, maximum, minimum,
                         extrema, count, any, all, sum_, prod_, maximum_, minimum_)
 from .accumulate import scan_, accumulate_, accumulate, cumsum, cumprod, cumsum_, cumprod_
+from .sorting import (isless, BitonicSort, QuickSort, sort_, sort, partialsort_, partialsort, sortperm_, sortperm)
 from . import _lib
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,332 @@
+// sort.cuh — onesweep LSD radix sort (8-bit digits) for sm_100a.
+//
+// Replaces the bitonic network of CUDACore/src/sorting.jl:525-975 (~240 full-array
+// passes for 2^30 keys) with: one histogram pass over the keys, then
+// one kernel per key byte in which every tile ranks its keys, publishes its digit
+// counts, resolves its global offsets by decoupled look-back over the preceding
+// tiles' counts, and scatters through shared memory so that global writes are
+// contiguous per digit run.  Stable, so sortperm ties keep ascending index
+// (sorting.jl:582-592) and `rev` is a key complement.
+//
+// Keys are mapped to unsigned integers whose order is Julia's `isless`
+// (float sign twiddle, NaNs last; signed: sign-bit flip) when they are first
+// read and mapped back when they are last written.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int RX_THREADS = 256;
+constexpr int RX_WARPS = RX_THREADS / 32;
+constexpr int RX_RADIX = 256;
+constexpr int RX_LOOK = 4;   // predecessor tiles inspected per look-back round trip
+
+template <int KB> struct KeyOf;
+template <> struct KeyOf<1> { using type = uint8_t; };
+template <> struct KeyOf<2> { using type = uint16_t; };
+template <> struct KeyOf<4> { using type = uint32_t; };
+template <> struct KeyOf<8> { using type = uint64_t; };
+
+struct NoPayload {};
+
+enum { RX_KIND_UNSIGNED = 0, RX_KIND_SIGNED = 1, RX_KIND_FLOAT = 2 };
+
+struct SortXform {
+    int32_t kind;
+    int32_t descending;
+    int32_t nan_canonical;   // 1: every NaN maps to one key (sortperm ties by index, like isless)
+    uint64_t sign_bit;
+    uint64_t inf_bits;       // exponent mask of the float format
+};
+
+template <class K> __device__ __forceinline__ K key_encode(K bits, const SortXform &x) {
+    const K sign = (K)x.sign_bit;
+    K key;
+    if (x.kind == RX_KIND_FLOAT) {
+        const K mag = bits & (K)~sign;
+        if (mag > (K)x.inf_bits) {
+            // NaN: after every finite value and +Inf.  sort! keeps the payload (sign dropped),
+            // sortperm makes all NaNs equal.
+            key = x.nan_canonical ? (K)~(K)0 : (K)(mag | sign);
+        } else {
+            key = (bits & sign) ? (K)~bits : (K)(bits | sign);
+        }
+    } else if (x.kind == RX_KIND_SIGNED) {
+        key = bits ^ sign;
+    } else {
+        key = bits;
+    }
+    return x.descending ? (K)~key : key;
+}
+
+template <class K> __device__ __forceinline__ K key_decode(K key, const SortXform &x) {
+    const K sign = (K)x.sign_bit;
+    if (x.descending) key = (K)~key;
+    if (x.kind == RX_KIND_FLOAT) return (key & sign) ? (K)(key ^ sign) : (K)~key;
+    if (x.kind == RX_KIND_SIGNED) return key ^ sign;
+    return key;
+}
+
+// ------------------------------------------------------------------ histogram of every digit
+// One read of the keys builds all sizeof(K) digit histograms (shared-memory atomics,
+// then one global atomic per (pass, bin) per CTA).
+template <class K>
+__global__ void __launch_bounds__(512) radix_hist_kernel(const K *__restrict__ keys, int64_t n, SortXform xf,
+                                                         unsigned long long *__restrict__ ghist) {
+    constexpr int P = (int)sizeof(K);
+    constexpr int VN = 16 / (int)sizeof(K);
+    __shared__ unsigned int sh[P * RX_RADIX];
+    for (int i = threadIdx.x; i < P * RX_RADIX; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const bool aligned = (reinterpret_cast<uintptr_t>(keys) % 16) == 0;
+    const int64_t nvec = aligned ? n / VN : 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    auto count = [&](K raw) {
+        const K key = key_encode<K>(raw, xf);
+#pragma unroll
+        for (int p = 0; p < P; ++p) atomicAdd(&sh[p * RX_RADIX + (int)((key >> (8 * p)) & 0xFF)], 1u);
+    };
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        Vec16 raw = ldg_stream16(reinterpret_cast<const char *>(keys) + v * 16);
+        K e[VN];
+        memcpy(e, &raw, 16);
+#pragma unroll
+        for (int k = 0; k < VN; ++k) count(e[k]);
+    }
+    for (int64_t i = nvec * VN + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) count(keys[i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < P * RX_RADIX; i += blockDim.x)
+        if (sh[i]) atomicAdd(ghist + i, (unsigned long long)sh[i]);
+}
+
+// Exclusive scan of each pass's 256-bin histogram: bins[p][d] = first output index of digit d.
+static __global__ void __launch_bounds__(RX_RADIX) radix_bins_kernel(const unsigned long long *__restrict__ ghist,
+                                                              unsigned long long *__restrict__ bins) {
+    __shared__ unsigned long long s[RX_RADIX];
+    const int d = threadIdx.x;
+    const unsigned long long c = ghist[blockIdx.x * RX_RADIX + d];
+    s[d] = c;
+    __syncthreads();
+    for (int o = 1; o < RX_RADIX; o <<= 1) {
+        unsigned long long v = d >= o ? s[d - o] : 0ull;
+        __syncthreads();
+        s[d] += v;
+        __syncthreads();
+    }
+    bins[blockIdx.x * RX_RADIX + d] = s[d] - c;
+}
+
+// ------------------------------------------------------------------ onesweep pass
+struct OnesweepParams {
+    const void *keys_in;
+    void *keys_out;
+    const void *vals_in;
+    void *vals_out;
+    int64_t n;
+    int32_t shift;
+    const unsigned long long *bins;   // [256] for this pass
+    void *status;                     // LookT[tiles][256]
+    unsigned long long *ticket;
+    SortXform xf;
+    int32_t encode_in;                // first pass: map raw keys to ordered unsigned keys
+    int32_t decode_out;               // last pass: map back
+    int32_t store_keys;               // 0 on sortperm's last pass
+    int32_t gen_payload;              // first sortperm pass: payload = element index
+    int32_t index_dtype;              // last sortperm pass: store index_base + payload as this dtype; -1: raw payload
+    int64_t index_base;               // 1 for per-segment 1-based indices (+ segment offset when linear)
+};
+
+template <class LookT> struct LookBits;
+template <> struct LookBits<uint32_t> {
+    static constexpr uint32_t PARTIAL = 1u << 30, INCLUSIVE = 2u << 30, MASK = (1u << 30) - 1, FLAGS = 3u << 30;
+};
+template <> struct LookBits<uint64_t> {
+    static constexpr uint64_t PARTIAL = 1ull << 62, INCLUSIVE = 2ull << 62, MASK = (1ull << 62) - 1, FLAGS = 3ull << 62;
+};
+
+template <class LookT> __device__ __forceinline__ LookT ld_relaxed(const LookT *p) {
+    LookT v;
+    if constexpr (sizeof(LookT) == 4) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    else asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+template <class LookT> __device__ __forceinline__ void st_relaxed(LookT *p, LookT v) {
+    if constexpr (sizeof(LookT) == 4) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+    else asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+template <class V> struct PayTraits { static constexpr bool HAS = true; using type = V; };
+template <> struct PayTraits<NoPayload> { static constexpr bool HAS = false; using type = uint32_t; };
+
+template <class K, class V, class LookT, int ITEMS>
+__global__ void __launch_bounds__(RX_THREADS) radix_onesweep_kernel(OnesweepParams p) {
+    using LB = LookBits<LookT>;
+    constexpr bool HAS_V = PayTraits<V>::HAS;
+    using VT = typename PayTraits<V>::type;
+    constexpr int TILE = RX_THREADS * ITEMS;
+    constexpr int WARP_ITEMS = 32 * ITEMS;
+
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    // layout: [warp hist 8*256 u32][digit offset 256 u32][global base 256 i64][keys TILE][vals TILE]
+    unsigned int *s_whist = reinterpret_cast<unsigned int *>(s_raw);
+    unsigned int *s_doff = s_whist + RX_WARPS * RX_RADIX;
+    long long *s_gbase = reinterpret_cast<long long *>(s_doff + RX_RADIX);
+    K *s_keys = reinterpret_cast<K *>(s_gbase + RX_RADIX);
+    VT *s_vals = reinterpret_cast<VT *>(reinterpret_cast<unsigned char *>(s_keys) + ((TILE * sizeof(K) + 15) / 16) * 16);
+    __shared__ unsigned long long s_ticket;
+    __shared__ unsigned int s_wsum[RX_WARPS];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_ticket = atomicAdd(p.ticket, 1ull);
+    // zero this warp's digit counters while the ticket is in flight
+    unsigned int *whist = s_whist + warp * RX_RADIX;
+#pragma unroll
+    for (int k = 0; k < RX_RADIX / 32; ++k) whist[k * 32 + lane] = 0;
+    __syncthreads();
+    const int64_t t = (int64_t)s_ticket;
+    const int64_t tile_base = t * TILE;
+    int64_t valid = p.n - tile_base;
+    if (valid > TILE) valid = TILE;
+
+    // ---- load keys, warp-striped: item i of lane l is element warp*WARP_ITEMS + i*32 + l
+    const K *kin = static_cast<const K *>(p.keys_in) + tile_base;
+    K keys[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int idx = warp * WARP_ITEMS + i * 32 + lane;
+        keys[i] = idx < valid ? ldg_stream(kin + idx) : (K)0;
+    }
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int idx = warp * WARP_ITEMS + i * 32 + lane;
+        if (p.encode_in) keys[i] = key_encode<K>(keys[i], p.xf);
+        if (idx >= valid) keys[i] = (K)~(K)0;   // padding ranks last inside digit 255
+    }
+
+    // ---- rank inside the warp: stable by (item, lane) = element order
+    unsigned short ranks[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const unsigned int digit = (unsigned int)((keys[i] >> p.shift) & 0xFF);
+        const unsigned int peers = __match_any_sync(0xffffffffu, digit);
+        const int leader = __ffs(peers) - 1;
+        const unsigned int below = __popc(peers & ((1u << lane) - 1u));
+        unsigned int old = 0;
+        if (lane == leader) {
+            old = whist[digit];
+            whist[digit] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        ranks[i] = (unsigned short)(old + below);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per digit (thread d): offsets of each warp inside the digit run, tile count
+    const int d = tid;
+    unsigned int tile_count = 0;
+#pragma unroll
+    for (int w = 0; w < RX_WARPS; ++w) {
+        const unsigned int c = s_whist[w * RX_RADIX + d];
+        s_whist[w * RX_RADIX + d] = tile_count;
+        tile_count += c;
+    }
+    const unsigned int pad = (unsigned int)(TILE - valid);
+    const unsigned int real_count = (d == RX_RADIX - 1) ? tile_count - pad : tile_count;
+    LookT *status = static_cast<LookT *>(p.status);
+    // publish as early as possible: tile 0 knows its inclusive prefix already
+    st_relaxed<LookT>(status + t * RX_RADIX + d, (LookT)((t > 0 ? LB::PARTIAL : LB::INCLUSIVE) | (LookT)real_count));
+
+    // exclusive scan of tile_count over the 256 digits -> start of each digit run in shared memory
+    unsigned int incl = tile_count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    unsigned int wbase = 0;
+#pragma unroll
+    for (int w = 0; w < RX_WARPS; ++w) wbase += (w < warp) ? s_wsum[w] : 0u;
+    const unsigned int doff = wbase + incl - tile_count;
+    s_doff[d] = doff;
+    __syncthreads();
+
+    // ---- scatter keys (and payload) into shared memory, sorted by digit
+    VT vals[HAS_V ? ITEMS : 1];
+    if constexpr (HAS_V) {
+        const VT *vin = static_cast<const VT *>(p.vals_in) + tile_base;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const int idx = warp * WARP_ITEMS + i * 32 + lane;
+            if (p.gen_payload) vals[i] = (VT)(tile_base + idx);
+            else vals[i] = idx < valid ? ldg_stream(vin + idx) : (VT)0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const unsigned int digit = (unsigned int)((keys[i] >> p.shift) & 0xFF);
+        const unsigned int pos = s_doff[digit] + whist[digit] + ranks[i];
+        s_keys[pos] = keys[i];
+        if constexpr (HAS_V) s_vals[pos] = vals[i];
+    }
+
+    // ---- decoupled look-back for digit d
+    unsigned long long excl = 0;
+    if (t > 0) {
+        int64_t u = t - 1;
+        bool done = false;
+        while (!done) {
+            LookT w[RX_LOOK];
+            bool all_valid;
+            do {
+                all_valid = true;
+#pragma unroll
+                for (int k = 0; k < RX_LOOK; ++k) {
+                    w[k] = LB::INCLUSIVE;   // virtual tiles before the first one: inclusive, zero
+                    if (u - k >= 0) w[k] = ld_relaxed<LookT>(status + (u - k) * RX_RADIX + d);
+                    all_valid = all_valid && ((w[k] & LB::FLAGS) != 0);
+                }
+            } while (!all_valid);
+#pragma unroll
+            for (int k = 0; k < RX_LOOK; ++k) {
+                if (!done) {
+                    excl += (unsigned long long)(w[k] & LB::MASK);
+                    done = (w[k] & LB::FLAGS) == LB::INCLUSIVE;
+                }
+            }
+            u -= RX_LOOK;
+        }
+        st_relaxed<LookT>(status + t * RX_RADIX + d, (LookT)(LB::INCLUSIVE | (LookT)(excl + real_count)));
+    }
+    s_gbase[d] = (long long)(p.bins[d] + excl) - (long long)doff;
+    __syncthreads();
+
+    // ---- write out: consecutive threads -> consecutive addresses inside each digit run
+    K *kout = static_cast<K *>(p.keys_out);
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const int i = tid + k * RX_THREADS;
+        if (i < valid) {
+            const K key = s_keys[i];
+            const unsigned int digit = (unsigned int)((key >> p.shift) & 0xFF);
+            const long long dst = s_gbase[digit] + i;
+            if (p.store_keys) kout[dst] = p.decode_out ? key_decode<K>(key, p.xf) : key;
+            if constexpr (HAS_V) {
+                const VT v = s_vals[i];
+                if (p.index_dtype < 0) {
+                    static_cast<VT *>(p.vals_out)[dst] = v;
+                } else {
+                    const long long ix = (long long)v + p.index_base;
+                    switch (p.index_dtype) {
+                        case B200_I64: case B200_U64: static_cast<long long *>(p.vals_out)[dst] = ix; break;
+                        default: static_cast<int *>(p.vals_out)[dst] = (int)ix; break;
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace b200

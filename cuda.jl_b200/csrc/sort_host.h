@@ -1,0 +1,30 @@
+// sort_host.h — host-side call descriptor shared by api_sort.cu and the per-key-width units.
+#pragma once
+#include "common.cuh"
+#include "sort.cuh"
+
+namespace b200 {
+
+enum SortMode { SORT_KEYS = 0, SORT_PERM = 1, SORT_PAIRS = 2 };
+
+struct SortCall {
+    void *ws;
+    size_t ws_bytes;
+    void *keys;            // KEYS/PAIRS: sorted in place; PERM: read only
+    void *payload;         // PERM: output permutation; PAIRS: permuted in place
+    int mode;
+    int payload_bytes;     // PAIRS: 4 or 8
+    int index_dtype;       // PERM: B200_I32/I64/U32/U64
+    int64_t index_base;    // PERM: added to the 0-based element index
+    int64_t n;
+    SortXform xf;
+    cudaStream_t stream;
+    size_t *query;         // non-null: only compute the workspace size
+};
+
+int32_t sort_run_k1(const SortCall &);
+int32_t sort_run_k2(const SortCall &);
+int32_t sort_run_k4(const SortCall &);
+int32_t sort_run_k8(const SortCall &);
+
+}  // namespace b200

@@ -1,0 +1,127 @@
+// sort_inst.cu — one translation unit per key width (-DB200_KEY_BYTES=1|2|4|8).
+// Host orchestration of the onesweep passes for keys / sortperm / pairs.
+#include "sort.cuh"
+#include "sort_host.h"
+
+namespace b200 {
+
+using K = KeyOf<B200_KEY_BYTES>::type;
+constexpr int P = B200_KEY_BYTES;                       // 8-bit digits: one pass per key byte
+constexpr int ITEMS = B200_KEY_BYTES == 8 ? 12 : 16;
+constexpr int TILE = RX_THREADS * ITEMS;
+
+template <class V> static size_t onesweep_smem() {
+    using VT = typename PayTraits<V>::type;
+    size_t s = (size_t)RX_WARPS * RX_RADIX * 4 + RX_RADIX * 4 + RX_RADIX * 8 + ((size_t)TILE * sizeof(K) + 15) / 16 * 16;
+    if (PayTraits<V>::HAS) s += (size_t)TILE * sizeof(VT);
+    return s;
+}
+
+template <class V, class LookT> static int32_t launch_pass(const OnesweepParams &p, int64_t tiles, cudaStream_t st) {
+    auto kern = radix_onesweep_kernel<K, V, LookT, ITEMS>;
+    const size_t smem = onesweep_smem<V>();
+    static thread_local bool attr_set[64];
+    int dev = 0;
+    B200_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[dev] = true;
+    }
+    kern<<<(unsigned int)tiles, RX_THREADS, smem, st>>>(p);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
+template <class LookT> static int32_t dispatch_pass(const OnesweepParams &p, int pay_bytes, int64_t tiles, cudaStream_t st) {
+    if (pay_bytes == 0) return launch_pass<NoPayload, LookT>(p, tiles, st);
+    if (pay_bytes == 4) return launch_pass<uint32_t, LookT>(p, tiles, st);
+    return launch_pass<uint64_t, LookT>(p, tiles, st);
+}
+
+#define B200_CAT2(a, b) a##b
+#define B200_CAT(a, b) B200_CAT2(a, b)
+
+int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
+    const int64_t n = c.n;
+    const int64_t tiles = cdiv(n, TILE);
+    const bool wide = n >= (1LL << 30);                    // 30-bit counts no longer hold every prefix
+    const size_t look_bytes = wide ? 8 : 4;
+    // payload width carried through the passes
+    int pay = 0;
+    if (c.mode == SORT_PERM) pay = n > 0xFFFFFFFFLL ? 8 : 4;
+    else if (c.mode == SORT_PAIRS) pay = c.payload_bytes;
+
+    Carver w(c.ws);
+    unsigned long long *ghist = w.take<unsigned long long>(P * RX_RADIX);
+    unsigned long long *bins = w.take<unsigned long long>(P * RX_RADIX);
+    unsigned long long *ticket = w.take<unsigned long long>(1);
+    char *status = w.take<char>((size_t)tiles * RX_RADIX * look_bytes);
+    char *kbuf0 = w.take<char>((size_t)n * sizeof(K));
+    char *kbuf1 = c.mode == SORT_PERM ? w.take<char>((size_t)n * sizeof(K)) : nullptr;
+    char *vbuf0 = pay ? w.take<char>((size_t)n * pay) : nullptr;
+    char *vbuf1 = c.mode == SORT_PERM ? w.take<char>((size_t)n * pay) : nullptr;
+    if (c.query) { *c.query = w.bytes(); return B200_OK; }
+    if (w.bytes() > c.ws_bytes) return B200_WORKSPACE_TOO_SMALL;
+    if (c.ws == nullptr) return B200_INVALID_VALUE;
+    if (tiles > 2147483647LL) return B200_INVALID_VALUE;
+    cudaStream_t st = c.stream;
+
+    // ---- digit histograms of all passes in one read, then their exclusive scans
+    B200_CUDA_TRY(cudaMemsetAsync(ghist, 0, (size_t)P * RX_RADIX * sizeof(unsigned long long), st));
+    {
+        const DevInfo &dev = devinfo();
+        int64_t grid = (int64_t)dev.sm_count * 4;
+        const int64_t need = cdiv(n, 512 * (16 / (int64_t)sizeof(K)));
+        if (grid > need) grid = need;
+        if (grid < 1) grid = 1;
+        radix_hist_kernel<K><<<(unsigned int)grid, 512, 0, st>>>(static_cast<const K *>(c.keys), n, c.xf, ghist);
+        B200_CHECK_LAUNCH();
+        radix_bins_kernel<<<P, RX_RADIX, 0, st>>>(ghist, bins);
+        B200_CHECK_LAUNCH();
+    }
+
+    const size_t clear = (size_t)((status + (size_t)tiles * RX_RADIX * look_bytes) - reinterpret_cast<char *>(ticket));
+    for (int pass = 0; pass < P; ++pass) {
+        OnesweepParams p{};
+        p.n = n;
+        p.shift = 8 * pass;
+        p.bins = bins + pass * RX_RADIX;
+        p.status = status;
+        p.ticket = ticket;
+        p.xf = c.xf;
+        p.encode_in = pass == 0;
+        p.decode_out = (pass == P - 1) && c.mode != SORT_PERM;
+        p.store_keys = !(pass == P - 1 && c.mode == SORT_PERM);
+        p.gen_payload = (pass == 0 && c.mode == SORT_PERM);
+        p.index_dtype = (pass == P - 1 && c.mode == SORT_PERM) ? c.index_dtype : -1;
+        p.index_base = c.index_base;
+        if (c.mode == SORT_PERM) {
+            char *kb[2] = {kbuf0, kbuf1};
+            char *vb[2] = {vbuf0, vbuf1};
+            p.keys_in = pass == 0 ? c.keys : kb[(pass - 1) & 1];
+            p.keys_out = kb[pass & 1];
+            p.vals_in = pass == 0 ? nullptr : vb[(pass - 1) & 1];
+            p.vals_out = pass == P - 1 ? c.payload : vb[pass & 1];
+        } else {
+            // ping-pong between the caller's buffer and the workspace copy
+            const bool from_user = (pass & 1) == 0;
+            p.keys_in = from_user ? c.keys : kbuf0;
+            p.keys_out = from_user ? kbuf0 : c.keys;
+            if (pay) {
+                p.vals_in = from_user ? c.payload : vbuf0;
+                p.vals_out = from_user ? vbuf0 : c.payload;
+            }
+        }
+        B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, clear, st));
+        int32_t rc = wide ? dispatch_pass<uint64_t>(p, pay, tiles, st) : dispatch_pass<uint32_t>(p, pay, tiles, st);
+        if (rc != B200_OK) return rc;
+    }
+    if (c.mode != SORT_PERM && (P & 1)) {
+        // odd number of passes: the result sits in the workspace copy
+        B200_CUDA_TRY(cudaMemcpyAsync(c.keys, kbuf0, (size_t)n * sizeof(K), cudaMemcpyDeviceToDevice, st));
+        if (pay) B200_CUDA_TRY(cudaMemcpyAsync(c.payload, vbuf0, (size_t)n * pay, cudaMemcpyDeviceToDevice, st));
+    }
+    return B200_OK;
+}
+
+}  // namespace b200

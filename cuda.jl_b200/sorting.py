@@ -1,0 +1,134 @@
+"""Host-side mirror of the Base hooks in CUDACore/src/sorting.jl:993-1070.
+
+`sort_` is `Base.sort!(c::AnyCuArray; alg, lt, by, rev, dims)`, `sortperm_` is
+`Base.sortperm!(ix, A; initialized, ...)`, etc.  Grafted for `lt=isless`, `by=identity`
+(kwargs do not dispatch, so each hook guards at run time); anything else
+raises NotGraftedError where Julia would `invoke` the reference's bitonic method.
+Device work: libb200arrays' onesweep radix sort (b200_sort_keys / b200_sortperm).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from . import dtypes as dt
+from .cuarray import CuArray, Workspace, current_stream_handle
+from .errors import ArgumentError, NotGraftedError
+from .mapreduce import identity
+
+
+class _Token:
+    def __init__(self, name):
+        self.name = name
+
+    def __repr__(self):
+        return self.name
+
+
+isless = _Token("isless")
+BitonicSort = _Token("CUDA.BitonicSort")      # sorting.jl:984-990: default alg token; the graft answers for it
+QuickSort = _Token("CUDA.QuickSort")          # not exercised on cc >= 9.0 (test/core/sorting.jl:256,282): not grafted
+SORTPERM_INDEX = 100
+
+
+def _guard(lt, by, alg):
+    if lt is not isless or by is not identity:
+        raise NotGraftedError("sort with a custom lt/by stays on the reference's bitonic kernels")
+    if alg is not BitonicSort:
+        raise NotGraftedError("alg=QuickSort stays on the reference path")
+
+
+def _segments(c, dims):
+    """(n, nseg) for sorting along `dims` when the segments are contiguous (dims == 1 or a vector)."""
+    if c.ndims <= 1:
+        if dims not in (None, 1):
+            raise ArgumentError("dimension out of range")
+        return c.length, 1
+    if dims is None:
+        raise NotGraftedError("sort! of a multidimensional array needs dims (Base raises UndefKeywordError)")
+    if dims != 1:
+        # segmented sorts along non-leading dims are "next"
+        raise NotGraftedError("sort along a non-leading dimension is not grafted yet")
+    n = c.dims[0]
+    return n, (c.length // n if n else 0)
+
+
+def sort_(c, alg=BitonicSort, lt=isless, by=identity, rev=False, dims=None):
+    """Base.sort!(c::AnyCuArray; alg=BitonicSort, lt, by, rev, dims) (sorting.jl:1003-1009)."""
+    _guard(lt, by, alg)
+    n, nseg = _segments(c, dims)
+    if n <= 1 or nseg == 0:
+        return c
+    lib = _lib.load()
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(lib.b200_sort_workspace_bytes(c.eltype, -1, n, nseg, ctypes.byref(nbytes)))
+    ws = Workspace(nbytes.value, c.buf.device)
+    _lib.check(lib.b200_sort_keys(ws.ptr, ws.nbytes, c.pointer, c.eltype, n, nseg, 1 if rev else 0,
+                                  current_stream_handle(c.buf.device)))
+    return c
+
+
+def sort(c, **kw):
+    """Base.sort(c::AnyCuArray; kw...) = sort!(copy(c); kw...) (sorting.jl:1011-1013)."""
+    return sort_(c.copy(), **kw)
+
+
+def _index_k(c, k):
+    """copy(c[k]) for a 1-based integer or range k."""
+    if isinstance(k, (int, np.integer)):
+        if not 1 <= k <= c.length:
+            raise IndexError(f"BoundsError: attempt to access {c.length}-element CuArray at index [{k}]")
+        sz = dt.SIZES[c.eltype]
+        return CuArray(c.buf[(k - 1) * sz:k * sz].clone(), (1,), c.eltype).to_host()[0]   # @allowscalar
+    k = range(k.start, k.stop, k.step or 1) if isinstance(k, slice) else k
+    if len(k) and (k.step != 1 or k[0] < 1 or k[-1] > c.length):
+        raise NotGraftedError("only unit-stride in-bounds ranges are grafted for partialsort")
+    sz = dt.SIZES[c.eltype]
+    lo = (k[0] - 1) if len(k) else 0
+    return CuArray(c.buf[lo * sz:(lo + len(k)) * sz].clone(), (len(k),), c.eltype)
+
+
+def partialsort_(c, k, alg=BitonicSort, lt=isless, by=identity, rev=False):
+    """Base.partialsort!(c, k, ::BitonicSortAlg; ...) = sort! then copy(c[k]) (sorting.jl:1015-1020)."""
+    if c.ndims != 1:
+        raise NotGraftedError("partialsort! is defined for vectors")
+    sort_(c, alg=alg, lt=lt, by=by, rev=rev)
+    return _index_k(c, k)
+
+
+def partialsort(c, k, **kw):
+    return partialsort_(c.copy(), k, **kw)
+
+
+def sortperm_(ix, A, initialized=False, alg=BitonicSort, lt=isless, by=identity, rev=False, dims=None):
+    """Base.sortperm!(ix::AnyCuArray, A::AnyCuArray; initialized=false, kw...) (sorting.jl:1051-1061)."""
+    if ix.dims != A.dims:
+        def axes(d):
+            return "(" + ", ".join(f"Base.OneTo({s})" for s in d) + ("," if len(d) == 1 else "") + ")"
+        raise ArgumentError("index array must have the same size/axes as the source array, "
+                            f"{axes(ix.dims)} != {axes(A.dims)}")              # sorting.jl:1052-1054
+    if A.length == 0:
+        return ix                                                              # sorting.jl:1055
+    _guard(lt, by, alg)
+    if initialized:
+        # a caller-supplied starting permutation breaks ties by index VALUE (sorting.jl:642-643)
+        raise NotGraftedError("sortperm!(...; initialized=true) stays on the reference path")
+    if ix.eltype not in (dt.I32, dt.I64, dt.U32, dt.U64):
+        raise NotGraftedError("index eltype must be a 32/64-bit integer")
+    n, nseg = _segments(A, dims)
+    lib = _lib.load()
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(lib.b200_sort_workspace_bytes(A.eltype, SORTPERM_INDEX, n, nseg, ctypes.byref(nbytes)))
+    ws = Workspace(nbytes.value, A.buf.device)
+    _lib.check(lib.b200_sortperm(ws.ptr, ws.nbytes, A.pointer, ix.pointer, A.eltype, ix.eltype, n, nseg,
+                                 1 if rev else 0, 1 if A.ndims > 1 else 0, current_stream_handle(A.buf.device)))
+    return ix
+
+
+def sortperm(c, dims=None, **kw):
+    """Base.sortperm(c::AnyCuVector) -> 1-based Int64 (sorting.jl:1063-1065); N-d needs dims and
+    returns linear indices (sorting.jl:1067-1070)."""
+    if c.ndims > 1 and dims is None:
+        raise ArgumentError("sortperm of a multidimensional array needs dims")  # Base: UndefKeywordError
+    ix = CuArray.undef(dt.I64, c.dims, c.buf.device)
+    return sortperm_(ix, c, dims=dims, **kw)

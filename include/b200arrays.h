@@ -161,7 +161,10 @@ int32_t b200_scan(void *workspace, size_t workspace_bytes,
  * `rev=true` (stable: ties keep ascending index, sorting.jl:582-592).
  * Stable LSD radix sort.  Segments: `nseg` independent contiguous vectors of
  * `n` keys each (sort!(A; dims=1) of an n x nseg matrix); nseg = 1 for vectors. */
-int32_t b200_sort_workspace_bytes(int32_t dtype_key, int32_t dtype_payload /* -1: keys only */,
+/* dtype_payload: -1 = keys only (b200_sort_keys), B200_SORTPERM_INDEX = b200_sortperm,
+ * otherwise the payload dtype of b200_sort_pairs. */
+#define B200_SORTPERM_INDEX 100
+int32_t b200_sort_workspace_bytes(int32_t dtype_key, int32_t dtype_payload,
                                   int64_t n, int64_t nseg, size_t *bytes);
 /* In place. */
 int32_t b200_sort_keys(void *workspace, size_t workspace_bytes,

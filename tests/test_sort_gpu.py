@@ -1,0 +1,207 @@
+"""Parity of the onesweep radix sort (through the host mirror of sorting.jl's Base hooks)
+against the CPU oracle.  Mirrors test/core/sorting.jl:285-403:
+  * sort!/sort validity = same multiset + issorted (check_equivalence, :169-171); here the
+    stronger element-wise equality with the oracle's stable sort is asserted as well;
+  * sortperm == Base.sortperm exactly (:248-253), incl. rev, Float32/Float64 1e6, Int32/UInt64
+    index eltypes, empty input, N-d dims=1;
+  * sizes 1,2,3,4, 2^16 + {0,1,31,32,33,127,128,129} (:351-362); Int8 4e6 (:307);
+  * partialsort k scalar and ranges (:368-372); ArgumentError on mismatched axes (:401).
+Bit-exact everywhere.
+"""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+RNG = np.random.default_rng(0x50F7)
+
+
+def npdt(name):
+    return oracle.bfloat16 if name == "bfloat16" else np.dtype(name)
+
+
+def rand(name, n):
+    d = npdt(name)
+    if oracle.is_float(d):
+        return RNG.random(n).astype(np.float32).astype(d) if d.itemsize < 8 else RNG.random(n)
+    if d == np.bool_:
+        return RNG.random(n) < 0.5
+    ii = np.iinfo(d)
+    return RNG.integers(ii.min, ii.max, size=n, dtype=d, endpoint=True)
+
+
+def bits(a):
+    a = np.asarray(a)
+    return a.view(np.dtype(f"u{a.dtype.itemsize}")) if a.dtype != np.bool_ else a.astype(np.uint8)
+
+
+ALL_TYPES = ["int64", "int32", "int8", "float64", "float32", "float16", "bfloat16", "uint8", "uint16", "int16",
+             "uint32", "uint64", "bool"]
+
+
+@pytest.mark.parametrize("dtype", ALL_TYPES)
+@pytest.mark.parametrize("rev", [False, True])
+def test_sort_types(b, dtype, rev):
+    a = rand(dtype, 10000)
+    c = b.CuArray(a)
+    out = b.sort_(c, rev=rev)
+    assert out is c
+    got = b.Array(c)
+    assert oracle.is_valid_sort(a, got, rev=rev)
+    np.testing.assert_array_equal(bits(got), bits(oracle.sort(a, rev=rev)))
+    s = b.sort(b.CuArray(a), rev=rev)
+    np.testing.assert_array_equal(bits(b.Array(s)), bits(oracle.sort(a, rev=rev)))
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 4, (1 << 16), (1 << 16) + 1, (1 << 16) + 31, (1 << 16) + 32, (1 << 16) + 33,
+                               (1 << 16) + 127, (1 << 16) + 128, (1 << 16) + 129, 4095, 4096, 4097])
+def test_sort_sizes(b, n):
+    a = rand("float32", n)
+    got = b.Array(b.sort_(b.CuArray(a)))
+    np.testing.assert_array_equal(bits(got), bits(oracle.sort(a)))
+
+
+@pytest.mark.parametrize("dtype,n,f", [("int32", 1_000_000, "sorted"), ("float32", 1_000_000, "sorted"),
+                                       ("int32", 1_000_000, "reverse"), ("float32", 1_000_000, "reverse"),
+                                       ("int8", 4_000_000, "random"), ("uint8", 100_000, "skew"),
+                                       ("float32", 1 << 22, "random"), ("int64", 1_000_000, "random"),
+                                       ("float64", 1_000_000, "random")])
+@pytest.mark.parametrize("rev", [False, True])
+def test_sort_orderings(b, dtype, n, f, rev):
+    d = npdt(dtype)
+    if f == "sorted":
+        a = np.arange(1, n + 1).astype(d)
+    elif f == "reverse":
+        a = (-np.arange(1, n + 1)).astype(d)
+    elif f == "skew":
+        a = np.round(255 * RNG.random(n) ** 3).astype(d)
+    else:
+        a = rand(dtype, n)
+    got = b.Array(b.sort_(b.CuArray(a), rev=rev))
+    assert oracle.is_valid_sort(a, got, rev=rev)
+    np.testing.assert_array_equal(bits(got), bits(oracle.sort(a, rev=rev)))
+
+
+def test_float_total_order(b):
+    """isless: -Inf < ... < -0.0 < +0.0 < ... < +Inf < NaN."""
+    special = np.array([np.nan, -np.nan, np.inf, -np.inf, 0.0, -0.0, 1.0, -1.0, 5e-324, -5e-324], dtype=np.float64)
+    for dtype in ("float64", "float32", "float16", "bfloat16"):
+        a = np.concatenate([special.astype(np.float32 if dtype != "float64" else np.float64), RNG.standard_normal(5000)]).astype(npdt(dtype))
+        RNG.shuffle(a)
+        for rev in (False, True):
+            got = b.Array(b.sort_(b.CuArray(a), rev=rev))
+            assert oracle.is_valid_sort(a, got, rev=rev)
+            ref = oracle.sort(a, rev=rev)
+            nan = np.isnan(ref.astype(np.float64))
+            np.testing.assert_array_equal(np.isnan(got.astype(np.float64)), nan)
+            np.testing.assert_array_equal(bits(got)[~nan], bits(ref)[~nan])
+            p = b.Array(b.sortperm(b.CuArray(a), rev=rev))
+            np.testing.assert_array_equal(p, oracle.sortperm(a, rev=rev))
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("rev", [False, True])
+def test_sortperm_1m(b, dtype, rev):
+    """test/core/sorting.jl:381-387: 1e6 Float32s have ~9.4e5 unique values, stability is non-trivial."""
+    a = rand(dtype, 1_000_000)
+    I = b.sortperm(b.CuArray(a), rev=rev)
+    assert I.eltype == b.dtypes.I64
+    np.testing.assert_array_equal(b.Array(I), oracle.sortperm(a, rev=rev))
+
+
+@pytest.mark.parametrize("dtype", ["int32", "uint8", "int8", "bool", "uint16", "float16", "int64", "uint64"])
+def test_sortperm_stability_few_unique(b, dtype):
+    a = rand(dtype, 300_001)
+    if dtype not in ("bool", "uint8", "int8"):
+        a = (a.astype(np.float64) % 17).astype(npdt(dtype))
+    for rev in (False, True):
+        np.testing.assert_array_equal(b.Array(b.sortperm(b.CuArray(a), rev=rev)), oracle.sortperm(a, rev=rev))
+
+
+def test_sortperm_empty_and_small(b):
+    assert b.Array(b.sortperm(b.CuArray(np.zeros(0, dtype=np.float32)))).size == 0
+    for n in (1, 2, 3, 33):
+        a = rand("float32", n)
+        np.testing.assert_array_equal(b.Array(b.sortperm(b.CuArray(a))), oracle.sortperm(a))
+
+
+def test_sortperm_bang_index_eltypes(b):
+    """test/core/sorting.jl:395-403."""
+    a = rand("float32", 1_000_000)
+    ix = b.CuArray(np.arange(1, a.size + 1, dtype=np.int32))
+    out = b.sortperm_(ix, b.CuArray(a))
+    assert out is ix
+    np.testing.assert_array_equal(b.Array(ix), oracle.sortperm(a).astype(np.int32))
+    ix0 = b.CuArray(np.zeros(0, dtype=np.int32))
+    assert b.sortperm_(ix0, b.CuArray(np.zeros(0, dtype=np.float32))) is ix0
+    ai = rand("int64", 1_000_000)
+    ixu = b.CuArray(np.arange(1, ai.size + 1, dtype=np.uint64))
+    b.sortperm_(ixu, b.CuArray(ai), initialized=False)
+    np.testing.assert_array_equal(b.Array(ixu), oracle.sortperm(ai).astype(np.uint64))
+    with pytest.raises(b.ArgumentError) as e:
+        b.sortperm_(b.CuArray(np.arange(1, 4)), b.CuArray(np.arange(1, 5)))
+    assert "index array must have the same size/axes as the source array" in str(e.value)
+    with pytest.raises(b.NotGraftedError):
+        b.sortperm_(b.CuArray(np.arange(1, 5)), b.CuArray(np.arange(1, 5)), initialized=True)
+    # keys are never modified (sorting.jl:857-858)
+    d = b.CuArray(a)
+    b.sortperm(d)
+    np.testing.assert_array_equal(b.Array(d), a)
+
+
+def test_partialsort(b):
+    """test/core/sorting.jl:368-372."""
+    a = rand("int64", 100_000)
+    ref = oracle.sort(a)
+    for k in (1, 100_000, 50_000):
+        c = b.CuArray(a)
+        assert b.partialsort_(c, k) == ref[k - 1]
+        assert oracle.is_valid_sort(a, b.Array(c))
+    for k in (range(10_000, 20_001), range(1, 100_001)):
+        c = b.CuArray(a)
+        out = b.partialsort_(c, k)
+        assert out.dims == (len(k),)
+        np.testing.assert_array_equal(b.Array(out), ref[k[0] - 1:k[-1]])
+    np.testing.assert_array_equal(b.Array(b.partialsort(b.CuArray(a), range(5, 10), rev=True)), oracle.sort(a, rev=True)[4:9])
+
+
+def test_dims1_segments(b):
+    """sort!(A; dims=1) / sortperm(A; dims=1) (test/core/sorting.jl:390,392 shapes, scaled)."""
+    A = np.asfortranarray(rand("float32", 10_000 * 16).reshape(10_000, 16))
+    c = b.CuArray(A)
+    b.sort_(c, dims=1)
+    np.testing.assert_array_equal(b.Array(c), oracle.sort_dims(A, 1))
+    np.testing.assert_array_equal(b.Array(b.sortperm(b.CuArray(A), dims=1)), oracle.sortperm_dims(A, 1))
+    B3 = np.asfortranarray(rand("int32", 100 * 16 * 8).reshape(100, 16, 8))
+    c3 = b.CuArray(B3)
+    b.sort_(c3, dims=1, rev=True)
+    np.testing.assert_array_equal(b.Array(c3), oracle.sort_dims(B3, 1, rev=True))
+    np.testing.assert_array_equal(b.Array(b.sortperm(b.CuArray(B3), dims=1)), oracle.sortperm_dims(B3, 1))
+
+
+def test_guards(b):
+    c = b.CuArray(rand("float32", 100))
+    with pytest.raises(b.NotGraftedError):
+        b.sort_(c, by=lambda x: abs(x - 0.5))
+    with pytest.raises(b.NotGraftedError):
+        b.sort_(c, alg=b.QuickSort)
+    with pytest.raises(b.NotGraftedError):
+        b.sort_(b.CuArray(np.zeros((4, 4), dtype=np.float32)), dims=2)
+
+
+def test_repetition_no_races(b):
+    """test/core/sorting.jl:273-278: repeat to hunt races."""
+    a = (np.arange(100_000, 0, -1) % 256).astype(np.uint8)
+    ref = oracle.sort(a)
+    for _ in range(10):
+        np.testing.assert_array_equal(b.Array(b.sort_(b.CuArray(a))), ref)
+
+
+def test_large_sort_and_sortperm(b):
+    n = (1 << 24) + 12345
+    a = rand("uint32", n)
+    got = b.Array(b.sort_(b.CuArray(a)))
+    np.testing.assert_array_equal(got, np.sort(a))
+    f = rand("float32", n)
+    np.testing.assert_array_equal(b.Array(b.sortperm(b.CuArray(f))), oracle.sortperm(f))
