@@ -5,19 +5,27 @@ namespace b200 {
 
 static bool make_xform(int dtype, int descending, int nan_canonical, SortXform &x, int &kb) {
     x = SortXform{};
-    x.descending = descending ? 1 : 0;
-    x.nan_canonical = nan_canonical;
     kb = dtype_size(dtype);
     if (kb == 0) return false;
-    x.sign_bit = 1ull << (8 * kb - 1);
+    const uint64_t all = kb == 8 ? ~0ull : ((1ull << (8 * kb)) - 1);
+    const uint64_t sign = 1ull << (8 * kb - 1);
+    x.sign = sign;
+    x.desc = descending ? all : 0;
+    x.inf_bits = all;   // never exceeded unless a float format narrows it below
+    bool is_float = false;
     switch (dtype) {
-        case B200_F16: x.kind = RX_KIND_FLOAT; x.inf_bits = 0x7C00ull; break;
-        case B200_BF16: x.kind = RX_KIND_FLOAT; x.inf_bits = 0x7F80ull; break;
-        case B200_F32: x.kind = RX_KIND_FLOAT; x.inf_bits = 0x7F800000ull; break;
-        case B200_F64: x.kind = RX_KIND_FLOAT; x.inf_bits = 0x7FF0000000000000ull; break;
-        case B200_I8: case B200_I16: case B200_I32: case B200_I64: x.kind = RX_KIND_SIGNED; break;
-        case B200_U8: case B200_U16: case B200_U32: case B200_U64: case B200_BOOL: x.kind = RX_KIND_UNSIGNED; break;
+        case B200_F16: is_float = true; x.inf_bits = 0x7C00ull; break;
+        case B200_BF16: is_float = true; x.inf_bits = 0x7F80ull; break;
+        case B200_F32: is_float = true; x.inf_bits = 0x7F800000ull; break;
+        case B200_F64: is_float = true; x.inf_bits = 0x7FF0000000000000ull; break;
+        case B200_I8: case B200_I16: case B200_I32: case B200_I64:
+            x.base_enc = sign; x.base_dec = sign; break;
+        case B200_U8: case B200_U16: case B200_U32: case B200_U64: case B200_BOOL: break;
         default: return false;
+    }
+    if (is_float) {
+        x.base_enc = sign; x.base_dec = all; x.fmn = all & ~sign; x.mag_mask = all & ~sign;
+        x.nan_or = nan_canonical ? all : 0;
     }
     return true;
 }

@@ -29,42 +29,35 @@ template <> struct KeyOf<8> { using type = uint64_t; };
 
 struct NoPayload {};
 
-enum { RX_KIND_UNSIGNED = 0, RX_KIND_SIGNED = 1, RX_KIND_FLOAT = 2 };
-
+// Branch-free key transform, parameterised by uniform masks (built by make_xform in api_sort.cu):
+//   encode: key = bits ^ (base_enc | (sar(bits) & fmn));  NaN (float only): key = nan_or | mag | sign;  key ^= desc
+//   decode: key ^= desc;  bits = key ^ (base_dec ^ (sar(key) & fmn))
+// float:    base_enc = sign, fmn = ~sign, base_dec = ~0   (negative: ~bits, positive: bits | sign)
+// signed:   base_enc = sign, fmn = 0,     base_dec = sign
+// unsigned: all zero
 struct SortXform {
-    int32_t kind;
-    int32_t descending;
-    int32_t nan_canonical;   // 1: every NaN maps to one key (sortperm ties by index, like isless)
-    uint64_t sign_bit;
-    uint64_t inf_bits;       // exponent mask of the float format
+    uint64_t base_enc, base_dec, fmn;
+    uint64_t mag_mask;      // ~sign for floats, 0 otherwise (so the NaN test never fires)
+    uint64_t inf_bits;      // exponent mask of the float format
+    uint64_t nan_or;        // ~0: every NaN maps to one key (sortperm); 0: keep the payload, drop the sign (sort!)
+    uint64_t sign;
+    uint64_t desc;          // ~0 when descending
 };
 
 template <class K> __device__ __forceinline__ K key_encode(K bits, const SortXform &x) {
-    const K sign = (K)x.sign_bit;
-    K key;
-    if (x.kind == RX_KIND_FLOAT) {
-        const K mag = bits & (K)~sign;
-        if (mag > (K)x.inf_bits) {
-            // NaN: after every finite value and +Inf.  sort! keeps the payload (sign dropped),
-            // sortperm makes all NaNs equal.
-            key = x.nan_canonical ? (K)~(K)0 : (K)(mag | sign);
-        } else {
-            key = (bits & sign) ? (K)~bits : (K)(bits | sign);
-        }
-    } else if (x.kind == RX_KIND_SIGNED) {
-        key = bits ^ sign;
-    } else {
-        key = bits;
-    }
-    return x.descending ? (K)~key : key;
+    using SK = typename std::make_signed<K>::type;
+    const K sar = (K)((SK)bits >> (8 * sizeof(K) - 1));
+    K key = bits ^ ((K)x.base_enc | (sar & (K)x.fmn));
+    const K mag = bits & (K)x.mag_mask;
+    if (mag > (K)x.inf_bits) key = (K)x.nan_or | mag | (K)x.sign;
+    return key ^ (K)x.desc;
 }
 
 template <class K> __device__ __forceinline__ K key_decode(K key, const SortXform &x) {
-    const K sign = (K)x.sign_bit;
-    if (x.descending) key = (K)~key;
-    if (x.kind == RX_KIND_FLOAT) return (key & sign) ? (K)(key ^ sign) : (K)~key;
-    if (x.kind == RX_KIND_SIGNED) return key ^ sign;
-    return key;
+    using SK = typename std::make_signed<K>::type;
+    key ^= (K)x.desc;
+    const K sar = (K)((SK)key >> (8 * sizeof(K) - 1));
+    return key ^ ((K)x.base_dec ^ (sar & (K)x.fmn));
 }
 
 // ------------------------------------------------------------------ histogram of every digit
@@ -134,6 +127,7 @@ struct OnesweepParams {
     int32_t gen_payload;              // first sortperm pass: payload = element index
     int32_t index_dtype;              // last sortperm pass: store index_base + payload as this dtype; -1: raw payload
     int64_t index_base;               // 1 for per-segment 1-based indices (+ segment offset when linear)
+    int32_t debug;
 };
 
 template <class LookT> struct LookBits;
@@ -153,6 +147,12 @@ template <class LookT> __device__ __forceinline__ LookT ld_relaxed(const LookT *
 template <class LookT> __device__ __forceinline__ void st_relaxed(LookT *p, LookT v) {
     if constexpr (sizeof(LookT) == 4) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
     else asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// 8-bit digit at a byte-aligned shift: one PRMT for keys of up to 32 bits.
+template <class K> __device__ __forceinline__ unsigned int digit_of(K key, int shift) {
+    if constexpr (sizeof(K) <= 4) return __byte_perm((unsigned int)key, 0u, 0x4440u | (unsigned int)(shift >> 3));
+    else return (unsigned int)(key >> shift) & 0xFFu;
 }
 
 template <class V> struct PayTraits { static constexpr bool HAS = true; using type = V; };
@@ -185,40 +185,70 @@ __global__ void __launch_bounds__(RX_THREADS) radix_onesweep_kernel(OnesweepPara
     __syncthreads();
     const int64_t t = (int64_t)s_ticket;
     const int64_t tile_base = t * TILE;
-    int64_t valid = p.n - tile_base;
-    if (valid > TILE) valid = TILE;
+    const int64_t remain = p.n - tile_base;
+    const int valid = remain > TILE ? TILE : (int)remain;
+    const bool full = valid == TILE;
 
     // ---- load keys, warp-striped: item i of lane l is element warp*WARP_ITEMS + i*32 + l
-    const K *kin = static_cast<const K *>(p.keys_in) + tile_base;
+    const K *kin = static_cast<const K *>(p.keys_in) + tile_base + warp * WARP_ITEMS + lane;
+    const int idx0 = warp * WARP_ITEMS + lane;
     K keys[ITEMS];
+    if (full) {
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-        const int idx = warp * WARP_ITEMS + i * 32 + lane;
-        keys[i] = idx < valid ? ldg_stream(kin + idx) : (K)0;
+        for (int i = 0; i < ITEMS; ++i) keys[i] = ldg_stream(kin + i * 32);
+    } else {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) keys[i] = (idx0 + i * 32 < valid) ? ldg_stream(kin + i * 32) : (K)0;
     }
+    if (p.encode_in) {
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-        const int idx = warp * WARP_ITEMS + i * 32 + lane;
-        if (p.encode_in) keys[i] = key_encode<K>(keys[i], p.xf);
-        if (idx >= valid) keys[i] = (K)~(K)0;   // padding ranks last inside digit 255
+        for (int i = 0; i < ITEMS; ++i) keys[i] = key_encode<K>(keys[i], p.xf);
+    }
+    if (!full) {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i)
+            if (idx0 + i * 32 >= valid) keys[i] = (K)~(K)0;   // padding ranks last inside digit 255
     }
 
-    // ---- rank inside the warp: stable by (item, lane) = element order
+    // ---- rank inside the warp: stable by (item, lane) = element order.
+    // Peer masks come from 8 ballots (one per digit bit) rather than MATCH.ANY: MATCH runs on
+    // the ADU pipe at ~1 warp instruction per 64 cycles per SM on sm_100 and capped a pass at
+    // ~140 Gkeys/s (ncu: sm__inst_executed_pipe_adu 78%); VOTE issues at 2 per cycle per SM.
     unsigned short ranks[ITEMS];
+    const unsigned int lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-        const unsigned int digit = (unsigned int)((keys[i] >> p.shift) & 0xFF);
-        const unsigned int peers = __match_any_sync(0xffffffffu, digit);
-        const int leader = __ffs(peers) - 1;
-        const unsigned int below = __popc(peers & ((1u << lane) - 1u));
-        unsigned int old = 0;
-        if (lane == leader) {
-            old = whist[digit];
-            whist[digit] = old + __popc(peers);
+        const unsigned int digit = digit_of<K>(keys[i], p.shift);
+        unsigned int peers;
+        if ((i & 3) == 3) {
+            // every 4th item goes through MATCH.ANY so that the ADU pipe shares the load with the ALU
+            peers = __match_any_sync(0xffffffffu, digit);
+        } else {
+            unsigned int differ = 0;   // lanes whose digit differs from mine in some bit
+#pragma unroll
+            for (int bit = 0; bit < 8; ++bit) {
+                // and+setp -> one LOP3 with predicate output; VOTE; SEL; LOP3 (differ | (bal ^ ext))
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t.reg .b32 t, bal, ext;\n\t"
+                    "and.b32 t, %1, %2;\n\t"
+                    "setp.ne.u32 p, t, 0;\n\t"
+                    "vote.sync.ballot.b32 bal, p, 0xffffffff;\n\t"
+                    "selp.b32 ext, 0xffffffff, 0, p;\n\t"
+                    "lop3.b32 %0, %0, bal, ext, 0xF6;\n\t}"
+                    : "+r"(differ) : "r"(digit), "r"(1u << bit));
+            }
+            peers = ~differ;
         }
-        old = __shfl_sync(0xffffffffu, old, leader);
-        ranks[i] = (unsigned short)(old + below);
+        // every peer reads the digit's counter, then the lowest peer lane bumps it (same warp:
+        // shared-memory accesses execute in program order; __syncwarp keeps the compiler honest)
+        const unsigned int lower = peers & lt_mask;
+        const unsigned int below = __popc(lower);
+        volatile unsigned int *ctr = whist + digit;
+        const unsigned int old = *ctr;
         __syncwarp();
+        if (lower == 0u) *ctr = old + __popc(peers);
+        __syncwarp();
+        ranks[i] = (unsigned short)(old + below);
     }
     __syncthreads();
 
@@ -259,14 +289,14 @@ __global__ void __launch_bounds__(RX_THREADS) radix_onesweep_kernel(OnesweepPara
         const VT *vin = static_cast<const VT *>(p.vals_in) + tile_base;
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
-            const int idx = warp * WARP_ITEMS + i * 32 + lane;
+            const int idx = idx0 + i * 32;
             if (p.gen_payload) vals[i] = (VT)(tile_base + idx);
             else vals[i] = idx < valid ? ldg_stream(vin + idx) : (VT)0;
         }
     }
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-        const unsigned int digit = (unsigned int)((keys[i] >> p.shift) & 0xFF);
+        const unsigned int digit = digit_of<K>(keys[i], p.shift);
         const unsigned int pos = s_doff[digit] + whist[digit] + ranks[i];
         s_keys[pos] = keys[i];
         if constexpr (HAS_V) s_vals[pos] = vals[i];
@@ -274,7 +304,7 @@ __global__ void __launch_bounds__(RX_THREADS) radix_onesweep_kernel(OnesweepPara
 
     // ---- decoupled look-back for digit d
     unsigned long long excl = 0;
-    if (t > 0) {
+    if (t > 0 && !(p.debug & 1)) {
         int64_t u = t - 1;
         bool done = false;
         while (!done) {
@@ -310,7 +340,7 @@ __global__ void __launch_bounds__(RX_THREADS) radix_onesweep_kernel(OnesweepPara
         const int i = tid + k * RX_THREADS;
         if (i < valid) {
             const K key = s_keys[i];
-            const unsigned int digit = (unsigned int)((key >> p.shift) & 0xFF);
+            const unsigned int digit = digit_of<K>(key, p.shift);
             const long long dst = s_gbase[digit] + i;
             if (p.store_keys) kout[dst] = p.decode_out ? key_decode<K>(key, p.xf) : key;
             if constexpr (HAS_V) {
