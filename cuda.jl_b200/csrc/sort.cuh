@@ -170,8 +170,12 @@ __global__ void __launch_bounds__(RX_THREADS) radix_onesweep_kernel(OnesweepPara
     // layout: [warp hist 8*256 u32][digit offset 256 u32][global base 256 i64][keys TILE][vals TILE]
     unsigned int *s_whist = reinterpret_cast<unsigned int *>(s_raw);
     unsigned int *s_doff = s_whist + RX_WARPS * RX_RADIX;
-    long long *s_gbase = reinterpret_cast<long long *>(s_doff + RX_RADIX);
-    K *s_keys = reinterpret_cast<K *>(s_gbase + RX_RADIX);
+    // global index of the tile's first key of each digit, minus its shared-memory position;
+    // 32-bit when n < 2^30 (LookT == uint32_t), which saves 64-bit address arithmetic per key
+    using BaseT = typename std::conditional<sizeof(LookT) == 4, int, long long>::type;
+    long long *s_gbase_raw = reinterpret_cast<long long *>(s_doff + RX_RADIX);
+    BaseT *s_gbase = reinterpret_cast<BaseT *>(s_gbase_raw);
+    K *s_keys = reinterpret_cast<K *>(s_gbase_raw + RX_RADIX);
     VT *s_vals = reinterpret_cast<VT *>(reinterpret_cast<unsigned char *>(s_keys) + ((TILE * sizeof(K) + 15) / 16) * 16);
     __shared__ unsigned long long s_ticket;
     __shared__ unsigned int s_wsum[RX_WARPS];
@@ -280,7 +284,9 @@ __global__ void __launch_bounds__(RX_THREADS) radix_onesweep_kernel(OnesweepPara
 #pragma unroll
     for (int w = 0; w < RX_WARPS; ++w) wbase += (w < warp) ? s_wsum[w] : 0u;
     const unsigned int doff = wbase + incl - tile_count;
-    s_doff[d] = doff;
+    // fold the digit run's start into every warp's offset: the scatter then needs one lookup
+#pragma unroll
+    for (int w = 0; w < RX_WARPS; ++w) s_whist[w * RX_RADIX + d] += doff;
     __syncthreads();
 
     // ---- scatter keys (and payload) into shared memory, sorted by digit
@@ -297,7 +303,7 @@ __global__ void __launch_bounds__(RX_THREADS) radix_onesweep_kernel(OnesweepPara
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         const unsigned int digit = digit_of<K>(keys[i], p.shift);
-        const unsigned int pos = s_doff[digit] + whist[digit] + ranks[i];
+        const unsigned int pos = whist[digit] + ranks[i];
         s_keys[pos] = keys[i];
         if constexpr (HAS_V) s_vals[pos] = vals[i];
     }
@@ -330,33 +336,44 @@ __global__ void __launch_bounds__(RX_THREADS) radix_onesweep_kernel(OnesweepPara
         }
         st_relaxed<LookT>(status + t * RX_RADIX + d, (LookT)(LB::INCLUSIVE | (LookT)(excl + real_count)));
     }
-    s_gbase[d] = (long long)(p.bins[d] + excl) - (long long)doff;
+    s_gbase[d] = (BaseT)((long long)(p.bins[d] + excl) - (long long)doff);
     __syncthreads();
 
-    // ---- write out: consecutive threads -> consecutive addresses inside each digit run
+    // ---- write out: consecutive threads -> consecutive addresses inside each digit run.
+    // The uniform choices (full tile? decode? keys? index conversion?) are hoisted out of
+    // the per-key loop: the common case is load-shared, one table lookup, one store.
     K *kout = static_cast<K *>(p.keys_out);
+    auto emit = [&](auto full_c, auto mode_c) {
+        constexpr bool kFull = decltype(full_c)::value;
+        constexpr int kMode = decltype(mode_c)::value;   // 0: keys as is, 1: keys decoded, 2: no keys
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const int i = tid + k * RX_THREADS;
-        if (i < valid) {
-            const K key = s_keys[i];
-            const unsigned int digit = digit_of<K>(key, p.shift);
-            const long long dst = s_gbase[digit] + i;
-            if (p.store_keys) kout[dst] = p.decode_out ? key_decode<K>(key, p.xf) : key;
-            if constexpr (HAS_V) {
-                const VT v = s_vals[i];
-                if (p.index_dtype < 0) {
-                    static_cast<VT *>(p.vals_out)[dst] = v;
-                } else {
-                    const long long ix = (long long)v + p.index_base;
-                    switch (p.index_dtype) {
-                        case B200_I64: case B200_U64: static_cast<long long *>(p.vals_out)[dst] = ix; break;
-                        default: static_cast<int *>(p.vals_out)[dst] = (int)ix; break;
+        for (int k = 0; k < ITEMS; ++k) {
+            const int i = tid + k * RX_THREADS;
+            if (kFull || i < valid) {
+                const K key = s_keys[i];
+                const BaseT dst = s_gbase[digit_of<K>(key, p.shift)] + i;
+                if constexpr (kMode == 0) kout[dst] = key;
+                if constexpr (kMode == 1) kout[dst] = key_decode<K>(key, p.xf);
+                if constexpr (HAS_V) {
+                    const VT v = s_vals[i];
+                    if (p.index_dtype < 0) {
+                        static_cast<VT *>(p.vals_out)[dst] = v;
+                    } else if (p.index_dtype == B200_I64 || p.index_dtype == B200_U64) {
+                        static_cast<long long *>(p.vals_out)[dst] = (long long)v + p.index_base;
+                    } else {
+                        static_cast<int *>(p.vals_out)[dst] = (int)((long long)v + p.index_base);
                     }
                 }
             }
         }
-    }
+    };
+    auto emit_mode = [&](auto full_c) {
+        if (!p.store_keys) emit(full_c, std::integral_constant<int, 2>{});
+        else if (p.decode_out) emit(full_c, std::integral_constant<int, 1>{});
+        else emit(full_c, std::integral_constant<int, 0>{});
+    };
+    if (full) emit_mode(std::true_type{});
+    else emit_mode(std::false_type{});
 }
 
 }  // namespace b200
