@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the grafted CuArray reduce / scan / sort path on B200.
+
+Metric (BASELINE.json): HBM GB/s for mapreduce / scan; sort Gkeys/s.  The headline line is
+quoted on BASELINE.json configs[1] — `sum(A; dims=1)`, `sum(A; dims=2)`, `maximum`, `count` on
+a 16384 x 16384 Float32 / BFloat16 CuMatrix (count: Bool matrix) — one "step" = those seven
+reductions once: 5.10 GB of algorithmic input bytes.  `value` = algorithmic bytes / device time
+with the matrices resident in HBM; `e2e` = the same step through the public host API starting
+from pinned HOST buffers (H2D of all three matrices and D2H of every result inside the timed
+region).  `extras` carries the other north-star configurations measured in the same run
+(sum / cumsum / sort! / sortperm on 2^30 elements), each with its own roofline fraction.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-extras]
+
+N > 1 (torchrun): every rank owns one 16384 x 16384 column block of a 16384 x (16384*N) matrix
+(weak scaling).  dims=1 sums need no exchange; dims=2 sums allreduce the 16384-vector of row
+sums; maximum / count allreduce a scalar (NCCL).  value = bytes of all ranks / max-over-ranks time.
+
+`--impl reference` times the reference's CPU path (Base Julia semantics restated in
+oracle/oracle_cpu.c — the reference itself is Julia and no julia binary exists in this image)
+on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M = 16384                       # matrix side of configs[1]
+F32_BYTES = M * M * 4
+BF16_BYTES = M * M * 2
+BOOL_BYTES = M * M
+STEP_BYTES = 3 * F32_BYTES + 3 * BF16_BYTES + BOOL_BYTES    # 5.10 GB algorithmic input bytes per step
+NOMINAL_GBS = 8000.0
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            sm, smax, reasons = [], [], set()
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                sm.append(float(f[1])); smax.append(float(f[2]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                       "samples": len(sm)}
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        return out
+
+
+# ============================================================================ reference arm
+def run_reference(args, rank, world):
+    """The reference's CPU path (Base Julia semantics, C restatement) on the host cores."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_cpu as oc
+    # bounded sample: a 4096-column block of the 16384 x 16384 matrices (1/4 of the step's bytes)
+    cols = 4096
+    rng = np.random.default_rng(0xB200 + 1)
+    A = np.asfortranarray(rng.uniform(-1, 1, size=(M, cols)).astype(np.float32))
+    H = np.asfortranarray((A.view(np.uint32) >> 16).astype(np.uint16))      # bf16 bits (truncation is fine for timing)
+    Bm = np.asfortranarray(rng.random((M, cols)) < 0.5)
+    sample_bytes = 3 * A.nbytes + 3 * H.nbytes + Bm.nbytes
+
+    def step():
+        oc.sum_dims(A, 1); oc.sum_dims(A, 2); oc.maximum_f32(A)
+        oc.sum_dims(H, 1); oc.sum_dims(H, 2); oc.maximum_bf16(H)
+        oc.count_bool(Bm)
+
+    steps = max(1, min(args.steps, 5))
+    for _ in range(min(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    gbs = sample_bytes * steps / dt / 1e9
+    sample = f"{M}x{cols} column block of each matrix (1/4 of a step), {steps} passes, single thread"
+    line = {
+        "impl": "reference", "metric": "HBM GB/s, sum/maximum/count on 16384x16384 F32+BF16+Bool (configs[1])",
+        "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": dt / steps * 1e3 * (STEP_BYTES / sample_bytes), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: sum(A;dims=1), sum(A;dims=2), maximum(A) on 16384x16384 Float32 and "
+                               "BFloat16, count on 16384x16384 Bool; CPU sample scaled to the full step"},
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores": os.cpu_count(),
+                         "note": "Base Julia's sum/maximum/count are single-threaded; C restatement oracle/oracle_cpu.c"},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ============================================================================ product arm
+def run_product(args, rank, world, local_rank):
+    import torch
+    import b200arrays as b
+    from b200arrays import dtypes as dt
+
+    assert torch.cuda.is_available(), "bench.py needs a B200"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = b._lib.load()            # fails loudly when the extension is missing
+    assert lib.b200_check_device() == 0, "not an sm_100 device"
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    peak, peak_src = measured_peak()
+    g = torch.Generator(device=dev); g.manual_seed(0xB200 + 1 + rank)
+    # ---- synthetic inputs of configs[1]: F32 uniform [-1,1), BF16 = rounded same, Bool p=0.5
+    A32 = torch.rand(M * M, device=dev, generator=g, dtype=torch.float32).mul_(2).sub_(1)
+    A16 = A32.to(torch.bfloat16)
+    AB = torch.rand(M * M, device=dev, generator=g) < 0.5
+    cA32 = b.CuArray.from_torch(A32, (M, M)); cA16 = b.CuArray.from_torch(A16, (M, M)); cAB = b.CuArray.from_torch(AB, (M, M))
+    r1_32 = b.CuArray.undef(dt.F32, (1, M)); r2_32 = b.CuArray.undef(dt.F32, (M, 1)); rm_32 = b.CuArray.undef(dt.F32, (1, 1))
+    r1_16 = b.CuArray.undef(dt.BF16, (1, M)); r2_16 = b.CuArray.undef(dt.BF16, (M, 1)); rm_16 = b.CuArray.undef(dt.BF16, (1, 1))
+    rc = b.CuArray.undef(dt.I64, (1, 1))
+    ninf = -np.inf
+
+    def exchange():
+        if dist is None:
+            return
+        # rows are split across ranks (column blocks): dims=2 partial row sums and the scalars need an allreduce
+        dist.all_reduce(r2_32.typed()); dist.all_reduce(r2_16.typed())
+        dist.all_reduce(rm_32.typed(), op=dist.ReduceOp.MAX); dist.all_reduce(rm_16.typed(), op=dist.ReduceOp.MAX)
+        dist.all_reduce(rc.typed())
+
+    def step():
+        # interleave the matrices so no input is still L2-resident when it is read again
+        b.mapreducedim_(b.identity, b.add_sum, r1_32, cA32, init=0)
+        b.mapreducedim_(b.identity, b.add_sum, r1_16, cA16, init=0)
+        b.mapreducedim_(b.identity, b.add_sum, rc, cAB, init=0)          # count
+        b.mapreducedim_(b.identity, b.add_sum, r2_32, cA32, init=0)
+        b.mapreducedim_(b.identity, b.add_sum, r2_16, cA16, init=0)
+        b.mapreducedim_(b.identity, b.max_, rm_32, cA32, init=ninf)
+        b.mapreducedim_(b.identity, b.max_, rm_16, cA16, init=ninf)
+        exchange()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.b200_reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = int(lib.b200_launch_count())
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = STEP_BYTES * world / (ms_per_step * 1e-3) / 1e9
+
+    # ---- per-kernel roofline of the dominant kernel: time each reduction alone (events on the launch stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def time_one(fn, reps=10):
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record(); e.synchronize()
+            ts.append(s.elapsed_time(e))
+        return float(np.mean(ts)), float(min(ts))
+
+    per_op = {}
+    if rank == 0:
+        ops = {
+            "sum(A;dims=1) F32 [reduce_contig_block_kernel]": (lambda: b.mapreducedim_(b.identity, b.add_sum, r1_32, cA32, init=0), F32_BYTES),
+            "sum(A;dims=2) F32 [reduce_strided_kernel]": (lambda: b.mapreducedim_(b.identity, b.add_sum, r2_32, cA32, init=0), F32_BYTES),
+            "maximum(A) F32 [reduce_contig_block_kernel]": (lambda: b.mapreducedim_(b.identity, b.max_, rm_32, cA32, init=ninf), F32_BYTES),
+            "sum(A;dims=1) BF16 [reduce_contig_block_kernel]": (lambda: b.mapreducedim_(b.identity, b.add_sum, r1_16, cA16, init=0), BF16_BYTES),
+            "sum(A;dims=2) BF16 [reduce_strided_kernel]": (lambda: b.mapreducedim_(b.identity, b.add_sum, r2_16, cA16, init=0), BF16_BYTES),
+            "maximum(A) BF16 [reduce_contig_block_kernel]": (lambda: b.mapreducedim_(b.identity, b.max_, rm_16, cA16, init=ninf), BF16_BYTES),
+            "count(A) Bool [reduce_contig_block_kernel]": (lambda: b.mapreducedim_(b.identity, b.add_sum, rc, cAB, init=0), BOOL_BYTES),
+        }
+        for name, (fn, nbytes) in ops.items():
+            mean_ms, min_ms = time_one(fn)
+            per_op[name] = {"ms": mean_ms, "min_ms": min_ms, "GB/s": nbytes / mean_ms / 1e6, "frac_of_measured_peak": nbytes / mean_ms / 1e6 / peak}
+    del flush
+
+    # ---- e2e: the same step through the public API from pinned HOST buffers
+    hA32 = A32.cpu().pin_memory(); hA16 = A16.cpu().pin_memory(); hAB = AB.cpu().pin_memory()
+    h2d = hA32.numel() * 4 + hA16.numel() * 2 + hAB.numel()
+    d2h = (M * 4 + M * 4 + 4) + (M * 2 + M * 2 + 2) + 8
+
+    def e2e_step():
+        dA32 = b.CuArray.from_torch(hA32.to(dev, non_blocking=True), (M, M))
+        dA16 = b.CuArray.from_torch(hA16.to(dev, non_blocking=True), (M, M))
+        dAB = b.CuArray.from_torch(hAB.to(dev, non_blocking=True), (M, M))
+        outs = [b.sum(dA32, dims=1), b.sum(dA32, dims=2), b.sum(dA16, dims=1), b.sum(dA16, dims=2)]
+        scal = [b.maximum(dA32), b.maximum(dA16), b.count(dAB)]        # dims=: reads the scalar back (D2H + sync)
+        return [o.to_host() for o in outs], scal
+
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = STEP_BYTES * world / (e2e_ms * 1e-3) / 1e9
+    del hA32, hA16, hAB
+
+    clocks = sampler.stop() if rank == 0 else {}
+    del A32, A16, AB, cA32, cA16, cAB
+    torch.cuda.empty_cache()
+
+    extras = {}
+    if not args.no_extras and world == 1:
+        extras = run_extras(b, dt, torch, dev, peak)
+
+    if rank != 0:
+        return
+    # ---- cpu baseline (bounded sample of the same workload, host cores of this box)
+    cpu = cpu_baseline_sample()
+    dom = max(per_op.items(), key=lambda kv: kv[1]["ms"]) if per_op else (None, None)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("reduce_strided_kernel_f32_dims2_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = None
+    if dom[0]:
+        nbytes = F32_BYTES if "F32" in dom[0] else (BF16_BYTES if "BF16" in dom[0] else BOOL_BYTES)
+        ach = nbytes / dom[1]["ms"] / 1e6
+        roofline = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "frac_of_nominal_8TBps": ach / NOMINAL_GBS, "peak_source": peak_src, "traffic": traffic,
+                    "algorithmic_bytes_per_launch": nbytes, "per_kernel": per_op}
+    line = {
+        "metric": "HBM GB/s, sum/maximum/count on 16384x16384 F32+BF16+Bool (configs[1])",
+        "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: sum(A;dims=1), sum(A;dims=2), maximum(A) on 16384x16384 Float32 and "
+                               "BFloat16, count on 16384x16384 Bool; 7 reductions = 5.10 GB algorithmic bytes per step",
+                   "l2": "inputs (256 MB - 1 GB each) exceed the 126 MB L2 and are interleaved between uses",
+                   "sharding": "column blocks, one 16384x16384 block per rank" if world > 1 else "single GPU",
+                   "frac_of_measured_peak": value / world / peak, "frac_of_nominal_8TBps": value / world / NOMINAL_GBS},
+        "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms, "steps": e2e_steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "extras": extras,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_sample():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import oracle_cpu as oc
+        cols = 2048
+        rng = np.random.default_rng(0xB200 + 1)
+        A = np.asfortranarray(rng.uniform(-1, 1, size=(M, cols)).astype(np.float32))
+        H = np.asfortranarray((A.view(np.uint32) >> 16).astype(np.uint16))
+        Bm = np.asfortranarray(rng.random((M, cols)) < 0.5)
+        nb = 3 * A.nbytes + 3 * H.nbytes + Bm.nbytes
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            oc.sum_dims(A, 1); oc.sum_dims(A, 2); oc.maximum_f32(A)
+            oc.sum_dims(H, 1); oc.sum_dims(H, 2); oc.maximum_bf16(H)
+            oc.count_bool(Bm)
+        dt_ = time.perf_counter() - t0
+        return {"value": nb * reps / dt_ / 1e9, "unit": "GB/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
+                "sample": f"{M}x{cols} column block of each matrix (1/8 of a step), {reps} passes, single thread "
+                          "(Base Julia's reductions are single-threaded); oracle/oracle_cpu.c"}
+    except Exception as e:  # the baseline is a reported number, never the product path
+        return {"value": None, "unit": "GB/s", "cores": 1, "kind": "port", "sample": f"unavailable: {e}"}
+
+
+def run_extras(b, dt, torch, dev, peak):
+    """North-star configurations beyond configs[1], measured in the same run (1 GPU)."""
+    out = {}
+
+    def tmin(fn, reps, pre=None):
+        ts = []
+        for _ in range(reps):
+            if pre is not None:
+                pre()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record(); e.synchronize()
+            ts.append(s.elapsed_time(e))
+        return float(np.median(ts)), float(min(ts))
+
+    n = 1 << 30
+    g = torch.Generator(device=dev); g.manual_seed(0xB200 + 3)
+    V = torch.rand(n, device=dev, generator=g, dtype=torch.float32)
+    cV = b.CuArray.from_torch(V)
+    R = b.CuArray.undef(dt.F32, (1,))
+    fn = lambda: b.mapreducedim_(b.identity, b.add_sum, R, cV, init=0)
+    fn(); med, mn = tmin(fn, 10)
+    out["sum 2^30 Float32"] = {"ms": med, "GB/s": 4 * n / med / 1e6, "frac_of_measured_peak": 4 * n / med / 1e6 / peak,
+                               "frac_of_nominal_8TBps": 4 * n / med / 1e6 / NOMINAL_GBS}
+    O = b.CuArray.undef(dt.F32, (n,))
+    fn = lambda: b.accumulate_(b.add, O, cV)
+    fn(); med, mn = tmin(fn, 5)
+    out["cumsum 2^30 Float32"] = {"ms": med, "GB/s": 8 * n / med / 1e6, "frac_of_measured_peak": 8 * n / med / 1e6 / peak,
+                                  "frac_of_nominal_8TBps": 8 * n / med / 1e6 / NOMINAL_GBS}
+    del O
+    # sort! / sortperm Float32 (keys restored from a pristine copy outside the timed region)
+    K = cV.copy()
+    restore = lambda: K.buf.copy_(cV.buf)
+    fn = lambda: b.sort_(K)
+    restore(); fn(); med, mn = tmin(fn, 3, pre=restore)
+    out["sort! 2^30 Float32"] = {"ms": med, "Gkeys/s": n / med / 1e6, "algorithmic_GB/s": 2 * 4 * n * 4 / med / 1e6,
+                                 "frac_of_radix_roofline_8TBps": 2 * 4 * n * 4 / med / 1e6 / NOMINAL_GBS,
+                                 "frac_of_radix_roofline_measured_peak": 2 * 4 * n * 4 / med / 1e6 / peak}
+    del K
+    fn = lambda: b.sortperm(cV)
+    fn(); med, mn = tmin(fn, 3)
+    out["sortperm 2^30 Float32"] = {"ms": med, "Gkeys/s": n / med / 1e6}
+    del V, cV
+    torch.cuda.empty_cache()
+    U = torch.randint(-2**31, 2**31 - 1, (n,), device=dev, generator=g, dtype=torch.int32)
+    cU = b.CuArray.from_torch(U, (n,), dt.U32)
+    K = cU.copy()
+    restore = lambda: K.buf.copy_(cU.buf)
+    fn = lambda: b.sort_(K)
+    restore(); fn(); med, mn = tmin(fn, 3, pre=restore)
+    out["sort! 2^30 UInt32"] = {"ms": med, "Gkeys/s": n / med / 1e6, "algorithmic_GB/s": 2 * 4 * n * 4 / med / 1e6,
+                                "frac_of_radix_roofline_8TBps": 2 * 4 * n * 4 / med / 1e6 / NOMINAL_GBS,
+                                "frac_of_radix_roofline_measured_peak": 2 * 4 * n * 4 / med / 1e6 / peak}
+    del K, U, cU
+    torch.cuda.empty_cache()
+    I = torch.randint(-2**20, 2**20, (n,), device=dev, generator=g, dtype=torch.int64)
+    cI = b.CuArray.from_torch(I)
+    O = b.CuArray.undef(dt.I64, (n,))
+    fn = lambda: b.accumulate_(b.add, O, cI)
+    fn(); med, mn = tmin(fn, 5)
+    out["cumsum 2^30 Int64"] = {"ms": med, "GB/s": 16 * n / med / 1e6, "frac_of_measured_peak": 16 * n / med / 1e6 / peak,
+                                "frac_of_nominal_8TBps": 16 * n / med / 1e6 / NOMINAL_GBS}
+    del I, cI, O
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_product(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -130,4 +130,23 @@ int32_t b200_sort_pairs(void *workspace, size_t workspace_bytes, void *keys, voi
     return run(kb, c);
 }
 
+int32_t b200_search_sorted(const void *sorted_keys, int64_t n, const void *needles, int64_t m, int32_t dtype_key,
+                           int32_t descending, void *lower_bounds_dev, b200_stream_t stream) {
+    using namespace b200;
+    if (n < 0 || m < 0) return B200_INVALID_VALUE;
+    SortXform xf; int kb;
+    if (!make_xform(dtype_key, descending, 1, xf, kb)) return B200_UNSUPPORTED;
+    if (m == 0) return B200_OK;
+    if (!needles || !lower_bounds_dev || (n > 0 && !sorted_keys)) return B200_INVALID_VALUE;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    long long *out = static_cast<long long *>(lower_bounds_dev);
+    switch (kb) {
+        case 1: return lower_bound_k1(sorted_keys, n, needles, m, xf, out, st);
+        case 2: return lower_bound_k2(sorted_keys, n, needles, m, xf, out, st);
+        case 4: return lower_bound_k4(sorted_keys, n, needles, m, xf, out, st);
+        case 8: return lower_bound_k8(sorted_keys, n, needles, m, xf, out, st);
+        default: return B200_UNSUPPORTED;
+    }
+}
+
 }  // extern "C"

@@ -109,6 +109,25 @@ static __global__ void __launch_bounds__(RX_RADIX) radix_bins_kernel(const unsig
     bins[blockIdx.x * RX_RADIX + d] = s[d] - c;
 }
 
+// ------------------------------------------------------------------ partition points
+// lower_bound of each needle in a sorted key array, in the ordered-key space (so it
+// honours isless and `rev`).  One thread per needle; used by the multi-GPU sample sort
+// to cut a locally sorted shard at the splitters.
+template <class K>
+__global__ void radix_lower_bound_kernel(const K *__restrict__ sorted, int64_t n, const K *__restrict__ needles,
+                                         int64_t m, SortXform xf, long long *__restrict__ out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const K needle = key_encode<K>(needles[j], xf);
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        if (key_encode<K>(sorted[mid], xf) < needle) lo = mid + 1;
+        else hi = mid;
+    }
+    out[j] = lo;
+}
+
 // ------------------------------------------------------------------ onesweep pass
 struct OnesweepParams {
     const void *keys_in;

@@ -26,5 +26,9 @@ int32_t sort_run_k1(const SortCall &);
 int32_t sort_run_k2(const SortCall &);
 int32_t sort_run_k4(const SortCall &);
 int32_t sort_run_k8(const SortCall &);
+int32_t lower_bound_k1(const void *, int64_t, const void *, int64_t, const SortXform &, long long *, cudaStream_t);
+int32_t lower_bound_k2(const void *, int64_t, const void *, int64_t, const SortXform &, long long *, cudaStream_t);
+int32_t lower_bound_k4(const void *, int64_t, const void *, int64_t, const SortXform &, long long *, cudaStream_t);
+int32_t lower_bound_k8(const void *, int64_t, const void *, int64_t, const SortXform &, long long *, cudaStream_t);
 
 }  // namespace b200

@@ -126,4 +126,14 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
     return B200_OK;
 }
 
+
+int32_t B200_CAT(lower_bound_k, B200_KEY_BYTES)(const void *sorted, int64_t n, const void *needles, int64_t m,
+                                               const SortXform &xf, long long *out, cudaStream_t st) {
+    if (m == 0) return B200_OK;
+    radix_lower_bound_kernel<K><<<(unsigned int)cdiv(m, 128), 128, 0, st>>>(static_cast<const K *>(sorted), n,
+                                                                           static_cast<const K *>(needles), m, xf, out);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
 }  // namespace b200

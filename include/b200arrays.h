@@ -185,6 +185,14 @@ int32_t b200_sort_pairs(void *workspace, size_t workspace_bytes,
                         int32_t dtype_key, int32_t dtype_payload, int64_t n,
                         int32_t descending, b200_stream_t stream);
 
+/* lower_bounds[j] = number of keys in `sorted_keys` (sorted by b200_sort_keys with the same
+ * `descending`) that order strictly before needles[j]; int64 on the device.  The multi-GPU
+ * sample sort cuts each locally sorted shard at the splitters with it (no
+ * reference counterpart: the reference has no multi-GPU sort). */
+int32_t b200_search_sorted(const void *sorted_keys, int64_t n, const void *needles, int64_t m,
+                           int32_t dtype_key, int32_t descending, void *lower_bounds_dev,
+                           b200_stream_t stream);
+
 /* ---- select: findall(::CuArray{Bool}) (indexing.jl:26-66) --------------- */
 /* Writes the 1-based linear indices (dtype_index I32/I64) of the non-zero flags
  * to `indices` in order and the number found to *count_dev (device int64).
