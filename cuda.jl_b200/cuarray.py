@@ -110,6 +110,8 @@ class CuArray:
 
     def typed(self):
         """The storage as a typed 1-D torch tensor (plumbing for collectives)."""
+        if self.buf.numel() == 0:
+            return torch.empty(0, dtype=_DT_TO_TORCH[self.eltype], device=self.buf.device)
         return self.buf.view(_DT_TO_TORCH[self.eltype])
 
     # -- host transfer: Array(c) ----------------------------------------------------

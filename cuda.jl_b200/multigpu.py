@@ -1,0 +1,254 @@
+"""Sharded (one process per GPU) versions of the 1-D primitives — SURVEY §8(e).
+
+The reference has NO multi-GPU path for reduce / scan / sort (SURVEY §2a "Collectives: none");
+this is new functionality layered on the shard-local kernels, as BASELINE.json's north star
+asks: shard-local reductions + allreduce of the partials; shard-local scans + all-gather of the
+shard carries; sample sort with splitter selection + all-to-all + local radix sort.
+`torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is the plumbing; every pass over the
+data is one of libb200arrays' kernels.
+
+Each rank holds a contiguous shard of a conceptual global vector, in rank order.
+
+`ops` is the provider of shard-local operations: `DeviceOps` (the library) by default; the CPU
+`gloo` tests inject a numpy-backed stand-in to exercise the host-side logic without a GPU.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import dtypes as dt
+from .cuarray import CuArray, current_stream_handle
+from .errors import NotGraftedError
+
+_TRANSPORT = {1: torch.uint8, 2: torch.int16, 4: torch.int32, 8: torch.int64}
+
+
+class DeviceOps:
+    """Shard-local operations on CuArrays through libb200arrays."""
+
+    def reduce(self, f, op, shard, out_eltype):
+        from .mapreduce import mapreducedim_, neutral_element, extrema_rf
+        R = CuArray.undef(out_eltype, (1,), shard.buf.device)
+        if shard.length == 0:
+            from .mapreduce import _fill
+            _fill(R, neutral_element(op, out_eltype))
+            return R
+        init = 0 if op is extrema_rf else neutral_element(op, out_eltype)
+        mapreducedim_(f, op, R, shard, init=init)
+        return R
+
+    def scan(self, op, out, shard, init, exclusive):
+        from .accumulate import scan_
+        return scan_(op, out, shard, 1, init=init, exclusive=exclusive)
+
+    def sort_keys(self, c, rev):
+        from .sorting import sort_
+        return sort_(c, rev=rev)
+
+    def sort_pairs(self, keys, payload, rev):
+        import ctypes
+        from . import _lib
+        from .cuarray import Workspace
+        lib = _lib.load()
+        if keys.length <= 1:
+            return
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.b200_sort_workspace_bytes(keys.eltype, payload.eltype, keys.length, 1, ctypes.byref(nbytes)))
+        ws = Workspace(nbytes.value, keys.buf.device)
+        _lib.check(lib.b200_sort_pairs(ws.ptr, ws.nbytes, keys.pointer, payload.pointer, keys.eltype, payload.eltype,
+                                       keys.length, 1 if rev else 0, current_stream_handle(keys.buf.device)))
+
+    def lower_bound(self, sorted_keys, needles, rev):
+        from . import _lib
+        lib = _lib.load()
+        out = CuArray.undef(dt.I64, (needles.length,), sorted_keys.buf.device)
+        _lib.check(lib.b200_search_sorted(sorted_keys.pointer if sorted_keys.length else None, sorted_keys.length,
+                                          needles.pointer if needles.length else None, needles.length,
+                                          sorted_keys.eltype, 1 if rev else 0, out.pointer,
+                                          current_stream_handle(sorted_keys.buf.device)))
+        return out
+
+
+def _world(group):
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def _typed(c):
+    """Storage viewed with a dtype every backend can transport (bit-preserving)."""
+    if c.buf.numel() == 0:
+        return torch.empty(0, dtype=_TRANSPORT[dt.SIZES[c.eltype]], device=c.buf.device)
+    return c.buf.view(_TRANSPORT[dt.SIZES[c.eltype]])
+
+
+def _acc_eltype(eltype):
+    return dt.F32 if eltype in (dt.F16, dt.BF16) else eltype
+
+
+# ----------------------------------------------------------------------------- reduce
+def dist_mapreduce(f, op, shard, group=None, ops=None):
+    """mapreduce(f, op, A) over the concatenation of all shards: shard-local single-pass
+    reduction + allreduce of one partial per GPU.  Float16/BFloat16 partials are combined in
+    Float32 and rounded once at the end.  Returns a host scalar (like `dims=:` does)."""
+    from .mapreduce import (add, add_sum, mul, mul_prod, max_, min_, and_, or_, _out_eltype)
+    ops = ops or DeviceOps()
+    out_et = _out_eltype(f, op, shard.eltype)
+    part_et = _acc_eltype(out_et)
+    partial = ops.reduce(f, op, shard, part_et)
+    red = {add: dist.ReduceOp.SUM, add_sum: dist.ReduceOp.SUM, mul: dist.ReduceOp.PRODUCT,
+           mul_prod: dist.ReduceOp.PRODUCT, max_: dist.ReduceOp.MAX, min_: dist.ReduceOp.MIN,
+           and_: dist.ReduceOp.BAND, or_: dist.ReduceOp.BOR}.get(op)
+    if red is None:
+        raise NotGraftedError(f"no collective for {op}")
+    t = partial.typed()
+    if t.dtype in (torch.uint32, torch.uint64):          # NCCL/gloo have no unsigned reductions: wrap-around add is bit-identical
+        if red not in (dist.ReduceOp.SUM, dist.ReduceOp.PRODUCT, dist.ReduceOp.BAND, dist.ReduceOp.BOR):
+            raise NotGraftedError("unsigned max/min across ranks")
+        t = t.view(torch.int32 if t.dtype == torch.uint32 else torch.int64)
+    if t.dtype == torch.bool:
+        t8 = t.view(torch.uint8)
+        dist.all_reduce(t8, op=dist.ReduceOp.MAX if red == dist.ReduceOp.BOR else dist.ReduceOp.MIN, group=group)
+    else:
+        dist.all_reduce(t, op=red, group=group)
+    host = partial.to_host().reshape(-1)[0]
+    return host.astype(dt.np_dtype(out_et)) if part_et != out_et else host
+
+
+def dist_extrema(shard, group=None, ops=None):
+    from .mapreduce import identity, max_, min_
+    return (dist_mapreduce(identity, min_, shard, group, ops), dist_mapreduce(identity, max_, shard, group, ops))
+
+
+# ----------------------------------------------------------------------------- scan
+def dist_accumulate(op, shard, exclusive=False, group=None, ops=None, out_eltype=None):
+    """accumulate(op, A) over the concatenation of all shards.  Each rank reduces its shard
+    (N reads), the G shard totals are all-gathered, every rank folds the totals of the ranks
+    before it into its carry, and scans its shard once with that carry as `init`
+    (N reads + N writes): 3N traffic instead of the 4N of scan-then-fix-up."""
+    from .mapreduce import identity, neutral_element
+    ops = ops or DeviceOps()
+    G, r = _world(group)
+    out_et = out_eltype if out_eltype is not None else shard.eltype
+    part_et = _acc_eltype(out_et)
+    total = ops.reduce(identity, op, shard, part_et)
+    gathered = CuArray.undef(part_et, (G,), shard.buf.device)
+    dist.all_gather_into_tensor(_typed(gathered), _typed(total), group=group) if hasattr(dist, "all_gather_into_tensor") \
+        and shard.buf.is_cuda else _all_gather_fallback(_typed(gathered), _typed(total), group)
+    out = shard.similar(out_et)
+    init = None
+    if r > 0:
+        before = CuArray(gathered.buf[:r * dt.SIZES[part_et]], (r,), part_et)
+        carry = ops.reduce(identity, op, before, part_et).to_host().reshape(-1)[0]
+        init = carry.astype(dt.np_dtype(out_et))
+    ops.scan(op, out, shard, init, exclusive)
+    return out
+
+
+def _all_gather_fallback(out_t, in_t, group):
+    G = dist.get_world_size(group)
+    parts = [torch.empty_like(in_t) for _ in range(G)]
+    dist.all_gather(parts, in_t, group=group)
+    out_t.copy_(torch.cat(parts))
+
+
+# ----------------------------------------------------------------------------- sort
+OVERSAMPLE = 32     # regular samples per rank and per destination
+
+
+def _exchange(c_sorted, bounds_host, group, extra=None):
+    """All-to-all of the G segments [bounds[k], bounds[k+1]) of a locally sorted shard."""
+    G, r = _world(group)
+    send_counts = torch.tensor(np.diff(bounds_host), dtype=torch.int64)
+    all_counts = [torch.empty(G, dtype=torch.int64) for _ in range(G)]
+    dev = c_sorted.buf.device
+    sc = send_counts.to(dev) if dev.type == "cuda" else send_counts
+    ac = [t.to(dev) for t in all_counts] if dev.type == "cuda" else all_counts
+    dist.all_gather(ac, sc, group=group)
+    counts = torch.stack(ac).cpu().numpy()               # counts[src, dst]
+    recv_counts = counts[:, r]
+    n_recv = int(recv_counts.sum())
+    outs = []
+    for c in (c_sorted,) + ((extra,) if extra is not None else ()):
+        t_in = _typed(c)
+        t_out = torch.empty(n_recv, dtype=t_in.dtype, device=dev)
+        dist.all_to_all_single(t_out, t_in, output_split_sizes=[int(x) for x in recv_counts],
+                               input_split_sizes=[int(x) for x in send_counts], group=group)
+        outs.append(CuArray(t_out.view(torch.uint8), (n_recv,), c.eltype))
+    return outs, counts
+
+
+def _splitters(c_sorted, rev, group, ops):
+    """G-1 splitter keys chosen identically on every rank from regular samples of the
+    locally sorted shards (samples are all-gathered and sorted with the library's sort)."""
+    G, r = _world(group)
+    n = c_sorted.length
+    S = OVERSAMPLE * G
+    dev = c_sorted.buf.device
+    tk = _typed(c_sorted)
+    if n > 0:
+        pos = torch.clamp(((torch.arange(S, dtype=torch.int64) + 1) * n) // (S + 1), max=n - 1).to(dev)
+        samples = tk[pos]
+        have = torch.ones(1, dtype=torch.int64, device=dev) * S
+    else:
+        samples = torch.zeros(S, dtype=tk.dtype, device=dev)
+        have = torch.zeros(1, dtype=torch.int64, device=dev)
+    all_s = [torch.empty_like(samples) for _ in range(G)]
+    all_h = [torch.empty_like(have) for _ in range(G)]
+    dist.all_gather(all_s, samples, group=group)
+    dist.all_gather(all_h, have, group=group)
+    pool = torch.cat([s for s, h in zip(all_s, all_h) if int(h.item()) > 0]) if any(int(h.item()) for h in all_h) \
+        else torch.zeros(0, dtype=tk.dtype, device=dev)
+    if pool.numel() == 0:
+        return None
+    cpool = CuArray(pool.contiguous().view(torch.uint8), (pool.numel(),), c_sorted.eltype)
+    ops.sort_keys(cpool, rev)
+    tp = _typed(cpool)
+    idx = torch.tensor([(k * pool.numel()) // G for k in range(1, G)], dtype=torch.int64, device=dev)
+    spl = tp[idx].contiguous()
+    return CuArray(spl.view(torch.uint8), (G - 1,), c_sorted.eltype)
+
+
+def dist_sort(shard, rev=False, group=None, ops=None):
+    """Distributed sample sort of the concatenation of all shards.  Returns this rank's slice of
+    the globally sorted sequence (slices are in rank order; their sizes are data dependent) and
+    the G x G matrix of exchanged counts."""
+    ops = ops or DeviceOps()
+    G, r = _world(group)
+    local = shard.copy()
+    ops.sort_keys(local, rev)
+    if G == 1:
+        return local, np.array([[local.length]])
+    spl = _splitters(local, rev, group, ops)
+    if spl is None:
+        return local, np.zeros((G, G), dtype=np.int64)
+    lb = ops.lower_bound(local, spl, rev).to_host().astype(np.int64)
+    bounds = np.concatenate([[0], lb, [local.length]])
+    (recv,), counts = _exchange(local, bounds, group)
+    ops.sort_keys(recv, rev)            # G sorted runs -> one (stable radix sort; a G-way merge is "next")
+    return recv, counts
+
+
+def dist_sortperm(shard, rev=False, group=None, ops=None):
+    """Distributed stable sortperm: returns this rank's slice of the global 1-based Int64
+    permutation.  The payload is the global index; equal keys keep ascending global index
+    because every stage (local sort, rank-ordered exchange, local sort) is stable."""
+    ops = ops or DeviceOps()
+    G, r = _world(group)
+    dev = shard.buf.device
+    n_local = torch.tensor([shard.length], dtype=torch.int64, device=dev)
+    sizes = [torch.empty_like(n_local) for _ in range(G)]
+    dist.all_gather(sizes, n_local, group=group)
+    offset = int(sum(int(s.item()) for s in sizes[:r]))
+    keys = shard.copy()
+    idx = torch.arange(offset + 1, offset + 1 + shard.length, dtype=torch.int64, device=dev)
+    payload = CuArray(idx.view(torch.uint8), (shard.length,), dt.I64)
+    ops.sort_pairs(keys, payload, rev)
+    if G == 1:
+        return payload
+    spl = _splitters(keys, rev, group, ops)
+    if spl is None:
+        return payload
+    lb = ops.lower_bound(keys, spl, rev).to_host().astype(np.int64)
+    bounds = np.concatenate([[0], lb, [keys.length]])
+    (rk, rp), _ = _exchange(keys, bounds, group, extra=payload)
+    ops.sort_pairs(rk, rp, rev)
+    return rp
