@@ -13,6 +13,7 @@ from .mapreduce import (identity, abs2, add_sum, mul_prod, add, mul, max_, min_,
                         extrema, count, any, all, sum_, prod_, maximum_, minimum_)
 from .accumulate import scan_, accumulate_, accumulate, cumsum, cumprod, cumsum_, cumprod_
 from .sorting import (isless, BitonicSort, QuickSort, sort_, sort, partialsort_, partialsort, sortperm_, sortperm)
+from .indexing import findall
 from . import multigpu
 from . import _lib
 

@@ -193,3 +193,15 @@ def test_unaligned_view(b):
     np.testing.assert_array_equal(b.Array(b.accumulate(b.add, v)), oracle.accumulate("add", base[1:]))
     M = rand("int32", (4099, 5))                                # odd segment length: segments unaligned
     check_scan(b, "add", M, dims=1)
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 4095, 4096, 4097, 100_003, (1 << 22) + 11])
+@pytest.mark.parametrize("p", [0.0, 0.5, 1.0, 0.01])
+def test_findall_fused_select(b, n, p):
+    """findall(::CuArray{Bool}) (CUDACore/src/indexing.jl:26-66): scan + compact in one pass."""
+    m = RNG.random(n) < p
+    got = b.Array(b.findall(b.CuArray(m)))
+    np.testing.assert_array_equal(got, oracle.findall(m))
+    if n >= 4096:
+        M = np.asfortranarray(m[: (n // 64) * 64].reshape(64, -1))
+        np.testing.assert_array_equal(b.Array(b.findall(b.CuArray(M))), oracle.findall(M))
