@@ -1,6 +1,6 @@
 // sort_inst.cu — one translation unit per key width (-DB200_KEY_BYTES=1|2|4|8).
 // Host orchestration of the onesweep passes for keys / sortperm / pairs.
-#include "sort.cuh"
+#include "sort_pipe.cuh"
 #include "sort_host.h"
 #include <cstdlib>
 
@@ -18,7 +18,38 @@ template <class V> static size_t onesweep_smem() {
     return s;
 }
 
+template <class V> static size_t pipe_smem() {
+    using VT = typename PayTraits<V>::type;
+    size_t s = (size_t)(RXP_STAGES + 2) * TILE * sizeof(K) + (size_t)RX_WARPS * RX_RADIX * 4 + 2 * RX_RADIX * 8;
+    if (PayTraits<V>::HAS) s += 2 * (size_t)TILE * sizeof(VT);
+    return s;
+}
+
+// Persistent pipelined pass: needs 16-byte aligned keys (TMA) and at least one full tile.
+template <class V, class LookT> static int32_t launch_pipe(const OnesweepParams &p, int64_t tiles, cudaStream_t st) {
+    auto kern = radix_onesweep_pipe_kernel<K, V, LookT, ITEMS>;
+    const size_t smem = pipe_smem<V>();
+    static thread_local bool attr_set[64];
+    int dev = 0;
+    B200_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[dev] = true;
+    }
+    int64_t per_sm = (int64_t)(220 * 1024 / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 3) per_sm = 3;
+    int64_t grid = (int64_t)devinfo().sm_count * per_sm;
+    if (grid > tiles) grid = tiles;
+    kern<<<(unsigned int)grid, RX_THREADS, smem, st>>>(p, (long long)tiles);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
 template <class V, class LookT> static int32_t launch_pass(const OnesweepParams &p, int64_t tiles, cudaStream_t st) {
+    static const bool use_pipe = getenv("B200_SORT_PIPE") != nullptr;   // persistent variant: measured slower (fewer warps per SM)
+    if (use_pipe && tiles >= 2 && (reinterpret_cast<uintptr_t>(p.keys_in) % 16) == 0 && pipe_smem<V>() <= 200 * 1024)
+        return launch_pipe<V, LookT>(p, tiles, st);
     auto kern = radix_onesweep_kernel<K, V, LookT, ITEMS>;
     const size_t smem = onesweep_smem<V>();
     static thread_local bool attr_set[64];
@@ -75,7 +106,15 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
         const int64_t need = cdiv(n, 512 * (16 / (int64_t)sizeof(K)));
         if (grid > need) grid = need;
         if (grid < 1) grid = 1;
-        radix_hist_kernel<K><<<(unsigned int)grid, 512, 0, st>>>(static_cast<const K *>(c.keys), n, c.xf, ghist);
+        constexpr size_t hist_smem = (size_t)P * RX_RADIX * RX_HIST_REPL * sizeof(unsigned int);
+        static thread_local bool hist_attr[64];
+        int hdev = 0;
+        B200_CUDA_TRY(cudaGetDevice(&hdev));
+        if (hdev >= 0 && hdev < 64 && !hist_attr[hdev]) {
+            B200_CUDA_TRY(cudaFuncSetAttribute(radix_hist_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+            hist_attr[hdev] = true;
+        }
+        radix_hist_kernel<K><<<(unsigned int)grid, 512, hist_smem, st>>>(static_cast<const K *>(c.keys), n, c.xf, ghist);
         B200_CHECK_LAUNCH();
         radix_bins_kernel<<<P, RX_RADIX, 0, st>>>(ghist, bins);
         B200_CHECK_LAUNCH();
