@@ -22,6 +22,7 @@
 // resident or finished (forward progress without relying on block scheduling order).
 #pragma once
 #include "ops.cuh"
+#include <cstdlib>
 
 namespace b200 {
 
@@ -715,6 +716,229 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
     }
 }
 
+// ------------------------------------------------------------------ warp-specialised pipeline
+// Same persistent TMA ring, but the look-back has its own warp: NT compute threads scan tiles
+// (pass 1 of tile i+1, pass 2 of tile i) while warp NT/32 resolves tile i's prefix, so a loaded
+// L2 round trip (~1.5 us under 5 TB/s of traffic) is hidden behind pass 1 instead of idling the
+// SM.  Compute warps and the look-back warp hand over through shared memory + mbarriers
+// (s_agg / s_prefix, two slots by tile parity); compute warps synchronise among themselves with
+// a named barrier so that the look-back warp never has to join a CTA-wide barrier.
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+
+template <class Tin, class Tout, class Op, int EPC, int K, int S, int NT, int LOOK>
+__global__ void __launch_bounds__(NT + 32) scan_pipe_ws_kernel(ScanParams p) {
+    using A = typename Op::acc_t;
+    constexpr int NWARPS = NT / 32;
+    constexpr int NW = StatusWords<A>::NW;
+    constexpr int WARP_ELEMS = 32 * EPC * K;
+    constexpr int TILE = NWARPS * WARP_ELEMS;
+    constexpr size_t STAGE_BYTES = (size_t)TILE * sizeof(Tin);
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    __shared__ __align__(8) uint64_t s_full[S];
+    __shared__ __align__(8) uint64_t s_agg_bar[2], s_prefix_bar[2];
+    __shared__ long long s_tile[S];        // ticket held by each stage
+    __shared__ int s_use[S];               // how many times the stage has been armed (barrier parity)
+    __shared__ A s_wexcl[2][NWARPS];       // warp-exclusive prefixes inside the tile: [tile parity][warp]
+    __shared__ A s_wtot[NWARPS];
+    __shared__ A s_agg[2];                 // tile aggregate            (compute -> look-back warp)
+    __shared__ long long s_agg_tile[2];    // its tile index, -1 = stop (compute -> look-back warp)
+    __shared__ A s_prefix[2];              // tile exclusive prefix     (look-back warp -> compute)
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool is_lb = warp == NWARPS;
+    const int64_t total = p.tiles_per_seg * p.post;
+    const int64_t wbase = (int64_t)warp * WARP_ELEMS;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int st = 0; st < S; ++st) { mbar_init(&s_full[st], 1); s_use[st] = 0; }
+        mbar_init(&s_agg_bar[0], 1); mbar_init(&s_agg_bar[1], 1);
+        mbar_init(&s_prefix_bar[0], 1); mbar_init(&s_prefix_bar[1], 1);
+        fence_proxy_async_smem();
+    }
+    __syncthreads();                       // the only CTA-wide barrier
+
+    if (is_lb) {
+        // ================= look-back warp =================
+        for (long long j = 0;; ++j) {
+            const int slot = (int)(j & 1);
+            mbar_wait(&s_agg_bar[slot], (uint32_t)((j >> 1) & 1));
+            const long long g = s_agg_tile[slot];
+            if (g < 0) break;
+            const A agg = s_agg[slot];
+            const int64_t seg = g / p.tiles_per_seg, t = g - seg * p.tiles_per_seg;
+            const A prefix = tile_lookback<Op, LOOK>(p, seg, t, lane, agg, /*publish_partial=*/false);
+            if (lane == 0) {
+                s_prefix[slot] = prefix;
+                mbar_arrive(&s_prefix_bar[slot]);       // release: s_prefix visible to the waiters
+            }
+            __syncwarp();
+        }
+        return;
+    }
+
+    // ================= compute warps =================
+    auto fill = [&](int stage, long long g) {
+        s_tile[stage] = g;
+        s_use[stage] += 1;
+        if (g < total) {
+            const int64_t seg = g / p.tiles_per_seg, t = g - seg * p.tiles_per_seg;
+            if (p.n - t * TILE >= TILE) {
+                mbar_expect_tx(&s_full[stage], (uint32_t)STAGE_BYTES);
+                tma_load_1d(s_dyn + stage * STAGE_BYTES, static_cast<const Tin *>(p.in) + seg * p.n + t * TILE,
+                            (uint32_t)STAGE_BYTES, &s_full[stage]);
+            } else {
+                mbar_arrive(&s_full[stage]);
+            }
+        }
+    };
+    auto pass1 = [&](int stage, A (&cpre)[K]) {
+        const long long g = s_tile[stage];
+        const int64_t seg = g / p.tiles_per_seg, t = g - seg * p.tiles_per_seg;
+        int64_t valid = p.n - t * TILE;
+        const bool full = valid >= TILE;
+        if (valid > TILE) valid = TILE;
+        Tin *s_in = reinterpret_cast<Tin *>(s_dyn + stage * STAGE_BYTES);
+        mbar_wait(&s_full[stage], (uint32_t)((s_use[stage] - 1) & 1));
+        A csum[K];
+        if (full) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                Tin e[EPC];
+                lds_chunk<Tin, EPC>(s_in + wbase + (k * 32 + lane) * EPC, e);
+                A acc = cvt<A>(e[0]);
+#pragma unroll
+                for (int q = 1; q < EPC; ++q) acc = Op::apply(acc, cvt<A>(e[q]));
+                csum[k] = acc;
+            }
+        } else {
+            const Tin *tin = static_cast<const Tin *>(p.in) + seg * p.n + t * TILE;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                A v[EPC];
+                load_chunk<Tin, A, Op, EPC>(tin, wbase + (k * 32 + lane) * EPC, valid, v);
+                Tin e[EPC];
+                A acc = v[0];
+                e[0] = cvt<Tin>(v[0]);
+#pragma unroll
+                for (int q = 1; q < EPC; ++q) { acc = Op::apply(acc, v[q]); e[q] = cvt<Tin>(v[q]); }
+                csum[k] = acc;
+                sts_chunk<Tin, EPC>(s_in + wbase + (k * 32 + lane) * EPC, e);
+            }
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                A up = shfl_up_any(csum[k], d);
+                if (lane >= d) csum[k] = Op::apply(up, csum[k]);
+            }
+        }
+        A run = Op::identity();
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            A excl = shfl_up_any(csum[k], 1);
+            A rtot = shfl_idx_any(csum[k], 31);
+            cpre[k] = lane == 0 ? run : Op::apply(run, excl);
+            run = Op::apply(run, rtot);
+        }
+        if (lane == 0) s_wtot[warp] = run;
+    };
+    // warp 0, after the compute barrier that follows pass1(stage): warp-exclusive prefixes, publish the
+    // aggregate to the other CTAs (status word) and hand it to the look-back warp (slot = tile parity)
+    auto finish_pass1 = [&](int stage, long long j) {
+        const long long g = s_tile[stage];
+        const int64_t seg = g / p.tiles_per_seg, t = g - seg * p.tiles_per_seg;
+        const int slot = (int)(j & 1);
+        A wincl = lane < NWARPS ? s_wtot[lane] : Op::identity();
+#pragma unroll
+        for (int d = 1; d < NWARPS; d <<= 1) {
+            A up = shfl_up_any(wincl, d);
+            if (lane >= d) wincl = Op::apply(up, wincl);
+        }
+        const A tile_agg = shfl_idx_any(wincl, NWARPS - 1);
+        A wexcl = shfl_up_any(wincl, 1);
+        if (lane == 0) wexcl = Op::identity();
+        if (lane < NWARPS) s_wexcl[slot][lane] = wexcl;
+        if (lane == 0) {
+            uint64_t *slots = p.status + seg * p.tiles_per_seg * NW;
+            if (t == 0) {
+                if (p.tiles_per_seg > 1) {
+                    const A seed = p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity();
+                    publish<A>(slots, SC_INCLUSIVE, Op::apply(seed, tile_agg));
+                }
+            } else {
+                publish<A>(slots + t * NW, SC_PARTIAL, tile_agg);
+            }
+            s_agg[slot] = tile_agg;
+            s_agg_tile[slot] = g;
+            mbar_arrive(&s_agg_bar[slot]);
+        }
+    };
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int st = 0; st < S; ++st) fill(st, (long long)atomicAdd(p.ticket, 1ull));
+    }
+    named_bar_sync(1, NT);
+    if (s_tile[0] >= total) {
+        if (threadIdx.x == 0) { s_agg_tile[0] = -1; mbar_arrive(&s_agg_bar[0]); }
+        return;
+    }
+
+    A cpre_cur[K], cpre_nxt[K];
+    pass1(0, cpre_cur);
+    named_bar_sync(1, NT);
+    if (warp == 0) finish_pass1(0, 0);
+
+    for (long long j = 0;; ++j) {                           // j = sequence number of the current tile in this CTA
+        const int stage = (int)(j % S);
+        const int nxt = (int)((j + 1) % S);
+        const int slot = (int)(j & 1);
+        const long long g = s_tile[stage];
+        const bool have_next = s_tile[nxt] < total;
+        long long next_ticket = 0;
+        if (threadIdx.x == 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);
+
+        // pass 1 of the next tile while the look-back warp resolves the current one
+        if (have_next) pass1(nxt, cpre_nxt);
+        named_bar_sync(1, NT);                              // (A) warp totals of the next tile visible
+        if (warp == 0) {
+            if (have_next) finish_pass1(nxt, j + 1);
+            else if (lane == 0) { s_agg_tile[slot ^ 1] = -1; mbar_arrive(&s_agg_bar[slot ^ 1]); }   // stop the look-back warp
+        }
+        mbar_wait(&s_prefix_bar[slot], (uint32_t)((j >> 1) & 1));   // prefix of the current tile
+        const A base = Op::apply(s_prefix[slot], s_wexcl[slot][warp]);
+
+        const int64_t seg = g / p.tiles_per_seg, t = g - seg * p.tiles_per_seg;
+        int64_t valid = p.n - t * TILE;
+        if (valid > TILE) valid = TILE;
+        Tout *tout = static_cast<Tout *>(p.out) + seg * p.n + t * TILE;
+        const Tin *s_in = reinterpret_cast<const Tin *>(s_dyn + stage * STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            Tin e[EPC];
+            lds_chunk<Tin, EPC>(s_in + wbase + (k * 32 + lane) * EPC, e);
+            A run2 = Op::apply(base, cpre_cur[k]);
+            A o[EPC];
+#pragma unroll
+            for (int q = 0; q < EPC; ++q) {
+                const A nxtv = Op::apply(run2, cvt<A>(e[q]));
+                o[q] = p.exclusive ? run2 : nxtv;
+                run2 = nxtv;
+            }
+            store_chunk<Tout, A, EPC>(tout, wbase + (k * 32 + lane) * EPC, valid, o);
+        }
+        named_bar_sync(1, NT);                              // (C) stage consumed; s_wtot free
+        if (threadIdx.x == 0) fill(stage, next_ticket);
+        if (!have_next) break;
+#pragma unroll
+        for (int k = 0; k < K; ++k) cpre_cur[k] = cpre_nxt[k];
+    }
+}
+
 // One thread per (i, j) column, marching along n.
 template <class Tin, class Tout, class Op>
 __global__ void __launch_bounds__(256) scan_strided_kernel(ScanParams p) {
@@ -815,10 +1039,15 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
         constexpr bool kWide = sizeof(A) > 4;
         constexpr int kStages = B200_SCAN_STAGES;
         constexpr int kThreads = kWide ? 256 : 512;
-        constexpr int kLook = kWide ? 4 : 5;
+#ifndef B200_SCAN_LOOK_NARROW
+#define B200_SCAN_LOOK_NARROW 3
+#endif
+        constexpr int kLook = kWide ? 4 : B200_SCAN_LOOK_NARROW;
         constexpr int64_t kTile = (int64_t)kThreads * S::EPC * S::K;
         constexpr size_t smem = (size_t)kTile * sizeof(Tin) * kStages;
-        auto kern = scan_pipe_kernel<Tin, Tout, Op, S::EPC, S::K, kStages, kThreads, kLook>;
+        static const bool use_ws = getenv("B200_SCAN_WS") != nullptr;   // warp-specialised variant: opt-in (measured slower)
+        auto kern = use_ws ? scan_pipe_ws_kernel<Tin, Tout, Op, S::EPC, S::K, kStages, kThreads, kLook>
+                           : scan_pipe_kernel<Tin, Tout, Op, S::EPC, S::K, kStages, kThreads, kLook>;
         static thread_local int attr_dev_mask[64];  // cudaFuncSetAttribute once per (thread, device, instantiation)
         int dev = 0;
         B200_CUDA_TRY(cudaGetDevice(&dev));
@@ -830,7 +1059,7 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
         const int64_t ptiles = p.tiles_per_seg * post;
         int64_t pgrid = (int64_t)devinfo().sm_count * ((200 * 1024) / (int64_t)smem > 0 ? (200 * 1024) / (int64_t)smem : 1);
         if (pgrid > ptiles) pgrid = ptiles;
-        kern<<<(unsigned int)pgrid, kThreads, smem, stream>>>(p);
+        kern<<<(unsigned int)pgrid, use_ws ? kThreads + 32 : kThreads, smem, stream>>>(p);
     }
     else scan_contig_kernel<Tin, Tout, Op, 1, S::K1><<<(unsigned int)grid, SC_THREADS, 0, stream>>>(p);
     B200_CHECK_LAUNCH();
