@@ -969,6 +969,69 @@ __global__ void __launch_bounds__(256) scan_strided_kernel(ScanParams p) {
     }
 }
 
+// Strided scan with look-back along n: for few, long columns (e.g.
+// accumulate(A; dims=2) on a 16384 x 16384 matrix) one thread per column cannot fill the GPU.
+// A CTA owns a 256-column x SS_ROWS-row tile; every thread scans its column's SS_ROWS values in
+// registers (row loads are coalesced across the CTA), publishes the column aggregate and resolves
+// its own look-back chain over the tiles above (same status words as the 1-D scan, one chain per
+// column).  Tickets are row-tile major, so every predecessor of a tile holds a smaller ticket.
+constexpr int SS_ROWS = 32;
+
+template <class Tin, class Tout, class Op>
+__global__ void __launch_bounds__(256) scan_strided_lb_kernel(ScanParams p, int64_t ncb, int64_t nrt) {
+    using A = typename Op::acc_t;
+    constexpr int NW = StatusWords<A>::NW;
+    __shared__ unsigned long long s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(p.ticket, 1ull);
+    __syncthreads();
+    const int64_t g = (int64_t)s_ticket;
+    const int64_t rt = g / ncb, cb = g - rt * ncb;
+    const int64_t cols = p.pre * p.post;
+    const int64_t c = cb * 256 + threadIdx.x;
+    if (c >= cols) return;
+    const int64_t j = c / p.pre, i = c - j * p.pre;
+    const int64_t r0 = rt * SS_ROWS;
+    const int rows = (int)((p.n - r0) < SS_ROWS ? (p.n - r0) : SS_ROWS);
+    const Tin *in = static_cast<const Tin *>(p.in) + i + p.pre * (r0 + p.n * j);
+    Tout *out = static_cast<Tout *>(p.out) + i + p.pre * (r0 + p.n * j);
+    A v[SS_ROWS];
+#pragma unroll
+    for (int r = 0; r < SS_ROWS; ++r) v[r] = r < rows ? cvt<A>(ld_coh(in + p.pre * r)) : Op::identity();
+#pragma unroll
+    for (int r = 1; r < SS_ROWS; ++r) v[r] = Op::apply(v[r - 1], v[r]);
+    const A agg = v[SS_ROWS - 1];
+    uint64_t *slots = p.status + c * NW;                    // slot of (rt, c) = status[(rt * cols + c) * NW]
+    const int64_t rstride = cols * NW;
+    A prefix;
+    if (rt == 0) {
+        prefix = p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity();
+        if (nrt > 1) publish<A>(slots, SC_INCLUSIVE, Op::apply(prefix, agg));
+    } else {
+        publish<A>(slots + rt * rstride, SC_PARTIAL, agg);
+        prefix = Op::identity();
+        int64_t u = rt - 1;
+        while (true) {
+            A val;
+            uint32_t flag;
+            do { flag = peek_slot<A>(slots + u * rstride, val); } while (flag == SC_INVALID);
+            prefix = Op::apply(val, prefix);
+            if (flag == SC_INCLUSIVE) break;
+            --u;
+        }
+        publish<A>(slots + rt * rstride, SC_INCLUSIVE, Op::apply(prefix, agg));
+    }
+    if (!p.exclusive) {
+#pragma unroll
+        for (int r = 0; r < SS_ROWS; ++r)
+            if (r < rows) out[p.pre * r] = cvt<Tout>(Op::apply(prefix, v[r]));
+    } else {
+        if (rows > 0) out[0] = cvt<Tout>(prefix);
+#pragma unroll
+        for (int r = 1; r < SS_ROWS; ++r)
+            if (r < rows) out[p.pre * r] = cvt<Tout>(Op::apply(prefix, v[r - 1]));
+    }
+}
+
 // ------------------------------------------------------------------ host
 template <class Tin, class Tout> struct ScanShape {
     static constexpr int WIDE = sizeof(Tin) > sizeof(Tout) ? sizeof(Tin) : sizeof(Tout);
@@ -996,11 +1059,27 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
         memcpy(&p.init_bits, &a, sizeof(A));
     }
     if (pre > 1) {
-        if (query_bytes) { *query_bytes = 0; return B200_OK; }
         const int64_t cols = pre * post;
-        const int64_t grid = cdiv(cols, 256);
-        if (grid > 2147483647LL) return B200_INVALID_VALUE;
-        scan_strided_kernel<Tin, Tout, Op><<<(unsigned int)grid, 256, 0, stream>>>(p);
+        // enough columns to fill the machine, or columns too short to tile: one thread per column
+        const bool use_lb = n >= 4 * SS_ROWS && cols < 2048LL * devinfo().sm_count;
+        const int64_t ncb = cdiv(cols, 256), nrt = cdiv(n, SS_ROWS);
+        Carver c(ws);
+        unsigned long long *ticket = c.take<unsigned long long>(1);
+        uint64_t *status = c.take<uint64_t>((size_t)(use_lb ? nrt * cols * NW : 0));
+        if (query_bytes) { *query_bytes = use_lb ? c.bytes() : 0; return B200_OK; }
+        if (!use_lb) {
+            const int64_t grid = cdiv(cols, 256);
+            if (grid > 2147483647LL) return B200_INVALID_VALUE;
+            scan_strided_kernel<Tin, Tout, Op><<<(unsigned int)grid, 256, 0, stream>>>(p);
+            B200_CHECK_LAUNCH();
+            return B200_OK;
+        }
+        if (c.bytes() > ws_bytes) return B200_WORKSPACE_TOO_SMALL;
+        if (ws == nullptr) return B200_INVALID_VALUE;
+        if (ncb * nrt > 2147483647LL) return B200_INVALID_VALUE;
+        p.status = status; p.ticket = ticket;
+        B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, c.bytes(), stream));
+        scan_strided_lb_kernel<Tin, Tout, Op><<<(unsigned int)(ncb * nrt), 256, 0, stream>>>(p, ncb, nrt);
         B200_CHECK_LAUNCH();
         return B200_OK;
     }

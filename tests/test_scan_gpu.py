@@ -205,3 +205,15 @@ def test_findall_fused_select(b, n, p):
     if n >= 4096:
         M = np.asfortranarray(m[: (n // 64) * 64].reshape(64, -1))
         np.testing.assert_array_equal(b.Array(b.findall(b.CuArray(M))), oracle.findall(M))
+
+
+@pytest.mark.parametrize("dtype", ["int64", "float32", "int32"])
+@pytest.mark.parametrize("shape,dims", [((300, 4097), 2), ((2048, 1500), 2), ((7, 1000, 9), 2), ((1, 5000, 3), 2),
+                                        ((129, 129, 129), 3)])
+def test_strided_lookback_scan(b, dtype, shape, dims):
+    """accumulate(op, A; dims) with dims > 1 on few, long columns: per-column look-back chains."""
+    A = rand(dtype, shape)
+    check_scan(b, "add", A, dims=dims)
+    check_scan(b, "add", A, dims=dims, exclusive=True, init=npdt(dtype).type(2))
+    if dtype != "float32":
+        check_scan(b, "max", A, dims=dims)

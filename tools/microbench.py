@@ -95,6 +95,15 @@ def scan_cases():
         del V, O, Vt, Ot
 
 
+def scan_dims_cases():
+    for e, name in ((dt.F32, "F32"), (dt.I64, "I64")):
+        A = rand_array(e, (16384, 16384 if e == dt.F32 else 8192))
+        O = b.CuArray.undef(e, A.dims)
+        for d in (1, 2):
+            report(f"cumsum dims={d} {A.dims} {name}", 2 * A.nbytes, *timeit(lambda: b.accumulate_(b.add, O, A, dims=d), reps=5))
+        del A, O
+
+
 def sort_cases():
     n = 1 << 30
     for e, name in ((dt.U32, "U32"), (dt.F32, "F32")):
@@ -123,4 +132,4 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["reduce"]
     torch.cuda.set_device(0)
     for w in which:
-        {"reduce": reduce_cases, "scan": scan_cases, "sort": sort_cases}[w]()
+        {"reduce": reduce_cases, "scan": scan_cases, "scan_dims": scan_dims_cases, "sort": sort_cases}[w]()
