@@ -29,6 +29,9 @@ SIGNATURES = {
     "b200_sort_workspace_bytes": (_i32, [_i32, _i32, _i64, _i64, _c.POINTER(_sz)]),
     "b200_sort_keys": (_i32, [_vp, _sz, _vp, _i32, _i64, _i64, _i32, _vp]),
     "b200_sortperm": (_i32, [_vp, _sz, _vp, _vp, _i32, _i32, _i64, _i64, _i32, _i32, _vp]),
+    "b200_sort_dims_workspace_bytes": (_i32, [_i32, _i32, _i64, _i64, _i64, _c.POINTER(_sz)]),
+    "b200_sort_keys_dims": (_i32, [_vp, _sz, _vp, _i32, _i64, _i64, _i64, _i32, _vp]),
+    "b200_sortperm_dims": (_i32, [_vp, _sz, _vp, _vp, _i32, _i32, _i64, _i64, _i64, _i32, _i32, _vp]),
     "b200_sort_pairs": (_i32, [_vp, _sz, _vp, _vp, _i32, _i32, _i64, _i32, _vp]),
     "b200_search_sorted": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp]),
     "b200_select_workspace_bytes": (_i32, [_i64, _c.POINTER(_sz)]),

@@ -46,70 +46,171 @@ static bool index_dtype_ok(int d) { return d == B200_I32 || d == B200_I64 || d =
 
 extern "C" {
 
+// ---- general (pre, n, post) machinery ------------------------------------------------
+}  // extern "C"  (helpers below are C++)
+
+namespace b200 {
+
+static int32_t run_block(int kb, const BlockSortParams &bp, int perm, int64_t nseg, cudaStream_t st) {
+    switch (kb) {
+        case 1: return block_sort_k1(bp, perm, nseg, st);
+        case 2: return block_sort_k2(bp, perm, nseg, st);
+        case 4: return block_sort_k4(bp, perm, nseg, st);
+        case 8: return block_sort_k8(bp, perm, nseg, st);
+        default: return B200_UNSUPPORTED;
+    }
+}
+
+template <class T>
+static int32_t transpose_T(const void *in, void *out, int64_t rows, int64_t cols, int64_t batch, cudaStream_t st) {
+    if (batch > 65535 || cdiv(cols, 32) > 65535) return B200_INVALID_VALUE;
+    dim3 grid((unsigned int)cdiv(rows, 32), (unsigned int)cdiv(cols, 32), (unsigned int)batch);
+    transpose_batched_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(in), static_cast<T *>(out), rows, cols);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+static int32_t transpose_bytes(int elem, const void *in, void *out, int64_t rows, int64_t cols, int64_t batch, cudaStream_t st) {
+    switch (elem) {
+        case 1: return transpose_T<uint8_t>(in, out, rows, cols, batch, st);
+        case 2: return transpose_T<uint16_t>(in, out, rows, cols, batch, st);
+        case 4: return transpose_T<uint32_t>(in, out, rows, cols, batch, st);
+        case 8: return transpose_T<uint64_t>(in, out, rows, cols, batch, st);
+        default: return B200_UNSUPPORTED;
+    }
+}
+
+// mode: SORT_KEYS or SORT_PERM.  Strategy: n <= 4096 -> one CTA per segment (any stride);
+// contiguous long segments -> device-wide onesweep per segment; strided long segments ->
+// transpose, sort the now contiguous segments, transpose / scatter back.
+static int32_t sort_dims(void *ws, size_t wsb, void *keys, void *perm, int dtype_key, int dtype_index, int mode,
+                         int64_t pre, int64_t n, int64_t post, int descending, int linear, cudaStream_t st,
+                         size_t *query) {
+    SortXform xf; int kb;
+    if (!make_xform(dtype_key, descending, mode == SORT_PERM ? 1 : 0, xf, kb)) return B200_UNSUPPORTED;
+    if (mode == SORT_PERM && !index_dtype_ok(dtype_index)) return B200_UNSUPPORTED;
+    if (query) *query = 0;
+    const int64_t nseg = pre * post;
+    if (n == 0 || nseg == 0) return B200_OK;
+    if (mode == SORT_KEYS && n == 1) return B200_OK;
+    const int ib = mode == SORT_PERM ? dtype_size(dtype_index) : 0;
+    if (mode == SORT_PERM && ib == 4 && (linear ? n * nseg : n) > 0x7FFFFFFFLL) return B200_INVALID_VALUE;
+
+    if (n <= RB_TILE) {
+        if (query) return B200_OK;
+        BlockSortParams bp{};
+        bp.keys_in = keys; bp.keys_out = keys; bp.perm_out = perm;
+        bp.pre = pre; bp.n = n; bp.post = post; bp.xf = xf; bp.index_dtype = dtype_index; bp.linear = linear;
+        return run_block(kb, bp, mode == SORT_PERM, nseg, st);
+    }
+    // inner device-wide sort of one contiguous segment
+    SortCall inner{};
+    inner.mode = mode; inner.n = n; inner.xf = xf; inner.stream = st;
+    inner.index_dtype = (pre == 1) ? dtype_index : B200_I64;
+    size_t inner_bytes = 0;
+    inner.query = &inner_bytes;
+    int32_t rc = run(kb, inner);
+    if (rc != B200_OK) return rc;
+    inner.query = nullptr;
+
+    Carver c(ws);
+    char *inner_ws = c.take<char>(inner_bytes);
+    char *tkeys = pre > 1 ? c.take<char>((size_t)n * nseg * kb) : nullptr;
+    long long *tperm = (pre > 1 && mode == SORT_PERM) ? c.take<long long>((size_t)n * nseg) : nullptr;
+    if (query) { *query = c.bytes(); return B200_OK; }
+    if (c.bytes() > wsb) return B200_WORKSPACE_TOO_SMALL;
+    if (ws == nullptr) return B200_INVALID_VALUE;
+    inner.ws = inner_ws; inner.ws_bytes = inner_bytes;
+
+    char *kbase = static_cast<char *>(keys);
+    if (pre > 1) {   // (pre, n, post) -> (n, pre, post): segments become contiguous
+        rc = transpose_bytes(kb, keys, tkeys, pre, n, post, st);
+        if (rc != B200_OK) return rc;
+        kbase = tkeys;
+    }
+    for (int64_t s = 0; s < nseg; ++s) {
+        inner.keys = kbase + (size_t)s * n * kb;
+        if (mode == SORT_PERM) {
+            if (pre == 1) {
+                inner.payload = static_cast<char *>(perm) + (size_t)s * n * ib;
+                inner.index_base = 1 + (linear ? s * n : 0);
+            } else {
+                inner.payload = tperm + (size_t)s * n;
+                inner.index_base = 1;
+            }
+        }
+        rc = run(kb, inner);
+        if (rc != B200_OK) return rc;
+    }
+    if (pre > 1) {
+        if (mode == SORT_KEYS) return transpose_bytes(kb, tkeys, keys, n, pre, post, st);
+        const int64_t total = n * nseg;
+        if (cdiv(total, 256) > 2147483647LL) return B200_INVALID_VALUE;
+        if (ib == 8) perm_scatter_kernel<long long><<<(unsigned int)cdiv(total, 256), 256, 0, st>>>(tperm, static_cast<long long *>(perm), pre, n, post, linear);
+        else perm_scatter_kernel<int><<<(unsigned int)cdiv(total, 256), 256, 0, st>>>(tperm, static_cast<int *>(perm), pre, n, post, linear);
+        B200_CHECK_LAUNCH();
+    }
+    return B200_OK;
+}
+
+}  // namespace b200
+
+extern "C" {
+
+int32_t b200_sort_dims_workspace_bytes(int32_t dtype_key, int32_t sortperm, int64_t pre, int64_t n, int64_t post,
+                                       size_t *bytes) {
+    using namespace b200;
+    if (!bytes || pre < 0 || n < 0 || post < 0) return B200_INVALID_VALUE;
+    *bytes = 0;
+    return sort_dims(nullptr, 0, nullptr, nullptr, dtype_key, B200_I64, sortperm ? SORT_PERM : SORT_KEYS, pre, n, post,
+                     0, 0, nullptr, bytes);
+}
+
+int32_t b200_sort_keys_dims(void *workspace, size_t workspace_bytes, void *keys, int32_t dtype_key, int64_t pre,
+                            int64_t n, int64_t post, int32_t descending, b200_stream_t stream) {
+    using namespace b200;
+    if (pre < 0 || n < 0 || post < 0) return B200_INVALID_VALUE;
+    if (pre * n * post > 0 && n > 1 && !keys) return B200_INVALID_VALUE;
+    return sort_dims(workspace, workspace_bytes, keys, nullptr, dtype_key, B200_I64, SORT_KEYS, pre, n, post, descending,
+                     0, reinterpret_cast<cudaStream_t>(stream), nullptr);
+}
+
+int32_t b200_sortperm_dims(void *workspace, size_t workspace_bytes, const void *keys, void *perm, int32_t dtype_key,
+                           int32_t dtype_index, int64_t pre, int64_t n, int64_t post, int32_t descending,
+                           int32_t linear, b200_stream_t stream) {
+    using namespace b200;
+    if (pre < 0 || n < 0 || post < 0) return B200_INVALID_VALUE;
+    if (pre * n * post > 0 && (!keys || !perm)) return B200_INVALID_VALUE;
+    return sort_dims(workspace, workspace_bytes, const_cast<void *>(keys), perm, dtype_key, dtype_index, SORT_PERM, pre, n,
+                     post, descending, linear, reinterpret_cast<cudaStream_t>(stream), nullptr);
+}
+
 int32_t b200_sort_workspace_bytes(int32_t dtype_key, int32_t dtype_payload, int64_t n, int64_t nseg, size_t *bytes) {
     using namespace b200;
     if (!bytes || n < 0 || nseg < 0) return B200_INVALID_VALUE;
     *bytes = 0;
+    if (dtype_payload < 0) return b200_sort_dims_workspace_bytes(dtype_key, 0, 1, n, nseg, bytes);
+    if (dtype_payload == B200_SORTPERM_INDEX) return b200_sort_dims_workspace_bytes(dtype_key, 1, 1, n, nseg, bytes);
     SortXform xf; int kb;
     if (!make_xform(dtype_key, 0, 0, xf, kb)) return B200_UNSUPPORTED;
-    if (n == 0 || nseg == 0) return B200_OK;
+    if (n == 0) return B200_OK;
     SortCall c{};
     c.n = n; c.xf = xf; c.query = bytes;
-    if (dtype_payload < 0) c.mode = SORT_KEYS;
-    else if (dtype_payload == B200_SORTPERM_INDEX) c.mode = SORT_PERM;
-    else {
-        c.mode = SORT_PAIRS;
-        c.payload_bytes = dtype_size(dtype_payload);
-        if (c.payload_bytes != 4 && c.payload_bytes != 8) return B200_UNSUPPORTED;
-    }
-    return run(kb, c);   // segments are sorted one after the other and share the workspace
+    c.mode = SORT_PAIRS;
+    c.payload_bytes = dtype_size(dtype_payload);
+    if (c.payload_bytes != 4 && c.payload_bytes != 8) return B200_UNSUPPORTED;
+    return run(kb, c);
 }
 
 int32_t b200_sort_keys(void *workspace, size_t workspace_bytes, void *keys, int32_t dtype_key, int64_t n, int64_t nseg,
                        int32_t descending, b200_stream_t stream) {
-    using namespace b200;
-    if (n < 0 || nseg < 0) return B200_INVALID_VALUE;
-    SortXform xf; int kb;
-    if (!make_xform(dtype_key, descending, 0, xf, kb)) return B200_UNSUPPORTED;
-    if (n <= 1 || nseg == 0) return B200_OK;
-    if (!keys) return B200_INVALID_VALUE;
-    for (int64_t s = 0; s < nseg; ++s) {
-        SortCall c{};
-        c.ws = workspace; c.ws_bytes = workspace_bytes;
-        c.keys = static_cast<char *>(keys) + (size_t)s * n * kb;
-        c.mode = SORT_KEYS; c.n = n; c.xf = xf;
-        c.stream = reinterpret_cast<cudaStream_t>(stream);
-        int32_t rc = run(kb, c);
-        if (rc != B200_OK) return rc;
-    }
-    return B200_OK;
+    return b200_sort_keys_dims(workspace, workspace_bytes, keys, dtype_key, 1, n, nseg, descending, stream);
 }
 
 int32_t b200_sortperm(void *workspace, size_t workspace_bytes, const void *keys, void *perm, int32_t dtype_key,
                       int32_t dtype_index, int64_t n, int64_t nseg, int32_t descending, int32_t linear,
                       b200_stream_t stream) {
-    using namespace b200;
-    if (n < 0 || nseg < 0) return B200_INVALID_VALUE;
-    SortXform xf; int kb;
-    if (!make_xform(dtype_key, descending, 1, xf, kb)) return B200_UNSUPPORTED;
-    if (!index_dtype_ok(dtype_index)) return B200_UNSUPPORTED;
-    if (n == 0 || nseg == 0) return B200_OK;
-    if (!keys || !perm) return B200_INVALID_VALUE;
-    const int ib = dtype_size(dtype_index);
-    if (ib == 4 && (linear ? n * nseg : n) > 0x7FFFFFFFLL) return B200_INVALID_VALUE;
-    for (int64_t s = 0; s < nseg; ++s) {
-        SortCall c{};
-        c.ws = workspace; c.ws_bytes = workspace_bytes;
-        c.keys = const_cast<char *>(static_cast<const char *>(keys)) + (size_t)s * n * kb;
-        c.payload = static_cast<char *>(perm) + (size_t)s * n * ib;
-        c.mode = SORT_PERM; c.n = n; c.xf = xf;
-        c.index_dtype = dtype_index;
-        c.index_base = 1 + (linear ? s * n : 0);
-        c.stream = reinterpret_cast<cudaStream_t>(stream);
-        int32_t rc = run(kb, c);
-        if (rc != B200_OK) return rc;
-    }
-    return B200_OK;
+    return b200_sortperm_dims(workspace, workspace_bytes, keys, perm, dtype_key, dtype_index, 1, n, nseg, descending,
+                              linear, stream);
 }
 
 int32_t b200_sort_pairs(void *workspace, size_t workspace_bytes, void *keys, void *payload, int32_t dtype_key,

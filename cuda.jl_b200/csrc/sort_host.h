@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "sort.cuh"
+#include "sort_block.cuh"
 
 namespace b200 {
 
@@ -26,6 +27,10 @@ int32_t sort_run_k1(const SortCall &);
 int32_t sort_run_k2(const SortCall &);
 int32_t sort_run_k4(const SortCall &);
 int32_t sort_run_k8(const SortCall &);
+int32_t block_sort_k1(const BlockSortParams &, int, int64_t, cudaStream_t);
+int32_t block_sort_k2(const BlockSortParams &, int, int64_t, cudaStream_t);
+int32_t block_sort_k4(const BlockSortParams &, int, int64_t, cudaStream_t);
+int32_t block_sort_k8(const BlockSortParams &, int, int64_t, cudaStream_t);
 int32_t lower_bound_k1(const void *, int64_t, const void *, int64_t, const SortXform &, long long *, cudaStream_t);
 int32_t lower_bound_k2(const void *, int64_t, const void *, int64_t, const SortXform &, long long *, cudaStream_t);
 int32_t lower_bound_k4(const void *, int64_t, const void *, int64_t, const SortXform &, long long *, cudaStream_t);

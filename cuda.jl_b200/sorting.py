@@ -38,33 +38,34 @@ def _guard(lt, by, alg):
         raise NotGraftedError("alg=QuickSort stays on the reference path")
 
 
-def _segments(c, dims):
-    """(n, nseg) for sorting along `dims` when the segments are contiguous (dims == 1 or a vector)."""
+def _factor(c, dims):
+    """(pre, n, post) of sorting along `dims` (1-based); vectors: dims in (None, 1)."""
     if c.ndims <= 1:
         if dims not in (None, 1):
             raise ArgumentError("dimension out of range")
-        return c.length, 1
+        return 1, c.length, 1
     if dims is None:
         raise NotGraftedError("sort! of a multidimensional array needs dims (Base raises UndefKeywordError)")
-    if dims != 1:
-        # SURVEY §8 f2: segmented sorts along non-leading dims are "next"
-        raise NotGraftedError("sort along a non-leading dimension is not grafted yet")
-    n = c.dims[0]
-    return n, (c.length // n if n else 0)
+    if not 1 <= dims <= c.ndims:
+        raise ArgumentError("dimension out of range")
+    pre = int(np.prod(c.dims[:dims - 1], dtype=np.int64))
+    n = int(c.dims[dims - 1])
+    post = int(np.prod(c.dims[dims:], dtype=np.int64))
+    return pre, n, post
 
 
 def sort_(c, alg=BitonicSort, lt=isless, by=identity, rev=False, dims=None):
     """Base.sort!(c::AnyCuArray; alg=BitonicSort, lt, by, rev, dims) (sorting.jl:1003-1009)."""
     _guard(lt, by, alg)
-    n, nseg = _segments(c, dims)
-    if n <= 1 or nseg == 0:
+    pre, n, post = _factor(c, dims)
+    if n <= 1 or pre * post == 0:
         return c
     lib = _lib.load()
     nbytes = ctypes.c_size_t(0)
-    _lib.check(lib.b200_sort_workspace_bytes(c.eltype, -1, n, nseg, ctypes.byref(nbytes)))
+    _lib.check(lib.b200_sort_dims_workspace_bytes(c.eltype, 0, pre, n, post, ctypes.byref(nbytes)))
     ws = Workspace(nbytes.value, c.buf.device)
-    _lib.check(lib.b200_sort_keys(ws.ptr, ws.nbytes, c.pointer, c.eltype, n, nseg, 1 if rev else 0,
-                                  current_stream_handle(c.buf.device)))
+    _lib.check(lib.b200_sort_keys_dims(ws.ptr, ws.nbytes, c.pointer, c.eltype, pre, n, post, 1 if rev else 0,
+                                       current_stream_handle(c.buf.device)))
     return c
 
 
@@ -115,13 +116,13 @@ def sortperm_(ix, A, initialized=False, alg=BitonicSort, lt=isless, by=identity,
         raise NotGraftedError("sortperm!(...; initialized=true) stays on the reference path")
     if ix.eltype not in (dt.I32, dt.I64, dt.U32, dt.U64):
         raise NotGraftedError("index eltype must be a 32/64-bit integer")
-    n, nseg = _segments(A, dims)
+    pre, n, post = _factor(A, dims)
     lib = _lib.load()
     nbytes = ctypes.c_size_t(0)
-    _lib.check(lib.b200_sort_workspace_bytes(A.eltype, SORTPERM_INDEX, n, nseg, ctypes.byref(nbytes)))
+    _lib.check(lib.b200_sort_dims_workspace_bytes(A.eltype, 1, pre, n, post, ctypes.byref(nbytes)))
     ws = Workspace(nbytes.value, A.buf.device)
-    _lib.check(lib.b200_sortperm(ws.ptr, ws.nbytes, A.pointer, ix.pointer, A.eltype, ix.eltype, n, nseg,
-                                 1 if rev else 0, 1 if A.ndims > 1 else 0, current_stream_handle(A.buf.device)))
+    _lib.check(lib.b200_sortperm_dims(ws.ptr, ws.nbytes, A.pointer, ix.pointer, A.eltype, ix.eltype, pre, n, post,
+                                      1 if rev else 0, 1 if A.ndims > 1 else 0, current_stream_handle(A.buf.device)))
     return ix
 
 

@@ -178,6 +178,18 @@ int32_t b200_sortperm(void *workspace, size_t workspace_bytes,
                       const void *keys, void *perm,
                       int32_t dtype_key, int32_t dtype_index, int64_t n, int64_t nseg,
                       int32_t descending, int32_t linear, b200_stream_t stream);
+/* General (pre, n, post) forms: sort!(A; dims) / sortperm(A; dims) along ANY dimension
+ * (sorting.jl:909-974 with dims; tests test/core/sorting.jl:314-315,388-392).  Segments of up
+ * to 4096 keys are sorted by one CTA each, whatever their stride; longer strided segments are
+ * transposed, sorted and transposed back.  b200_sort_keys / b200_sortperm are the pre == 1 case. */
+int32_t b200_sort_dims_workspace_bytes(int32_t dtype_key, int32_t sortperm, int64_t pre, int64_t n,
+                                       int64_t post, size_t *bytes);
+int32_t b200_sort_keys_dims(void *workspace, size_t workspace_bytes, void *keys, int32_t dtype_key,
+                            int64_t pre, int64_t n, int64_t post, int32_t descending,
+                            b200_stream_t stream);
+int32_t b200_sortperm_dims(void *workspace, size_t workspace_bytes, const void *keys, void *perm,
+                           int32_t dtype_key, int32_t dtype_index, int64_t pre, int64_t n,
+                           int64_t post, int32_t descending, int32_t linear, b200_stream_t stream);
 /* Sorts keys in place and permutes `payload` (4- or 8-byte elements, dtype
  * I32/U32/I64/U64/F32/F64 treated as raw bits) along with them. */
 int32_t b200_sort_pairs(void *workspace, size_t workspace_bytes,

@@ -76,6 +76,26 @@ function b200_sortperm(ws, ws_bytes, keys, perm, dkey, dindex, n, nseg, descendi
               linear::Int32, s::CUDACore.CUstream)::Int32)
 end
 
+function b200_sort_dims_workspace_bytes(dkey, sortperm, pre, n, post)
+    bytes = Ref{Csize_t}(0)
+    check(@ccall libb200arrays[].b200_sort_dims_workspace_bytes(dkey::Int32, sortperm::Int32, pre::Int64, n::Int64,
+              post::Int64, bytes::Ref{Csize_t})::Int32)
+    return Int(bytes[])
+end
+
+function b200_sort_keys_dims(ws, ws_bytes, keys, dkey, pre, n, post, descending, s::CuStream)
+    initialize_context()
+    check(@gcsafe_ccall libb200arrays[].b200_sort_keys_dims(ws::CuPtr{Cvoid}, ws_bytes::Csize_t, keys::CuPtr{Cvoid},
+              dkey::Int32, pre::Int64, n::Int64, post::Int64, descending::Int32, s::CUDACore.CUstream)::Int32)
+end
+
+function b200_sortperm_dims(ws, ws_bytes, keys, perm, dkey, dindex, pre, n, post, descending, linear, s::CuStream)
+    initialize_context()
+    check(@gcsafe_ccall libb200arrays[].b200_sortperm_dims(ws::CuPtr{Cvoid}, ws_bytes::Csize_t, keys::CuPtr{Cvoid},
+              perm::CuPtr{Cvoid}, dkey::Int32, dindex::Int32, pre::Int64, n::Int64, post::Int64, descending::Int32,
+              linear::Int32, s::CUDACore.CUstream)::Int32)
+end
+
 # Temporaries come from CUDA.jl's stream-ordered pool, freed in stream order
 # (with_workspace, CUDACore/src/utils/call.jl:23-103).
 function with_ws(f, bytes::Int)

@@ -1,20 +1,21 @@
-# Base.sort! / sortperm! / partialsort! for dense CuVectors (and dims=1 of matrices) with
+# Base.sort! / sortperm! / partialsort! for dense CuArrays along any `dims` with
 # lt=isless, by=identity — replaces the bitonic path of CUDACore/src/sorting.jl:1003-1070.
 # kwargs do not dispatch, so each hook guards at run time and `invoke`s the reference
-# method otherwise (custom lt/by, alg=QuickSort, user-supplied initialized=true, other dims).
+# method otherwise (custom lt/by, alg=QuickSort, user-supplied initialized=true).
 
 graftable(lt, by, alg) = lt === isless && by === identity && alg === CUDACore.BitonicSort
 
 function Base.sort!(c::CuArray{T}; alg::CUDACore.SortingAlgorithm=CUDACore.BitonicSort, lt=isless, by=identity,
                     rev::Bool=false, dims::Integer=1) where {T<:SortTypes}
-    if !enabled() || !graftable(lt, by, alg) || dims != 1
+    if !enabled() || !graftable(lt, by, alg) || !(1 <= dims <= ndims(c))
         return invoke(sort!, Tuple{CUDACore.AnyCuArray}, c; alg, lt, by, rev, dims)
     end
-    n = size(c, 1); nseg = n == 0 ? 0 : length(c) ÷ n
-    (n <= 1 || nseg == 0) && return c
-    bytes = b200_sort_workspace_bytes(dtype_code(T), Int32(-1), n, nseg)
+    sz = size(c)
+    pre, n, post = prod(sz[1:dims-1]), sz[dims], prod(sz[dims+1:end])
+    (n <= 1 || pre * post == 0) && return c
+    bytes = b200_sort_dims_workspace_bytes(dtype_code(T), Int32(0), pre, n, post)
     with_ws(bytes) do ws, nb
-        b200_sort_keys(ws, nb, c, dtype_code(T), n, nseg, Int32(rev), stream())
+        b200_sort_keys_dims(ws, nb, c, dtype_code(T), pre, n, post, Int32(rev), stream())
     end
     return c
 end
@@ -26,13 +27,15 @@ function Base.sortperm!(ix::CuArray{I}, A::CuArray{T}; initialized::Bool=false,
         throw(ArgumentError("index array must have the same size/axes as the source array, $(axes(ix)) != $(axes(A))"))
     end
     isempty(A) && return ix
-    if !enabled() || !graftable(lt, by, alg) || initialized || dims != 1
+    if !enabled() || !graftable(lt, by, alg) || initialized || !(1 <= dims <= ndims(A))
         return invoke(sortperm!, Tuple{CUDACore.AnyCuArray,CUDACore.AnyCuArray}, ix, A; initialized, alg, lt, by, rev, dims)
     end
-    n = size(A, 1); nseg = length(A) ÷ n
-    bytes = b200_sort_workspace_bytes(dtype_code(T), SORTPERM_INDEX, n, nseg)
+    sz = size(A)
+    pre, n, post = prod(sz[1:dims-1]), sz[dims], prod(sz[dims+1:end])
+    bytes = b200_sort_dims_workspace_bytes(dtype_code(T), Int32(1), pre, n, post)
     with_ws(bytes) do ws, nb
-        b200_sortperm(ws, nb, A, ix, dtype_code(T), dtype_code(I), n, nseg, Int32(rev), Int32(ndims(A) > 1), stream())
+        b200_sortperm_dims(ws, nb, A, ix, dtype_code(T), dtype_code(I), pre, n, post, Int32(rev),
+                           Int32(ndims(A) > 1), stream())
     end
     return ix
 end

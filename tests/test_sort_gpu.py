@@ -186,8 +186,8 @@ def test_guards(b):
         b.sort_(c, by=lambda x: abs(x - 0.5))
     with pytest.raises(b.NotGraftedError):
         b.sort_(c, alg=b.QuickSort)
-    with pytest.raises(b.NotGraftedError):
-        b.sort_(b.CuArray(np.zeros((4, 4), dtype=np.float32)), dims=2)
+    with pytest.raises(b.ArgumentError):
+        b.sort_(b.CuArray(np.zeros((4, 4), dtype=np.float32)), dims=3)
 
 
 def test_repetition_no_races(b):
@@ -205,3 +205,48 @@ def test_large_sort_and_sortperm(b):
     np.testing.assert_array_equal(got, np.sort(a))
     f = rand("float32", n)
     np.testing.assert_array_equal(b.Array(b.sortperm(b.CuArray(f))), oracle.sortperm(f))
+
+
+@pytest.mark.parametrize("shape,dims,dtype,rev", [
+    ((4, 50000, 4), 2, "int32", False),          # test/core/sorting.jl:314
+    ((2, 2, 50000), 3, "int32", True),           # :315
+    ((100_000, 4), 1, "float32", False), ((4, 100_000), 2, "float32", False),     # :326-327 shapes
+    ((100, 16), 1, "float32", False), ((100, 16), 2, "float32", True), ((100, 256, 64), 1, "float32", False),
+    ((3, 5000, 7), 2, "float64", False), ((33, 4096, 3), 2, "uint16", True), ((7, 4097, 2), 2, "int8", False),
+    ((5, 3, 1000), 2, "int64", False), ((1, 1, 9), 3, "float32", False),
+])
+def test_sort_any_dims(b, shape, dims, dtype, rev):
+    """sort!(A; dims) / sortperm(A; dims) along any dimension."""
+    A = np.asfortranarray(rand(dtype, int(np.prod(shape))).reshape(shape))
+    c = b.CuArray(A)
+    assert b.sort_(c, dims=dims, rev=rev) is c
+    np.testing.assert_array_equal(bits(b.Array(c)), bits(oracle.sort_dims(A, dims, rev=rev)))
+    got = b.Array(b.sortperm(b.CuArray(A), dims=dims, rev=rev))
+    np.testing.assert_array_equal(got, oracle.sortperm_dims(A, dims, rev=rev) if not rev else _sortperm_dims_rev(A, dims))
+
+
+def _sortperm_dims_rev(A, dims):
+    ax = dims - 1
+    lin = (np.arange(A.size, dtype=np.int64) + 1).reshape(A.shape, order="F")
+    M, L = np.moveaxis(A, ax, -1), np.moveaxis(lin, ax, -1)
+    out = np.empty(M.shape, dtype=np.int64)
+    for idx in np.ndindex(M.shape[:-1]):
+        out[idx] = L[idx][oracle.sortperm(M[idx], rev=True) - 1]
+    return np.moveaxis(out, -1, ax)
+
+
+def test_sortperm_dims_reference_shapes(b):
+    """test/core/sorting.jl:388-392: (100_000, 16) dims=1 and dims=2, (100, 256, 256) dims=1 (scaled)."""
+    A = np.asfortranarray(rand("float32", 100_000 * 16).reshape(100_000, 16))
+    for d in (1, 2):
+        np.testing.assert_array_equal(b.Array(b.sortperm(b.CuArray(A), dims=d)), oracle.sortperm_dims(A, d))
+    B3 = np.asfortranarray(rand("float32", 100 * 256 * 32).reshape(100, 256, 32))
+    np.testing.assert_array_equal(b.Array(b.sortperm(b.CuArray(B3), dims=1)), oracle.sortperm_dims(B3, 1))
+
+
+@pytest.mark.parametrize("n", [5, 100, 1000, 4095, 4096])
+@pytest.mark.parametrize("dtype", ["float32", "int64", "uint8", "float16"])
+def test_small_block_sort(b, n, dtype):
+    a = rand(dtype, n)
+    np.testing.assert_array_equal(bits(b.Array(b.sort_(b.CuArray(a)))), bits(oracle.sort(a)))
+    np.testing.assert_array_equal(b.Array(b.sortperm(b.CuArray(a), rev=True)), oracle.sortperm(a, rev=True))
