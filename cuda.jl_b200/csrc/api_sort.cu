@@ -179,6 +179,7 @@ int32_t b200_sortperm_dims(void *workspace, size_t workspace_bytes, const void *
                            int32_t linear, b200_stream_t stream) {
     using namespace b200;
     if (pre < 0 || n < 0 || post < 0) return B200_INVALID_VALUE;
+    if (!index_dtype_ok(dtype_index) || dtype_size(dtype_key) == 0) return B200_UNSUPPORTED;
     if (pre * n * post > 0 && (!keys || !perm)) return B200_INVALID_VALUE;
     return sort_dims(workspace, workspace_bytes, const_cast<void *>(keys), perm, dtype_key, dtype_index, SORT_PERM, pre, n,
                      post, descending, linear, reinterpret_cast<cudaStream_t>(stream), nullptr);
