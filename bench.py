@@ -351,6 +351,82 @@ def cpu_baseline_sample():
         return {"value": None, "unit": "GB/s", "cores": 1, "kind": "port", "sample": f"unavailable: {e}"}
 
 
+def run_comparators(b, dt, torch, dev):
+    """BASELINE.md §2 baselines timed in the same run on the same inputs' shapes:
+    R = the reference's ALGORITHMS restated in CUDA C++ (bench/baselines/ref_algos.cu; the reference is Julia and
+    cannot run here), L = library state of practice (torch.sum / cumsum / sort, i.e. CUB)."""
+    out = {}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "bench", "baselines"))
+        import ref_algos as R
+        R.lib()
+    except Exception as e:
+        R = None
+        out["reference_algorithms"] = f"unavailable: {e}"
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def tmed(fn, reps, pre=None):
+        ts = []
+        for _ in range(reps):
+            if pre is not None:
+                pre()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record(); e.synchronize()
+            ts.append(s.elapsed_time(e))
+        return float(np.median(ts))
+
+    g = torch.Generator(device=dev); g.manual_seed(0xB200 + 7)
+    # configs[1] F32 matrix
+    A = torch.rand(M * M, device=dev, generator=g, dtype=torch.float32)
+    At = A.view(M, M)                      # torch is row-major: dim 1 of the view is the contiguous (Julia dim 1) axis
+    r = torch.empty(M, device=dev, dtype=torch.float32)
+    part = torch.empty(M * 4096, device=dev, dtype=torch.float32)
+    for name, tdim, pre, red, post in (("sum(A;dims=1) 16384^2 F32", 1, 1, M, M), ("sum(A;dims=2) 16384^2 F32", 0, M, M, 1)):
+        d = {}
+        fn = lambda: torch.sum(At, dim=tdim, out=r)
+        fn(); d["torch_ms"] = tmed(fn, 5)
+        if R is not None:
+            fn = lambda: R.sum_f32(A.data_ptr(), r.data_ptr(), part.data_ptr(), pre, red, post, stream)
+            fn(); d["reference_algorithm_ms"] = tmed(fn, 5)
+        out[name] = d
+    del A, At, r
+    n = 1 << 30
+    V = torch.rand(n, device=dev, generator=g, dtype=torch.float32)
+    r1 = torch.empty(1, device=dev, dtype=torch.float32)
+    d = {}
+    fn = lambda: torch.sum(V); fn(); d["torch_ms"] = tmed(fn, 5)
+    if R is not None:
+        fn = lambda: R.sum_f32(V.data_ptr(), r1.data_ptr(), part.data_ptr(), 1, n, 1, stream); fn(); d["reference_algorithm_ms"] = tmed(fn, 5)
+    out["sum 2^30 Float32"] = d
+    O = torch.empty_like(V)
+    d = {}
+    fn = lambda: torch.cumsum(V, 0, out=O); fn(); d["torch_ms"] = tmed(fn, 3)
+    if R is not None:
+        scratch = torch.empty(n // 512 + 4096, device=dev, dtype=torch.float32)
+        fn = lambda: R.cumsum(V.data_ptr(), O.data_ptr(), scratch.data_ptr(), n, stream); fn(); d["reference_algorithm_ms"] = tmed(fn, 3)
+        del scratch
+    out["cumsum 2^30 Float32"] = d
+    del O
+    d = {}
+    fn = lambda: torch.sort(V); fn(); d["torch_ms"] = tmed(fn, 2)
+    out["sort 2^30 Float32"] = d
+    del V, part
+    torch.cuda.empty_cache()
+    if R is not None:
+        U = torch.randint(-2**31, 2**31 - 1, (n,), device=dev, generator=g, dtype=torch.int32)
+        K = U.clone()
+        fn = lambda: R.bitonic_sort_u32(K.data_ptr(), n, stream)
+        fn()
+        ok = bool((K.view(torch.uint32)[1:1 << 20].to(torch.int64) >= K.view(torch.uint32)[:(1 << 20) - 1].to(torch.int64)).all().item())
+        out["sort! 2^30 UInt32"] = {"reference_algorithm_ms": tmed(fn, 1, pre=lambda: K.copy_(U)), "reference_algorithm_sorted_prefix_ok": ok,
+                                    "launches": 240}
+        del U, K
+    torch.cuda.empty_cache()
+    out["_labels"] = {"reference_algorithm": "restatement of CUDA.jl's algorithm + launch structure in CUDA C++ (nvcc, not Julia-JIT): "
+                                            "bench/baselines/ref_algos.cu", "torch": "torch 2.11 (CUB) library comparator"}
+    return out
+
+
 def run_extras(b, dt, torch, dev, peak):
     """North-star configurations beyond configs[1], measured in the same run (1 GPU)."""
     out = {}
@@ -414,6 +490,10 @@ def run_extras(b, dt, torch, dev, peak):
                                 "frac_of_nominal_8TBps": 16 * n / med / 1e6 / NOMINAL_GBS}
     del I, cI, O
     torch.cuda.empty_cache()
+    try:
+        out["comparators"] = run_comparators(b, dt, torch, dev)
+    except Exception as e:  # baselines are reported numbers, never the product path
+        out["comparators"] = {"error": repr(e)}
     return out
 
 
