@@ -1117,16 +1117,26 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
         // window vs 4.4 TB/s with two 256-thread CTAs; Int64 4.8 TB/s with two 256-thread CTAs vs 4.5 TB/s
         constexpr bool kWide = sizeof(A) > 4;
         constexpr int kStages = B200_SCAN_STAGES;
-        constexpr int kThreads = kWide ? 256 : 512;
+#ifndef B200_SCAN_NT_NARROW
+#define B200_SCAN_NT_NARROW 512
+#endif
+#ifndef B200_SCAN_K_NARROW
+#define B200_SCAN_K_NARROW 8
+#endif
+#ifndef B200_SCAN_NT_WIDE
+#define B200_SCAN_NT_WIDE 256
+#endif
+        constexpr int kThreads = kWide ? B200_SCAN_NT_WIDE : B200_SCAN_NT_NARROW;
+        constexpr int kK = kWide ? S::K : B200_SCAN_K_NARROW;
 #ifndef B200_SCAN_LOOK_NARROW
 #define B200_SCAN_LOOK_NARROW 3
 #endif
         constexpr int kLook = kWide ? 4 : B200_SCAN_LOOK_NARROW;
-        constexpr int64_t kTile = (int64_t)kThreads * S::EPC * S::K;
+        constexpr int64_t kTile = (int64_t)kThreads * S::EPC * kK;
         constexpr size_t smem = (size_t)kTile * sizeof(Tin) * kStages;
         static const bool use_ws = getenv("B200_SCAN_WS") != nullptr;   // warp-specialised variant: opt-in (measured slower)
-        auto kern = use_ws ? scan_pipe_ws_kernel<Tin, Tout, Op, S::EPC, S::K, kStages, kThreads, kLook>
-                           : scan_pipe_kernel<Tin, Tout, Op, S::EPC, S::K, kStages, kThreads, kLook>;
+        auto kern = use_ws ? scan_pipe_ws_kernel<Tin, Tout, Op, S::EPC, kK, kStages, (kThreads > 992 ? 992 : kThreads), kLook>
+                           : scan_pipe_kernel<Tin, Tout, Op, S::EPC, kK, kStages, kThreads, kLook>;
         static thread_local int attr_dev_mask[64];  // cudaFuncSetAttribute once per (thread, device, instantiation)
         int dev = 0;
         B200_CUDA_TRY(cudaGetDevice(&dev));

@@ -19,6 +19,9 @@ namespace b200 {
 constexpr int RX_THREADS = 256;
 constexpr int RX_WARPS = RX_THREADS / 32;
 constexpr int RX_RADIX = 256;
+#ifndef B200_RX_MATCH_MASK
+#define B200_RX_MATCH_MASK 0x8888   // items 3, 7, 11, 15 of every 16
+#endif
 constexpr int RX_LOOK = 4;   // predecessor tiles inspected per look-back round trip
 
 template <int KB> struct KeyOf;
@@ -271,8 +274,8 @@ __global__ void __launch_bounds__(RX_THREADS) radix_onesweep_kernel(OnesweepPara
     for (int i = 0; i < ITEMS; ++i) {
         const unsigned int digit = digit_of<K>(keys[i], p.shift);
         unsigned int peers;
-        if ((i & 3) == 3) {
-            // every 4th item goes through MATCH.ANY so that the ADU pipe shares the load with the ALU
+        if ((B200_RX_MATCH_MASK >> (i & 15)) & 1) {
+            // a quarter of the items go through MATCH.ANY so that the ADU pipe shares the load with the ALU
             peers = __match_any_sync(0xffffffffu, digit);
         } else {
             unsigned int differ = 0;   // lanes whose digit differs from mine in some bit

@@ -9,11 +9,19 @@ namespace b200 {
 
 using K = KeyOf<B200_KEY_BYTES>::type;
 constexpr int P = B200_KEY_BYTES;                       // 8-bit digits: one pass per key byte
-constexpr int ITEMS = B200_KEY_BYTES == 8 ? 12 : 16;
-constexpr int TILE = RX_THREADS * ITEMS;
+// Keys per thread.  Measured on B200 (2^30 UInt32): keys-only 19.9 ms at 16, 17.4 ms at 20, 17.8 ms at 24;
+// pairs 24.9 ms at 16, 25.4 ms at 20, 28.5 ms at 24 (shared-memory staging of key + payload costs occupancy).
+#ifndef B200_RX_ITEMS_KEYS
+#define B200_RX_ITEMS_KEYS 20
+#endif
+template <class V> struct ItemsFor {
+    static constexpr int value = B200_KEY_BYTES == 8 ? 12 : (PayTraits<V>::HAS ? 16 : B200_RX_ITEMS_KEYS);
+};
+template <class V> constexpr int tile_for() { return RX_THREADS * ItemsFor<V>::value; }
 
 template <class V> static size_t onesweep_smem() {
     using VT = typename PayTraits<V>::type;
+    constexpr int TILE = tile_for<V>();
     size_t s = (size_t)RX_WARPS * RX_RADIX * 4 + RX_RADIX * 4 + RX_RADIX * 8 + ((size_t)TILE * sizeof(K) + 15) / 16 * 16;
     if (PayTraits<V>::HAS) s += (size_t)TILE * sizeof(VT);
     return s;
@@ -21,6 +29,7 @@ template <class V> static size_t onesweep_smem() {
 
 template <class V> static size_t pipe_smem() {
     using VT = typename PayTraits<V>::type;
+    constexpr int TILE = tile_for<V>();
     size_t s = (size_t)(RXP_STAGES + 2) * TILE * sizeof(K) + (size_t)RX_WARPS * RX_RADIX * 4 + 2 * RX_RADIX * 8;
     if (PayTraits<V>::HAS) s += 2 * (size_t)TILE * sizeof(VT);
     return s;
@@ -28,7 +37,7 @@ template <class V> static size_t pipe_smem() {
 
 // Persistent pipelined pass: needs 16-byte aligned keys (TMA) and at least one full tile.
 template <class V, class LookT> static int32_t launch_pipe(const OnesweepParams &p, int64_t tiles, cudaStream_t st) {
-    auto kern = radix_onesweep_pipe_kernel<K, V, LookT, ITEMS>;
+    auto kern = radix_onesweep_pipe_kernel<K, V, LookT, ItemsFor<V>::value>;
     const size_t smem = pipe_smem<V>();
     static thread_local bool attr_set[64];
     int dev = 0;
@@ -51,7 +60,7 @@ template <class V, class LookT> static int32_t launch_pass(const OnesweepParams 
     static const bool use_pipe = getenv("B200_SORT_PIPE") != nullptr;   // persistent variant: measured slower (fewer warps per SM)
     if (use_pipe && tiles >= 2 && (reinterpret_cast<uintptr_t>(p.keys_in) % 16) == 0 && pipe_smem<V>() <= 200 * 1024)
         return launch_pipe<V, LookT>(p, tiles, st);
-    auto kern = radix_onesweep_kernel<K, V, LookT, ITEMS>;
+    auto kern = radix_onesweep_kernel<K, V, LookT, ItemsFor<V>::value>;
     const size_t smem = onesweep_smem<V>();
     static thread_local bool attr_set[64];
     int dev = 0;
@@ -76,7 +85,7 @@ template <class LookT> static int32_t dispatch_pass(const OnesweepParams &p, int
 
 int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
     const int64_t n = c.n;
-    const int64_t tiles = cdiv(n, TILE);
+    const int64_t tiles = cdiv(n, c.mode == SORT_KEYS ? tile_for<NoPayload>() : tile_for<uint32_t>());
     const bool wide = n >= (1LL << 30);                    // 30-bit counts no longer hold every prefix
     const size_t look_bytes = wide ? 8 : 4;
     // payload width carried through the passes

@@ -1,1 +1,2 @@
-for v in _l3 _l10; do for ws in 0 1; do echo "variant=$v ws=$ws"; if [ $ws = 1 ]; then export B200_SCAN_WS=1; else unset B200_SCAN_WS; fi; B200ARRAYS_LIB=$PWD/cuda.jl_b200/libb200arrays$v.so timeout 150 python tools/microbench.py scan 2>&1 | grep "F32" | grep -v torch; done; done
+timeout 300 python -m pytest tests/test_sort_gpu.py -m gpu -x -q --timeout 90 --timeout-method=thread 2>&1 | tail -2
+for v in "" _a; do echo "variant=$v"; B200ARRAYS_LIB=$PWD/cuda.jl_b200/libb200arrays$v.so timeout 150 python tools/microbench.py sort 2>&1 | grep -v torch | tail -4; done
