@@ -10,7 +10,8 @@ from .errors import ArgumentError, DimensionMismatch, NotGraftedError, B200Array
 from .cuarray import CuArray, Array
 from .mapreduce import (identity, abs2, add_sum, mul_prod, add, mul, max_, min_, and_, or_, extrema_rf,
                         neutral_element, mapreducedim_, mapreduce, reduce, sum, prod, maximum, minimum,
-                        extrema, count, any, all, sum_, prod_, maximum_, minimum_)
+                        extrema, count, any, all, sum_, prod_, maximum_, minimum_,
+                        findmax, findmin, argmax, argmin)
 from .accumulate import scan_, accumulate_, accumulate, cumsum, cumprod, cumsum_, cumprod_
 from .sorting import (isless, BitonicSort, QuickSort, sort_, sort, partialsort_, partialsort, sortperm_, sortperm)
 from .indexing import findall

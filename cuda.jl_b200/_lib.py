@@ -24,6 +24,8 @@ SIGNATURES = {
     "b200_reset_launch_count": (None, []),
     "b200_reduce_workspace_bytes": (_i32, [_i32, _i32, _i32, _i32, _i64, _i64, _i64, _c.POINTER(_sz)]),
     "b200_reduce": (_i32, [_vp, _sz, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i32, _vp]),
+    "b200_findminmax_workspace_bytes": (_i32, [_i32, _i64, _i64, _i64, _c.POINTER(_sz)]),
+    "b200_findminmax": (_i32, [_vp, _sz, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _i64, _vp]),
     "b200_scan_workspace_bytes": (_i32, [_i32, _i32, _i32, _i64, _i64, _i64, _c.POINTER(_sz)]),
     "b200_scan": (_i32, [_vp, _sz, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _vp, _vp]),
     "b200_sort_workspace_bytes": (_i32, [_i32, _i32, _i64, _i64, _c.POINTER(_sz)]),

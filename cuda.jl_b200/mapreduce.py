@@ -263,3 +263,44 @@ sum_ = _bang(add_sum)
 prod_ = _bang(mul_prod)
 maximum_ = _bang(max_)
 minimum_ = _bang(min_)
+
+
+# --- findmax / findmin / argmax / argmin ------------------------------------
+def _findminmax(A, dims, is_max):
+    """Base.findmax(A; dims) / findmin on a CuArray (reference: GPUArrays' findminmax through
+    mapreducedim!; tests test/core/array.jl:767-769,782-784).  Returns (values, linear 1-based
+    Int64 indices); with dims=None a host (value, index) pair.  (Julia returns CartesianIndex for
+    N-d inputs: the linear index carries the same information.)"""
+    if A.length == 0:
+        raise ArgumentError("reducing over an empty collection is not allowed")
+    rd = _reduced_dims(A.dims, dims)
+    pre, red, post = _factor(A.dims, rd)
+    vals = CuArray.undef(A.eltype, rd, A.buf.device)
+    idx = CuArray.undef(dt.I64, rd, A.buf.device)
+    lib = _lib.load()
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(lib.b200_findminmax_workspace_bytes(A.eltype, pre, red, post, ctypes.byref(nbytes)))
+    ws = Workspace(nbytes.value, A.buf.device)
+    _lib.check(lib.b200_findminmax(ws.ptr, ws.nbytes, A.pointer, vals.pointer, idx.pointer, A.eltype,
+                                   1 if is_max else 0, pre, red, post, current_stream_handle(A.buf.device)))
+    if dims is None:
+        return vals.to_host().reshape(-1)[0], int(idx.to_host().reshape(-1)[0])
+    return vals, idx
+
+
+def findmax(A, dims=None):
+    return _findminmax(A, dims, True)
+
+
+def findmin(A, dims=None):
+    return _findminmax(A, dims, False)
+
+
+def argmax(A, dims=None):
+    r = _findminmax(A, dims, True)
+    return r[1]
+
+
+def argmin(A, dims=None):
+    r = _findminmax(A, dims, False)
+    return r[1]

@@ -141,6 +141,16 @@ int32_t b200_reduce(void *workspace, size_t workspace_bytes,
                     int64_t pre, int64_t red, int64_t post,
                     int32_t init_mode, b200_stream_t stream);
 
+/* findmax / findmin / argmax / argmin (reference: GPUArrays findminmax through
+ * mapreducedim!, tests test/core/array.jl:767-769,782-784).  out_vals[i,0,j] = extremal value of the
+ * slice (dtype as the input), out_idx = its 1-based LINEAR index into the input (Int64).  Julia's
+ * rules: first extremal element wins; NaN is the maximum for findmax and the minimum for findmin;
+ * -0.0 < +0.0. */
+int32_t b200_findminmax_workspace_bytes(int32_t dtype, int64_t pre, int64_t red, int64_t post, size_t *bytes);
+int32_t b200_findminmax(void *workspace, size_t workspace_bytes, const void *in, void *out_vals,
+                        void *out_idx, int32_t dtype, int32_t is_max,
+                        int64_t pre, int64_t red, int64_t post, b200_stream_t stream);
+
 /* ---- scan: CUDACore.scan! (accumulate.jl:135) --------------------------- */
 /* Inclusive (exclusive != 0: exclusive) prefix-op along n.  `init` is a HOST
  * pointer to one dtype_out value (the x of Some(x)) folded into every output,

@@ -51,3 +51,41 @@ function GPUArrays.mapreducedim!(f::F, op::OP, R::CuArray{To}, A::CuArray{Ti};
     end
     return R                                                     # mapreduce.jl:211,300
 end
+
+# findmax / findmin (GPUArrays: Base.findmax(a::AnyGPUArray; dims=:) -> findminmax -> mapreducedim! with a
+# tuple-valued op; tests test/core/array.jl:767-769,782-784).  One (pre, red, post) call to b200_findminmax;
+# linear indices are turned into CartesianIndices on the host side of the API like GPUArrays does.
+function b200_findminmax(ws, ws_bytes, A, vals, idx, din, is_max, pre, red, post, s::CuStream)
+    initialize_context()
+    check(@gcsafe_ccall libb200arrays[].b200_findminmax(ws::CuPtr{Cvoid}, ws_bytes::Csize_t, A::CuPtr{Cvoid},
+              vals::CuPtr{Cvoid}, idx::CuPtr{Cvoid}, din::Int32, is_max::Int32, pre::Int64, red::Int64, post::Int64,
+              s::CUDACore.CUstream)::Int32)
+end
+
+function graft_findminmax(A::CuArray{T}, dims, is_max::Bool) where {T<:ReduceTypes}
+    isempty(A) && throw(ArgumentError("reducing over an empty collection is not allowed"))
+    rsz = dims === Colon() ? ntuple(_ -> 1, ndims(A)) : ntuple(d -> d in dims ? 1 : size(A, d), ndims(A))
+    f = factor_dims(size(A), rsz)
+    f === nothing && return nothing
+    pre, red, post = f
+    vals = similar(A, T, rsz); idx = similar(A, Int64, rsz)
+    bytes = Ref{Csize_t}(0)
+    check(@ccall libb200arrays[].b200_findminmax_workspace_bytes(dtype_code(T)::Int32, pre::Int64, red::Int64,
+              post::Int64, bytes::Ref{Csize_t})::Int32)
+    with_ws(Int(bytes[])) do ws, nb
+        b200_findminmax(ws, nb, A, vals, idx, dtype_code(T), Int32(is_max), pre, red, post, stream())
+    end
+    if dims === Colon()
+        v, i = CUDACore.@allowscalar(vals[1]), CUDACore.@allowscalar(idx[1])
+        return (v, ndims(A) == 1 ? i : CartesianIndices(A)[i])
+    end
+    ci = CartesianIndices(A)
+    return (vals, map(i -> ci[i], idx))
+end
+
+for (fn, mx) in ((:findmax, true), (:findmin, false))
+    @eval function Base.$fn(A::CuArray{T}; dims=:) where {T<:ReduceTypes}
+        r = enabled() ? graft_findminmax(A, dims, $mx) : nothing
+        r === nothing ? invoke(Base.$fn, Tuple{GPUArrays.AnyGPUArray}, A; dims) : r
+    end
+end

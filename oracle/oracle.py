@@ -323,3 +323,25 @@ def is_valid_sort(orig, result, rev=False):
 def findall(mask):
     """findall(::Array{Bool}) -> 1-based linear indices (CUDACore/src/indexing.jl:26-66)."""
     return np.flatnonzero(np.asarray(mask).reshape(-1, order="F")).astype(np.int64) + 1
+
+
+def findminmax(A, dims=None, is_max=True):
+    """Base.findmax / findmin: first extremal element, NaN is the maximum (findmax) or the minimum
+    (findmin), -0.0 < +0.0.  Returns (values, 1-based linear indices); dims=None -> over everything."""
+    A = np.asarray(A)
+    key = total_order_key(A)
+    kf = key.astype(np.float64) if key.dtype.itemsize < 8 else key
+    if is_float(A.dtype) and not is_max:
+        nan = np.isnan(A.astype(np.float64))
+        key = np.where(nan, np.zeros_like(key), key)
+    lin = (np.arange(A.size, dtype=np.int64) + 1).reshape(A.shape, order="F")
+    if dims is None:
+        flat_k, flat_l = key.reshape(-1, order="F"), lin.reshape(-1, order="F")
+        j = int(np.argmax(flat_k) if is_max else np.argmin(flat_k))     # first occurrence
+        return A.reshape(-1, order="F")[j], int(flat_l[j])
+    ax = tuple(d - 1 for d in ((dims,) if isinstance(dims, int) else dims))
+    assert len(ax) == 1, "oracle: one reduced dim"
+    a = ax[0]
+    j = np.argmax(key, axis=a) if is_max else np.argmin(key, axis=a)
+    jj = np.expand_dims(j, a)
+    return np.take_along_axis(A, jj, axis=a), np.take_along_axis(lin, jj, axis=a)

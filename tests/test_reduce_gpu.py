@@ -245,3 +245,38 @@ def test_unaligned_views(b):
     got = b.Array(b.sum(v, dims=2)).astype(np.float64).reshape(-1)
     ref = h[:, 1:].astype(np.float64).sum(axis=1)
     assert np.all(np.abs(got - ref) <= 0.05 * np.abs(h[:, 1:].astype(np.float64)).sum(axis=1))
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64", "float16", "bfloat16", "int32", "int64", "uint32", "uint64"])
+def test_findmax_findmin(b, dtype):
+    """findmax / findmin (test/core/array.jl:767-769,782-784): first extremal element wins."""
+    a = rand(dtype, (100_003,))
+    a[::1000] = a[7]                        # ties: the first one must win
+    for is_max, fn in ((True, b.findmax), (False, b.findmin)):
+        v, i = fn(b.CuArray(a))
+        rv, ri = oracle.findminmax(a, None, is_max)
+        assert i == ri and np.asarray(v).reshape(1).tobytes() == np.asarray(rv).reshape(1).tobytes()
+    for shape, dims in (((300, 257), 1), ((300, 257), 2), ((33, 65, 17), 2), ((5, 40_000), 2), ((40_000, 5), 1), ((2, 3, 50_000), 3)):
+        A = np.asfortranarray(rand(dtype, shape))
+        for is_max, fn in ((True, b.findmax), (False, b.findmin)):
+            V, I = fn(b.CuArray(A), dims=dims)
+            rv, ri = oracle.findminmax(A, dims, is_max)
+            np.testing.assert_array_equal(b.Array(I), ri)
+            assert np.ascontiguousarray(b.Array(V)).tobytes() == np.ascontiguousarray(rv).tobytes()
+    assert b.argmax(b.CuArray(a)) == oracle.findminmax(a, None, True)[1]
+
+
+def test_findmax_nan_and_zero_rules(b):
+    a = np.array([1.0, -0.0, 0.0, np.nan, 5.0, np.nan, -7.0], dtype=np.float32)
+    assert b.findmax(b.CuArray(a))[1] == 4 and np.isnan(b.findmax(b.CuArray(a))[0])      # first NaN
+    assert b.findmin(b.CuArray(a))[1] == 4 and np.isnan(b.findmin(b.CuArray(a))[0])
+    z = np.array([0.0, -0.0, 0.0, -0.0], dtype=np.float64)
+    assert b.findmax(b.CuArray(z))[1] == 1 and b.findmin(b.CuArray(z))[1] == 2
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    big = 1024 * sms + 5                                                                    # "large map reduce" shape
+    A = np.asfortranarray(RNG.random((big, 31), dtype=np.float32))
+    V, I = b.findmax(b.CuArray(A), dims=2)
+    rv, ri = oracle.findminmax(A, 2, True)
+    np.testing.assert_array_equal(b.Array(V), rv)
+    np.testing.assert_array_equal(b.Array(I), ri)
