@@ -1,0 +1,247 @@
+// partition.cu — stable multi-way partition of keys (and an 8-byte payload) by G-1 splitters,
+// G <= 16.  First stage of the multi-GPU sample sort: every rank cuts its UNSORTED
+// shard into G destination buckets, exchanges them (all-to-all) and sorts once — instead of
+// sorting, cutting, exchanging and sorting again.  No reference counterpart (the reference has no
+// multi-GPU sort).  Bucket b receives the keys with splitter[b-1] <= key < splitter[b] in the
+// order-preserving key space of the sort (isless / rev); within a bucket the input order is kept.
+//
+// Three small kernels: per-tile bucket counts -> per-bucket exclusive scan over the tiles ->
+// ranked scatter (same ballot ranking as the onesweep pass, 4 bits instead of 8).
+#include "sort.cuh"
+
+namespace b200 {
+
+constexpr int PT_ITEMS = 16;
+constexpr int PT_TILE = RX_THREADS * PT_ITEMS;
+constexpr int PT_MAXB = 16;
+
+struct PartParams {
+    const void *keys_in;
+    void *keys_out;
+    const void *vals_in;     // optional 8-byte payload
+    void *vals_out;
+    const void *splitters;   // G-1 raw keys (device)
+    long long *tile_counts;  // [G][tiles]: counts, then exclusive prefixes over tiles
+    long long *bucket_counts;// [G]
+    int64_t n;
+    int64_t tiles;
+    int32_t G;
+    SortXform xf;
+};
+
+template <class K>
+__device__ __forceinline__ void load_tile_buckets(const PartParams &p, const K *s_spl, int64_t tile_base, int valid,
+                                                  int idx0, K (&keys)[PT_ITEMS], unsigned char (&bid)[PT_ITEMS]) {
+    const K *kin = static_cast<const K *>(p.keys_in) + tile_base + idx0;
+#pragma unroll
+    for (int i = 0; i < PT_ITEMS; ++i) keys[i] = (idx0 + i * 32 < valid) ? ldg_stream(kin + i * 32) : (K)0;
+#pragma unroll
+    for (int i = 0; i < PT_ITEMS; ++i) {
+        const K e = key_encode<K>(keys[i], p.xf);
+        int b = 0;
+        for (int s = 0; s < p.G - 1; ++s) b += (e >= s_spl[s]) ? 1 : 0;
+        bid[i] = (idx0 + i * 32 < valid) ? (unsigned char)b : (unsigned char)0xFF;   // padding matches no bucket
+    }
+}
+
+template <class K>
+__global__ void __launch_bounds__(RX_THREADS) partition_count_kernel(PartParams p) {
+    __shared__ K s_spl[PT_MAXB];
+    __shared__ unsigned int s_cnt[PT_MAXB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < p.G - 1) s_spl[tid] = key_encode<K>(static_cast<const K *>(p.splitters)[tid], p.xf);
+    if (tid < PT_MAXB) s_cnt[tid] = 0;
+    __syncthreads();
+    const int64_t t = blockIdx.x, tile_base = t * PT_TILE;
+    const int valid = (int)((p.n - tile_base) < PT_TILE ? (p.n - tile_base) : PT_TILE);
+    K keys[PT_ITEMS];
+    unsigned char bid[PT_ITEMS];
+    load_tile_buckets<K>(p, s_spl, tile_base, valid, warp * (32 * PT_ITEMS) + lane, keys, bid);
+    for (int b = 0; b < p.G; ++b) {
+        unsigned int c = 0;
+#pragma unroll
+        for (int i = 0; i < PT_ITEMS; ++i) c += __popc(__ballot_sync(0xffffffffu, bid[i] == b));
+        if (lane == 0) atomicAdd(&s_cnt[b], c);
+    }
+    __syncthreads();
+    if (tid < p.G) p.tile_counts[(int64_t)tid * p.tiles + t] = s_cnt[tid];
+}
+
+// one CTA per bucket: exclusive scan of its tile counts, total to bucket_counts
+__global__ void __launch_bounds__(256) partition_scan_kernel(PartParams p) {
+    __shared__ long long s_w[8];
+    __shared__ long long s_run;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long *row = p.tile_counts + (int64_t)b * p.tiles;
+    if (tid == 0) s_run = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < p.tiles; base += 256) {
+        const int64_t i = base + tid;
+        const long long v = i < p.tiles ? row[i] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        long long wb = 0;
+        for (int w = 0; w < warp; ++w) wb += s_w[w];
+        const long long run = s_run;
+        if (i < p.tiles) row[i] = run + wb + incl - v;
+        __syncthreads();
+        if (tid == 255) s_run = run + wb + incl;
+        __syncthreads();
+    }
+    if (tid == 0) p.bucket_counts[b] = s_run;
+}
+
+template <class K, bool HAS_V>
+__global__ void __launch_bounds__(RX_THREADS) partition_scatter_kernel(PartParams p) {
+    __shared__ K s_spl[PT_MAXB];
+    __shared__ unsigned int s_wcnt[RX_WARPS][PT_MAXB];
+    __shared__ long long s_base[PT_MAXB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < p.G - 1) s_spl[tid] = key_encode<K>(static_cast<const K *>(p.splitters)[tid], p.xf);
+    if (tid < RX_WARPS * PT_MAXB) (&s_wcnt[0][0])[tid] = 0;
+    __syncthreads();
+    const int64_t t = blockIdx.x, tile_base = t * PT_TILE;
+    const int valid = (int)((p.n - tile_base) < PT_TILE ? (p.n - tile_base) : PT_TILE);
+    const int idx0 = warp * (32 * PT_ITEMS) + lane;
+    K keys[PT_ITEMS];
+    unsigned char bid[PT_ITEMS];
+    load_tile_buckets<K>(p, s_spl, tile_base, valid, idx0, keys, bid);
+    // stable rank inside the warp, by (item, lane)
+    unsigned short ranks[PT_ITEMS];
+    const unsigned int lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < PT_ITEMS; ++i) {
+        const unsigned int d = bid[i];
+        unsigned int differ = 0;
+#pragma unroll
+        for (int bit = 0; bit < 8; bit += (bit == 3 ? 4 : 1)) {   // bits 0..3 and bit 7 (the padding marker)
+            const bool one = (d >> bit) & 1u;
+            const unsigned int bal = __ballot_sync(0xffffffffu, one);
+            differ |= bal ^ (one ? 0xffffffffu : 0u);
+        }
+        const unsigned int peers = ~differ;
+        const unsigned int lower = peers & lt_mask;
+        const bool real = d < PT_MAXB;
+        volatile unsigned int *ctr = &s_wcnt[warp][real ? d : 0];
+        const unsigned int old = real ? *ctr : 0u;
+        __syncwarp();
+        if (real && lower == 0u) *ctr = old + __popc(peers);
+        __syncwarp();
+        ranks[i] = (unsigned short)(old + __popc(lower));
+    }
+    __syncthreads();
+    if (tid < p.G) {
+        // bucket base = sum of the totals of the buckets before it; + this tile's prefix; then per-warp offsets
+        long long base = 0;
+        for (int b = 0; b < tid; ++b) base += p.bucket_counts[b];
+        base += p.tile_counts[(int64_t)tid * p.tiles + t];
+        s_base[tid] = base;
+        unsigned int run = 0;
+        for (int w = 0; w < RX_WARPS; ++w) { const unsigned int c = s_wcnt[w][tid]; s_wcnt[w][tid] = run; run += c; }
+    }
+    __syncthreads();
+    K *kout = static_cast<K *>(p.keys_out);
+    const unsigned long long *vin = static_cast<const unsigned long long *>(p.vals_in) + tile_base + idx0;
+    unsigned long long *vout = static_cast<unsigned long long *>(p.vals_out);
+#pragma unroll
+    for (int i = 0; i < PT_ITEMS; ++i) {
+        if (bid[i] < PT_MAXB) {
+            const long long dst = s_base[bid[i]] + s_wcnt[warp][bid[i]] + ranks[i];
+            kout[dst] = keys[i];
+            if constexpr (HAS_V) vout[dst] = ldg_stream(vin + i * 32);
+        }
+    }
+}
+
+template <class K>
+static int32_t run_partition(void *ws, size_t wsb, PartParams p, bool has_v, cudaStream_t st, size_t *query) {
+    p.tiles = cdiv(p.n, PT_TILE);
+    Carver c(ws);
+    long long *tile_counts = c.take<long long>((size_t)p.G * p.tiles);
+    if (query) { *query = c.bytes(); return B200_OK; }
+    if (c.bytes() > wsb) return B200_WORKSPACE_TOO_SMALL;
+    if (!ws) return B200_INVALID_VALUE;
+    if (p.tiles > 2147483647LL) return B200_INVALID_VALUE;
+    p.tile_counts = tile_counts;
+    partition_count_kernel<K><<<(unsigned int)p.tiles, RX_THREADS, 0, st>>>(p);
+    B200_CHECK_LAUNCH();
+    partition_scan_kernel<<<p.G, 256, 0, st>>>(p);
+    B200_CHECK_LAUNCH();
+    if (has_v) partition_scatter_kernel<K, true><<<(unsigned int)p.tiles, RX_THREADS, 0, st>>>(p);
+    else partition_scatter_kernel<K, false><<<(unsigned int)p.tiles, RX_THREADS, 0, st>>>(p);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
+// same transform as the sort (api_sort.cu make_xform), NaNs canonical so that they all go last
+static bool part_xform(int dtype, int descending, SortXform &x, int &kb) {
+    x = SortXform{};
+    kb = dtype_size(dtype);
+    if (kb == 0) return false;
+    const uint64_t all = kb == 8 ? ~0ull : ((1ull << (8 * kb)) - 1);
+    const uint64_t sign = 1ull << (8 * kb - 1);
+    x.sign = sign; x.desc = descending ? all : 0; x.inf_bits = all;
+    bool is_float = false;
+    switch (dtype) {
+        case B200_F16: is_float = true; x.inf_bits = 0x7C00ull; break;
+        case B200_BF16: is_float = true; x.inf_bits = 0x7F80ull; break;
+        case B200_F32: is_float = true; x.inf_bits = 0x7F800000ull; break;
+        case B200_F64: is_float = true; x.inf_bits = 0x7FF0000000000000ull; break;
+        case B200_I8: case B200_I16: case B200_I32: case B200_I64: x.base_enc = sign; x.base_dec = sign; break;
+        case B200_U8: case B200_U16: case B200_U32: case B200_U64: case B200_BOOL: break;
+        default: return false;
+    }
+    if (is_float) { x.base_enc = sign; x.base_dec = all; x.fmn = all & ~sign; x.mag_mask = all & ~sign; x.nan_or = all; }
+    return true;
+}
+
+}  // namespace b200
+
+extern "C" {
+
+int32_t b200_partition_workspace_bytes(int64_t n, int32_t nbuckets, size_t *bytes) {
+    using namespace b200;
+    if (!bytes || n < 0 || nbuckets < 1 || nbuckets > PT_MAXB) return B200_INVALID_VALUE;
+    *bytes = 0;
+    if (n == 0) return B200_OK;
+    PartParams p{};
+    p.n = n; p.G = nbuckets;
+    return run_partition<uint32_t>(nullptr, 0, p, false, nullptr, bytes);
+}
+
+int32_t b200_partition(void *workspace, size_t workspace_bytes, const void *keys_in, void *keys_out,
+                       const void *payload_in, void *payload_out, int32_t dtype_key, int64_t n,
+                       const void *splitters, int32_t nbuckets, int32_t descending, void *bucket_counts_dev,
+                       b200_stream_t stream) {
+    using namespace b200;
+    if (n < 0 || nbuckets < 1 || nbuckets > PT_MAXB || !bucket_counts_dev) return B200_INVALID_VALUE;
+    SortXform xf; int kb;
+    if (!part_xform(dtype_key, descending, xf, kb)) return B200_UNSUPPORTED;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (n == 0) {
+        B200_CUDA_TRY(cudaMemsetAsync(bucket_counts_dev, 0, sizeof(long long) * nbuckets, st));
+        return B200_OK;
+    }
+    if (!keys_in || !keys_out || (nbuckets > 1 && !splitters) || ((payload_in == nullptr) != (payload_out == nullptr)))
+        return B200_INVALID_VALUE;
+    PartParams p{};
+    p.keys_in = keys_in; p.keys_out = keys_out; p.vals_in = payload_in; p.vals_out = payload_out;
+    p.splitters = splitters; p.bucket_counts = static_cast<long long *>(bucket_counts_dev);
+    p.n = n; p.G = nbuckets; p.xf = xf;
+    const bool has_v = payload_in != nullptr;
+    switch (kb) {
+        case 1: return run_partition<uint8_t>(workspace, workspace_bytes, p, has_v, st, nullptr);
+        case 2: return run_partition<uint16_t>(workspace, workspace_bytes, p, has_v, st, nullptr);
+        case 4: return run_partition<uint32_t>(workspace, workspace_bytes, p, has_v, st, nullptr);
+        case 8: return run_partition<uint64_t>(workspace, workspace_bytes, p, has_v, st, nullptr);
+        default: return B200_UNSUPPORTED;
+    }
+}
+
+}  // extern "C"

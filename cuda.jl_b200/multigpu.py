@@ -58,6 +58,28 @@ class DeviceOps:
         _lib.check(lib.b200_sort_pairs(ws.ptr, ws.nbytes, keys.pointer, payload.pointer, keys.eltype, payload.eltype,
                                        keys.length, 1 if rev else 0, current_stream_handle(keys.buf.device)))
 
+    def partition(self, keys, payload, splitters, nbuckets, rev):
+        """Stable partition of an unsorted shard into nbuckets (<= 16) destination buckets.
+        Returns (keys_out, payload_out | None, counts CuArray{Int64}[nbuckets])."""
+        import ctypes
+        from . import _lib
+        from .cuarray import Workspace
+        lib = _lib.load()
+        dev = keys.buf.device
+        kout = keys.similar()
+        pout = payload.similar() if payload is not None else None
+        counts = CuArray.undef(dt.I64, (nbuckets,), dev)
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.b200_partition_workspace_bytes(keys.length, nbuckets, ctypes.byref(nbytes)))
+        ws = Workspace(nbytes.value, dev)
+        _lib.check(lib.b200_partition(ws.ptr, ws.nbytes, keys.pointer if keys.length else None,
+                                      kout.pointer if keys.length else None,
+                                      payload.pointer if (payload is not None and keys.length) else None,
+                                      pout.pointer if (pout is not None and keys.length) else None,
+                                      keys.eltype, keys.length, splitters.pointer if splitters.length else None,
+                                      nbuckets, 1 if rev else 0, counts.pointer, current_stream_handle(dev)))
+        return kout, pout, counts
+
     def lower_bound(self, sorted_keys, needles, rev):
         from . import _lib
         lib = _lib.load()
@@ -207,16 +229,45 @@ def _splitters(c_sorted, rev, group, ops):
     return CuArray(spl.view(torch.uint8), (G - 1,), c_sorted.eltype)
 
 
+MAX_PARTITION_BUCKETS = 16
+
+
+def _sample_unsorted(c, group):
+    """S regular samples of an unsorted shard (a random sample for shuffled data; for presorted
+    data regular positions are exactly the regular-sampling choice)."""
+    return c
+
+
 def dist_sort(shard, rev=False, group=None, ops=None):
     """Distributed sample sort of the concatenation of all shards.  Returns this rank's slice of
     the globally sorted sequence (slices are in rank order; their sizes are data dependent) and
-    the G x G matrix of exchanged counts."""
+    the G x G matrix of exchanged counts.
+
+    G <= 16: partition-first — sample the UNSORTED shard, agree on splitters, cut the shard into G
+    buckets with one stable partition pass (b200_partition), all-to-all, sort ONCE.  More ranks:
+    sort, cut at the splitters, exchange, sort again."""
     ops = ops or DeviceOps()
+    G, r = _world(group)
+    if G == 1:
+        local = shard.copy()
+        ops.sort_keys(local, rev)
+        return local, np.array([[local.length]])
+    if G > MAX_PARTITION_BUCKETS or not hasattr(ops, "partition"):
+        return _dist_sort_sorted_first(shard, rev, group, ops)
+    spl = _splitters(shard, rev, group, ops)            # regular samples of the unsorted shard
+    if spl is None:
+        return shard.copy(), np.zeros((G, G), dtype=np.int64)
+    parted, _, counts = ops.partition(shard, None, spl, G, rev)
+    bounds = np.concatenate([[0], np.cumsum(counts.to_host().astype(np.int64))])
+    (recv,), cmat = _exchange(parted, bounds, group)
+    ops.sort_keys(recv, rev)
+    return recv, cmat
+
+
+def _dist_sort_sorted_first(shard, rev, group, ops):
     G, r = _world(group)
     local = shard.copy()
     ops.sort_keys(local, rev)
-    if G == 1:
-        return local, np.array([[local.length]])
     spl = _splitters(local, rev, group, ops)
     if spl is None:
         return local, np.zeros((G, G), dtype=np.int64)
@@ -230,7 +281,7 @@ def dist_sort(shard, rev=False, group=None, ops=None):
 def dist_sortperm(shard, rev=False, group=None, ops=None):
     """Distributed stable sortperm: returns this rank's slice of the global 1-based Int64
     permutation.  The payload is the global index; equal keys keep ascending global index
-    because every stage (local sort, rank-ordered exchange, local sort) is stable."""
+    because every stage (stable partition, rank-ordered exchange, stable local sort) is stable."""
     ops = ops or DeviceOps()
     G, r = _world(group)
     dev = shard.buf.device
@@ -238,12 +289,23 @@ def dist_sortperm(shard, rev=False, group=None, ops=None):
     sizes = [torch.empty_like(n_local) for _ in range(G)]
     dist.all_gather(sizes, n_local, group=group)
     offset = int(sum(int(s.item()) for s in sizes[:r]))
-    keys = shard.copy()
     idx = torch.arange(offset + 1, offset + 1 + shard.length, dtype=torch.int64, device=dev)
     payload = CuArray(idx.view(torch.uint8), (shard.length,), dt.I64)
-    ops.sort_pairs(keys, payload, rev)
     if G == 1:
+        keys = shard.copy()
+        ops.sort_pairs(keys, payload, rev)
         return payload
+    if G <= MAX_PARTITION_BUCKETS and hasattr(ops, "partition"):
+        spl = _splitters(shard, rev, group, ops)
+        if spl is None:
+            return payload
+        pk, pp, counts = ops.partition(shard, payload, spl, G, rev)
+        bounds = np.concatenate([[0], np.cumsum(counts.to_host().astype(np.int64))])
+        (rk, rp), _ = _exchange(pk, bounds, group, extra=pp)
+        ops.sort_pairs(rk, rp, rev)
+        return rp
+    keys = shard.copy()
+    ops.sort_pairs(keys, payload, rev)
     spl = _splitters(keys, rev, group, ops)
     if spl is None:
         return payload

@@ -215,6 +215,16 @@ int32_t b200_search_sorted(const void *sorted_keys, int64_t n, const void *needl
                            int32_t dtype_key, int32_t descending, void *lower_bounds_dev,
                            b200_stream_t stream);
 
+/* Stable partition of keys (and an optional 8-byte payload) into `nbuckets` <= 16 buckets by
+ * nbuckets-1 splitter keys (device): bucket b = keys with splitter[b-1] <= key < splitter[b] in
+ * the sort's order (isless / descending).  bucket_counts_dev: int64[nbuckets].  First stage of the
+ * multi-GPU sample sort: partition the unsorted shard, all-to-all, sort once. */
+int32_t b200_partition_workspace_bytes(int64_t n, int32_t nbuckets, size_t *bytes);
+int32_t b200_partition(void *workspace, size_t workspace_bytes, const void *keys_in, void *keys_out,
+                       const void *payload_in, void *payload_out, int32_t dtype_key, int64_t n,
+                       const void *splitters, int32_t nbuckets, int32_t descending,
+                       void *bucket_counts_dev, b200_stream_t stream);
+
 /* ---- select: findall(::CuArray{Bool}) (indexing.jl:26-66) --------------- */
 /* Writes the 1-based linear indices (dtype_index I32/I64) of the non-zero flags
  * to `indices` in order and the number found to *count_dev (device int64).

@@ -62,6 +62,19 @@ class FakeOps:
         keys.buf.copy_(torch.from_numpy(np.ascontiguousarray(k[perm]).view(np.uint8).copy()))
         payload.buf.copy_(torch.from_numpy(np.ascontiguousarray(p[perm]).view(np.uint8).copy()))
 
+    def partition(self, keys, payload, splitters, nbuckets, rev):
+        k = keys.to_host()
+        ke = self.o.total_order_key(k)
+        se = self.o.total_order_key(splitters.to_host())
+        if rev:
+            ke, se = ~ke, ~se
+        bid = np.searchsorted(se, ke, side="right") if se.size else np.zeros(k.size, dtype=np.int64)
+        order = np.argsort(bid, kind="stable")
+        counts = np.bincount(bid, minlength=nbuckets).astype(np.int64)
+        kout = _mk(k[order], self.b)
+        pout = _mk(payload.to_host()[order], self.b) if payload is not None else None
+        return kout, pout, _mk(counts, self.b)
+
     def lower_bound(self, sorted_keys, needles, rev):
         ks = self.o.total_order_key(sorted_keys.to_host())
         nd = self.o.total_order_key(needles.to_host())

@@ -250,3 +250,29 @@ def test_small_block_sort(b, n, dtype):
     a = rand(dtype, n)
     np.testing.assert_array_equal(bits(b.Array(b.sort_(b.CuArray(a)))), bits(oracle.sort(a)))
     np.testing.assert_array_equal(b.Array(b.sortperm(b.CuArray(a), rev=True)), oracle.sortperm(a, rev=True))
+
+
+@pytest.mark.parametrize("dtype", ["float32", "uint32", "int64", "float16", "uint8"])
+@pytest.mark.parametrize("nb", [1, 2, 8, 16])
+@pytest.mark.parametrize("rev", [False, True])
+def test_partition_by_splitters(b, dtype, nb, rev):
+    """b200_partition: stable multi-way partition used by the multi-GPU sample sort."""
+    ops = b.multigpu.DeviceOps()
+    for n in (0, 5, 4096, 100_003):
+        a = rand(dtype, n)
+        if dtype.startswith("float") and n > 10:
+            a[3] = np.nan
+        spl = oracle.sort(rand(dtype, nb - 1), rev=rev) if nb > 1 else np.zeros(0, dtype=a.dtype)
+        pay = np.arange(n, dtype=np.int64)
+        kout, pout, counts = ops.partition(b.CuArray(a), b.CuArray(pay), b.CuArray(spl), nb, rev)
+        ke, se = oracle.total_order_key(a), oracle.total_order_key(spl)
+        if rev:
+            ke, se = ~ke, ~se
+        bid = np.searchsorted(se, ke, side="right") if nb > 1 else np.zeros(n, dtype=np.int64)
+        order = np.argsort(bid, kind="stable")
+        np.testing.assert_array_equal(b.Array(counts), np.bincount(bid, minlength=nb).astype(np.int64))
+        np.testing.assert_array_equal(b.Array(pout), pay[order])
+        np.testing.assert_array_equal(bits(b.Array(kout)), bits(a[order]))
+        k2, p2, c2 = ops.partition(b.CuArray(a), None, b.CuArray(spl), nb, rev)
+        assert p2 is None
+        np.testing.assert_array_equal(bits(b.Array(k2)), bits(a[order]))
