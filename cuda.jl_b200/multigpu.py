@@ -177,24 +177,41 @@ OVERSAMPLE = 32     # regular samples per rank and per destination
 
 
 def _exchange(c_sorted, bounds_host, group, extra=None):
-    """All-to-all of the G segments [bounds[k], bounds[k+1]) of a locally sorted shard."""
+    """All-to-all of the G segments [bounds[k], bounds[k+1]) of a bucketed shard.
+
+    The segments differ in size, but torch/NCCL's UNEVEN all_to_all_single runs at a quarter of
+    the speed of the even one on 8 B200s (measured, 1 GiB per rank: 5.8 ms vs 1.6 ms), so every
+    segment travels in a slot of the global maximum size (samples keep the imbalance at a few
+    percent) and the received slots are compacted afterwards (device-to-device copies)."""
     G, r = _world(group)
-    send_counts = torch.tensor(np.diff(bounds_host), dtype=torch.int64)
-    all_counts = [torch.empty(G, dtype=torch.int64) for _ in range(G)]
     dev = c_sorted.buf.device
-    sc = send_counts.to(dev) if dev.type == "cuda" else send_counts
-    ac = [t.to(dev) for t in all_counts] if dev.type == "cuda" else all_counts
-    dist.all_gather(ac, sc, group=group)
-    counts = torch.stack(ac).cpu().numpy()               # counts[src, dst]
+    send_counts = np.diff(bounds_host).astype(np.int64)
+    sc = torch.from_numpy(send_counts).to(dev)
+    allc = torch.empty(G * G, dtype=torch.int64, device=dev)
+    if dev.type == "cuda":
+        dist.all_gather_into_tensor(allc, sc, group=group)
+    else:
+        _all_gather_fallback(allc, sc, group)
+    counts = allc.view(G, G).cpu().numpy()               # counts[src, dst]
     recv_counts = counts[:, r]
     n_recv = int(recv_counts.sum())
+    slot = int(counts.max())
     outs = []
     for c in (c_sorted,) + ((extra,) if extra is not None else ()):
         t_in = _typed(c)
-        t_out = torch.empty(n_recv, dtype=t_in.dtype, device=dev)
-        dist.all_to_all_single(t_out, t_in, output_split_sizes=[int(x) for x in recv_counts],
-                               input_split_sizes=[int(x) for x in send_counts], group=group)
-        outs.append(CuArray(t_out.view(torch.uint8), (n_recv,), c.eltype))
+        if slot == 0:
+            outs.append(CuArray(torch.empty(0, dtype=torch.uint8, device=dev), (0,), c.eltype))
+            continue
+        send = torch.empty(G * slot, dtype=t_in.dtype, device=dev)
+        for k in range(G):
+            if send_counts[k]:
+                send[k * slot:k * slot + int(send_counts[k])].copy_(t_in[int(bounds_host[k]):int(bounds_host[k + 1])])
+        recv = torch.empty(G * slot, dtype=t_in.dtype, device=dev)
+        dist.all_to_all_single(recv, send, group=group)
+        t_out = torch.cat([recv[k * slot:k * slot + int(recv_counts[k])] for k in range(G)]) if n_recv else \
+            torch.empty(0, dtype=t_in.dtype, device=dev)
+        outs.append(CuArray(t_out.view(torch.uint8) if n_recv else torch.empty(0, dtype=torch.uint8, device=dev),
+                            (n_recv,), c.eltype))
     return outs, counts
 
 
