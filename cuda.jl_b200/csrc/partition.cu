@@ -57,11 +57,30 @@ __global__ void __launch_bounds__(RX_THREADS) partition_count_kernel(PartParams 
     K keys[PT_ITEMS];
     unsigned char bid[PT_ITEMS];
     load_tile_buckets<K>(p, s_spl, tile_base, valid, warp * (32 * PT_ITEMS) + lane, keys, bid);
-    for (int b = 0; b < p.G; ++b) {
-        unsigned int c = 0;
+    // per-thread counts packed 8 bits per bucket (<= 16 items per thread), widened to 16-bit fields
+    // before the warp reduction (<= 512 per warp), then one shared atomic per bucket per warp
+    unsigned long long pk[2] = {0ull, 0ull};
 #pragma unroll
-        for (int i = 0; i < PT_ITEMS; ++i) c += __popc(__ballot_sync(0xffffffffu, bid[i] == b));
-        if (lane == 0) atomicAdd(&s_cnt[b], c);
+    for (int i = 0; i < PT_ITEMS; ++i) {
+        const unsigned int bsel = bid[i];
+        if (bsel < PT_MAXB) pk[bsel >> 3] += 1ull << ((bsel & 7) * 8);
+    }
+    unsigned long long wide[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        wide[2 * h] = pk[h] & 0x00FF00FF00FF00FFull;            // buckets 8h + {0,2,4,6}
+        wide[2 * h + 1] = (pk[h] >> 8) & 0x00FF00FF00FF00FFull; // buckets 8h + {1,3,5,7}
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) wide[q] += __shfl_xor_sync(0xffffffffu, wide[q], o);
+    }
+    if (lane < p.G) {
+        const int b = lane;
+        const unsigned long long w = wide[2 * (b >> 3) + (b & 1)];
+        const unsigned int c = (unsigned int)((w >> (16 * ((b & 7) >> 1))) & 0xFFFFull);
+        if (c) atomicAdd(&s_cnt[b], c);
     }
     __syncthreads();
     if (tid < p.G) p.tile_counts[(int64_t)tid * p.tiles + t] = s_cnt[tid];

@@ -174,6 +174,8 @@ def _all_gather_fallback(out_t, in_t, group):
 
 # ----------------------------------------------------------------------------- sort
 OVERSAMPLE = 32     # regular samples per rank and per destination
+import os as _os
+PADDED_EXCHANGE_MIN_RANKS = int(_os.environ.get("B200_PADDED_EXCHANGE_MIN_RANKS", "6"))   # from this many ranks on, equal-size slots beat the uneven all-to-all
 
 
 def _exchange(c_sorted, bounds_host, group, extra=None):
@@ -197,8 +199,17 @@ def _exchange(c_sorted, bounds_host, group, extra=None):
     n_recv = int(recv_counts.sum())
     slot = int(counts.max())
     outs = []
+    padded = G >= PADDED_EXCHANGE_MIN_RANKS
     for c in (c_sorted,) + ((extra,) if extra is not None else ()):
         t_in = _typed(c)
+        if not padded:
+            # few ranks: the uneven collective is fine (measured at 2 GPUs: 1.6 ms vs 4.2 ms padded)
+            t_out = torch.empty(n_recv, dtype=t_in.dtype, device=dev)
+            dist.all_to_all_single(t_out, t_in, output_split_sizes=[int(x) for x in recv_counts],
+                                   input_split_sizes=[int(x) for x in send_counts], group=group)
+            outs.append(CuArray(t_out.view(torch.uint8) if n_recv else torch.empty(0, dtype=torch.uint8, device=dev),
+                                (n_recv,), c.eltype))
+            continue
         if slot == 0:
             outs.append(CuArray(torch.empty(0, dtype=torch.uint8, device=dev), (0,), c.eltype))
             continue

@@ -85,6 +85,9 @@ class FakeOps:
 
 def _worker(rank, world, port, case, ret):
     try:
+        if case == "sort_padded":       # force the equal-slot exchange used from 6 ranks on
+            os.environ["B200_PADDED_EXCHANGE_MIN_RANKS"] = "2"
+            case = "sort"
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(port)
         dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -169,10 +172,10 @@ def test_sharded_reduce_and_scan(world):
     assert np.all(np.abs(got - ref) <= oracle.scan_tolerance(full_f, 1, np.float32) + 1e-7 * ref)
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sample_sort(world):
+@pytest.mark.parametrize("world,case", [(2, "sort"), (3, "sort"), (3, "sort_padded")])
+def test_sample_sort(world, case):
     import oracle
-    res = _run(world, "sort")
+    res = _run(world, case)
     rng = np.random.default_rng(1234)
     full = rng.standard_normal(50_000).astype(np.float32)
     full[::97] = 0.25
