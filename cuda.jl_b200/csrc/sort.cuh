@@ -157,7 +157,6 @@ struct OnesweepParams {
     int32_t gen_payload;              // first sortperm pass: payload = element index
     int32_t index_dtype;              // last sortperm pass: store index_base + payload as this dtype; -1: raw payload
     int64_t index_base;               // 1 for per-segment 1-based indices (+ segment offset when linear)
-    int32_t debug;
 };
 
 template <class LookT> struct LookBits;
@@ -359,7 +358,7 @@ __global__ void __launch_bounds__(RX_THREADS) radix_onesweep_kernel(OnesweepPara
 
     // ---- decoupled look-back for digit d
     unsigned long long excl = 0;
-    if (t > 0 && !(p.debug & 1)) {
+    if (t > 0) {
         int64_t u = t - 1;
         bool done = false;
         while (!done) {

@@ -145,7 +145,6 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
         p.gen_payload = (pass == 0 && c.mode == SORT_PERM);
         p.index_dtype = (pass == P - 1 && c.mode == SORT_PERM) ? c.index_dtype : -1;
         p.index_base = c.index_base;
-        { const char *e = getenv("B200_SORT_DEBUG"); p.debug = e ? atoi(e) : 0; }
         if (c.mode == SORT_PERM) {
             char *kb[2] = {kbuf0, kbuf1};
             char *vb[2] = {vbuf0, vbuf1};
