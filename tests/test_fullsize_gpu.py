@@ -1,0 +1,128 @@
+"""Parity at BASELINE.json's FULL sizes through size-independent properties (the oracle cannot
+finish 2^30-element cases in seconds): checksums, linearity, sortedness, permutation validity,
+stability.  Checks run on the device with torch as test plumbing; every value under test comes
+from libb200arrays."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N30 = 1 << 30
+M = 16384
+
+
+def _gen(torch, seed):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    return g
+
+
+def test_configs1_matrix_reductions_full_size(b):
+    """configs[1]: 16384 x 16384 Float32 / Int32 / Bool: sum(dims=1) and sum(dims=2) must agree with each
+    other and with the full reduction (ints exactly; floats within the stated tolerance); maximum must be
+    an element that dominates every column maximum; count == sum of per-column counts."""
+    import torch
+    g = _gen(torch, 0xB200 + 1)
+    Ai = torch.randint(-2**20, 2**20, (M * M,), device="cuda", generator=g, dtype=torch.int32)
+    cA = b.CuArray.from_torch(Ai, (M, M))
+    s1 = b.sum(cA, dims=1); s2 = b.sum(cA, dims=2); tot = b.sum(cA)
+    assert s1.eltype == b.dtypes.I64
+    assert int(s1.typed().sum().item()) == int(tot) == int(s2.typed().sum().item())
+    ref_cols = Ai.view(M, M).to(torch.int64).sum(dim=1)            # torch view is row-major: row k = Julia column k
+    assert torch.equal(s1.typed(), ref_cols)
+    assert torch.equal(s2.typed(), Ai.view(M, M).to(torch.int64).sum(dim=0))
+    mx1 = b.maximum(cA, dims=1)
+    assert int(b.maximum(cA)) == int(mx1.typed().max().item()) == int(Ai.max().item())
+    del Ai, cA
+    Af = torch.rand(M * M, device="cuda", generator=g, dtype=torch.float32)
+    cF = b.CuArray.from_torch(Af, (M, M))
+    f1 = b.sum(cF, dims=1).typed().double(); f2 = b.sum(cF, dims=2).typed().double(); ft = float(b.sum(cF))
+    ref = float(Af.double().sum().item())
+    tol = 4 * 28 * 2.0 ** -23 * ref                                 # 4*log2(n)*eps(Float32)*sum|x|, n = 2^28
+    assert abs(ft - ref) <= tol and abs(float(f1.sum()) - ref) <= tol and abs(float(f2.sum()) - ref) <= tol
+    assert float((f1 - Af.view(M, M).double().sum(dim=1)).abs().max()) <= 4 * 14 * 2.0 ** -23 * M
+    del Af, cF
+    Bm = torch.rand(M * M, device="cuda", generator=g) < 0.5
+    cB = b.CuArray.from_torch(Bm, (M, M))
+    assert int(b.count(cB)) == int(Bm.sum().item()) == int(b.count(cB, dims=2).typed().sum().item())
+
+
+@pytest.mark.parametrize("dtype", ["int64", "float32"])
+def test_cumsum_full_size(b, dtype):
+    """configs[2]: cumsum of 2^30 elements: last element == sum, first differences reproduce the input
+    (exactly for Int64), inclusive == exclusive shifted."""
+    import torch
+    g = _gen(torch, 0xB200 + 2)
+    if dtype == "int64":
+        V = torch.randint(-2**20, 2**20, (N30,), device="cuda", generator=g, dtype=torch.int64)
+        cV = b.CuArray.from_torch(V)
+        O = b.cumsum(cV).typed()
+        assert int(O[-1].item()) == int(b.sum(cV)) == int(V.sum().item())
+        step = 1 << 27
+        for lo in range(0, N30, step):                                # in slices: keeps the check's own memory small
+            hi = min(lo + step, N30)
+            d = O[lo:hi].clone()
+            d[1:] -= O[lo:hi - 1]
+            if lo:
+                d[0] -= O[lo - 1]
+            assert torch.equal(d, V[lo:hi])
+        E = b.accumulate(b.add, cV, exclusive=True).typed()
+        assert int(E[0].item()) == 0 and torch.equal(E[1:1 << 24], O[:(1 << 24) - 1]) and int(E[-1].item()) == int(O[-2].item())
+    else:
+        V = torch.rand(N30, device="cuda", generator=g, dtype=torch.float32)
+        cV = b.CuArray.from_torch(V)
+        O = b.cumsum(cV).typed()
+        ref_total = float(V.double().sum().item())
+        tol = 4 * 30 * 2.0 ** -23                                     # relative, 4*log2(n)*eps
+        assert abs(float(O[-1].item()) - ref_total) <= tol * ref_total
+        idx = torch.randint(0, N30, (4096,), device="cuda", generator=g)
+        for i in idx[:64].tolist():                                   # spot prefixes against a Float64 prefix sum
+            refp = float(V[:i + 1].double().sum().item())
+            assert abs(float(O[i].item()) - refp) <= tol * refp + 1e-6
+        # non-negative input: monotone up to the rounding of differently associated prefixes (a few ulps)
+        d = O[1:1 << 26].double() - O[:(1 << 26) - 1].double()
+        assert float(d.min().item()) >= -4 * 2.0 ** -23 * float(O[(1 << 26) - 1].item())
+
+
+@pytest.mark.parametrize("dtype", ["uint32", "float32"])
+def test_sort_and_sortperm_full_size(b, dtype):
+    """configs[3]: sort! / sortperm of 2^30 keys: sortedness, multiset checksums, permutation validity,
+    stability among equal keys."""
+    import torch
+    g = _gen(torch, 0xB200 + 3)
+    if dtype == "uint32":
+        raw = torch.randint(-2**31, 2**31 - 1, (N30,), device="cuda", generator=g, dtype=torch.int32)
+        raw[:1 << 20] = raw[0]                                        # a block of duplicates
+        cK = b.CuArray.from_torch(raw, (N30,), b.dtypes.U32)
+        as_ord = lambda t: t.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    else:
+        raw = torch.rand(N30, device="cuda", generator=g, dtype=torch.float32) - 0.5
+        raw[:1 << 20] = raw[0]
+        raw[5] = float("inf"); raw[6] = float("-inf"); raw[7] = 0.0; raw[8] = -0.0
+        cK = b.CuArray.from_torch(raw, (N30,), b.dtypes.F32)
+        as_ord = lambda t: t.view(torch.float32).double()
+    bits0 = raw.view(torch.int32)
+    chk = (int(bits0.to(torch.int64).sum().item()), int(torch.bitwise_xor(bits0[::2], bits0[1::2]).to(torch.int64).sum().item()))
+    S = b.sort(cK)
+    s_bits = S.buf.view(torch.int32)
+    step = 1 << 27
+    for lo in range(0, N30 - 1, step):
+        hi = min(lo + step + 1, N30)
+        o = as_ord(s_bits[lo:hi])
+        assert bool((o[1:] >= o[:-1]).all().item()), f"not sorted in [{lo},{hi})"
+    assert int(s_bits.to(torch.int64).sum().item()) == chk[0]          # same multiset (sum of bit patterns)
+    del S, s_bits
+    P = b.sortperm(cK).typed()                                          # Int64, 1-based
+    assert int(P.min().item()) == 1 and int(P.max().item()) == N30
+    assert int(P.sum().item()) == N30 * (N30 + 1) // 2
+    for lo in range(0, N30 - 1, step):
+        hi = min(lo + step + 1, N30)
+        p = P[lo:hi] - 1
+        o = as_ord(bits0[p])
+        assert bool((o[1:] >= o[:-1]).all().item())
+        kb = bits0[p]
+        ties = kb[1:] == kb[:-1]                                      # identical keys (bitwise: -0.0 and +0.0 are different keys)
+        assert bool((p[1:][ties] > p[:-1][ties]).all().item()), "sortperm is not stable"
+    seen = torch.zeros(N30, dtype=torch.uint8, device="cuda")
+    seen[P - 1] = 1
+    assert int(seen.sum(dtype=torch.int64).item()) == N30              # a permutation: every index exactly once
