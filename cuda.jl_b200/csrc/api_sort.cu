@@ -63,10 +63,14 @@ static int32_t run_block(int kb, const BlockSortParams &bp, int perm, int64_t ns
 
 template <class T>
 static int32_t transpose_T(const void *in, void *out, int64_t rows, int64_t cols, int64_t batch, cudaStream_t st) {
-    if (batch > 65535 || cdiv(cols, 32) > 65535) return B200_INVALID_VALUE;
-    dim3 grid((unsigned int)cdiv(rows, 32), (unsigned int)cdiv(cols, 32), (unsigned int)batch);
-    transpose_batched_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(in), static_cast<T *>(out), rows, cols);
-    B200_CHECK_LAUNCH();
+    if (cdiv(cols, 32) > 65535) return B200_INVALID_VALUE;
+    for (int64_t b0 = 0; b0 < batch; b0 += 65535) {          // gridDim.z is limited to 65535
+        const int64_t nb = batch - b0 < 65535 ? batch - b0 : 65535;
+        dim3 grid((unsigned int)cdiv(rows, 32), (unsigned int)cdiv(cols, 32), (unsigned int)nb);
+        transpose_batched_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(in) + b0 * rows * cols,
+                                                          static_cast<T *>(out) + b0 * rows * cols, rows, cols);
+        B200_CHECK_LAUNCH();
+    }
     return B200_OK;
 }
 static int32_t transpose_bytes(int elem, const void *in, void *out, int64_t rows, int64_t cols, int64_t batch, cudaStream_t st) {
