@@ -19,6 +19,9 @@ namespace b200 {
 constexpr int RX_THREADS = 256;
 constexpr int RX_WARPS = RX_THREADS / 32;
 constexpr int RX_RADIX = 256;
+#ifndef B200_RX_ATOMOR_MASK
+#define B200_RX_ATOMOR_MASK 0
+#endif
 #ifndef B200_RX_MATCH_MASK
 #define B200_RX_MATCH_MASK 0x8888   // items 3, 7, 11, 15 of every 16
 #endif
@@ -208,6 +211,9 @@ __global__ void __launch_bounds__(RX_THREADS) radix_onesweep_kernel(OnesweepPara
     VT *s_vals = reinterpret_cast<VT *>(reinterpret_cast<unsigned char *>(s_keys) + ((TILE * sizeof(K) + 15) / 16) * 16);
     __shared__ unsigned long long s_ticket;
     __shared__ unsigned int s_wsum[RX_WARPS];
+#if B200_RX_ATOMOR_MASK
+    __shared__ unsigned int s_match[RX_WARPS][RX_RADIX];   // per-warp peer-mask table for the atomic-or matched items
+#endif
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_ticket = atomicAdd(p.ticket, 1ull);
@@ -215,6 +221,10 @@ __global__ void __launch_bounds__(RX_THREADS) radix_onesweep_kernel(OnesweepPara
     unsigned int *whist = s_whist + warp * RX_RADIX;
 #pragma unroll
     for (int k = 0; k < RX_RADIX / 32; ++k) whist[k * 32 + lane] = 0;
+#if B200_RX_ATOMOR_MASK
+#pragma unroll
+    for (int k = 0; k < RX_RADIX / 32; ++k) s_match[warp][k * 32 + lane] = 0;
+#endif
     __syncthreads();
     const int64_t t = (int64_t)s_ticket;
     const int64_t tile_base = t * TILE;
@@ -276,6 +286,16 @@ __global__ void __launch_bounds__(RX_THREADS) radix_onesweep_kernel(OnesweepPara
         if ((B200_RX_MATCH_MASK >> (i & 15)) & 1) {
             // a quarter of the items go through MATCH.ANY so that the ADU pipe shares the load with the ALU
             peers = __match_any_sync(0xffffffffu, digit);
+#if B200_RX_ATOMOR_MASK
+        } else if ((B200_RX_ATOMOR_MASK >> (i & 15)) & 1) {
+            // ... and some through a shared-memory atomic-or table, which runs on the LSU pipe
+            volatile unsigned int *mt = &s_match[warp][digit];
+            atomicOr(const_cast<unsigned int *>(mt), 1u << lane);
+            __syncwarp();
+            peers = *mt;
+            __syncwarp();
+            if ((peers & lt_mask) == 0u) *mt = 0u;
+#endif
         } else {
             unsigned int differ = 0;   // lanes whose digit differs from mine in some bit
 #pragma unroll
