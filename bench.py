@@ -294,7 +294,9 @@ def run_product(args, rank, world, local_rank):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("reduce_strided_kernel_f32_dims2_bytes_per_launch")
+            tj = json.load(f)
+            traffic = tj.get("reduce_strided_kernel_f32_dims2_bytes_per_launch" if (dom[0] and "strided" in dom[0])
+                             else "reduce_contig_block_kernel_f32_dims1_bytes_per_launch")
     except Exception:
         pass
     roofline = None
