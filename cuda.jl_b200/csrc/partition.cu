@@ -20,6 +20,12 @@ struct PartParams {
     void *keys_out;
     const void *vals_in;     // optional 8-byte payload
     void *vals_out;
+    // scatter destinations: bucket b goes to dst_keys[b] (+ dst_vals[b]) starting at element dst_base[b];
+    // local partition: all the same buffer with the packed bucket bases; multi-GPU: peer (NVLink-mapped) buffers
+    void *dst_keys[16];
+    void *dst_vals[16];
+    long long dst_base[16];
+    int32_t local_bases;     // 1: dst_base is derived from bucket_counts on the device (packed local output)
     const void *splitters;   // G-1 raw keys (device)
     long long *tile_counts;  // [G][tiles]: counts, then exclusive prefixes over tiles
     long long *bucket_counts;// [G]
@@ -116,11 +122,19 @@ __global__ void __launch_bounds__(256) partition_scan_kernel(PartParams p) {
     if (tid == 0) p.bucket_counts[b] = s_run;
 }
 
+// Ranked scatter.  Keys (and payload) are first staged in shared memory grouped by bucket, then
+// written out with consecutive threads on consecutive addresses of each bucket run (~TILE/G keys,
+// i.e. full 128-byte lines): this is what makes stores into PEER memory over NVLink efficient.
 template <class K, bool HAS_V>
 __global__ void __launch_bounds__(RX_THREADS) partition_scatter_kernel(PartParams p) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    K *s_keys = reinterpret_cast<K *>(s_raw);                                        // [PT_TILE]
+    unsigned char *s_bid = reinterpret_cast<unsigned char *>(s_keys + PT_TILE);      // [PT_TILE]
+    unsigned long long *s_vals = reinterpret_cast<unsigned long long *>(s_bid + PT_TILE);   // [PT_TILE] (HAS_V)
     __shared__ K s_spl[PT_MAXB];
     __shared__ unsigned int s_wcnt[RX_WARPS][PT_MAXB];
-    __shared__ long long s_base[PT_MAXB];
+    __shared__ unsigned int s_boff[PT_MAXB];       // start of each bucket run inside the staged tile
+    __shared__ long long s_dst[PT_MAXB];           // destination element index of the run's first key
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < p.G - 1) s_spl[tid] = key_encode<K>(static_cast<const K *>(p.splitters)[tid], p.xf);
     if (tid < RX_WARPS * PT_MAXB) (&s_wcnt[0][0])[tid] = 0;
@@ -156,30 +170,43 @@ __global__ void __launch_bounds__(RX_THREADS) partition_scatter_kernel(PartParam
     }
     __syncthreads();
     if (tid < p.G) {
-        // bucket base = sum of the totals of the buckets before it; + this tile's prefix; then per-warp offsets
-        long long base = 0;
-        for (int b = 0; b < tid; ++b) base += p.bucket_counts[b];
-        base += p.tile_counts[(int64_t)tid * p.tiles + t];
-        s_base[tid] = base;
         unsigned int run = 0;
         for (int w = 0; w < RX_WARPS; ++w) { const unsigned int c = s_wcnt[w][tid]; s_wcnt[w][tid] = run; run += c; }
+        s_boff[tid] = run;                         // bucket total for now
+        long long base = p.dst_base[tid];
+        if (p.local_bases) { base = 0; for (int b = 0; b < tid; ++b) base += p.bucket_counts[b]; }
+        s_dst[tid] = base + p.tile_counts[(int64_t)tid * p.tiles + t];
     }
     __syncthreads();
-    K *kout = static_cast<K *>(p.keys_out);
+    if (tid == 0) {
+        unsigned int run = 0;
+        for (int b = 0; b < p.G; ++b) { const unsigned int c = s_boff[b]; s_boff[b] = run; run += c; }
+    }
+    __syncthreads();
     const unsigned long long *vin = static_cast<const unsigned long long *>(p.vals_in) + tile_base + idx0;
-    unsigned long long *vout = static_cast<unsigned long long *>(p.vals_out);
 #pragma unroll
     for (int i = 0; i < PT_ITEMS; ++i) {
         if (bid[i] < PT_MAXB) {
-            const long long dst = s_base[bid[i]] + s_wcnt[warp][bid[i]] + ranks[i];
-            kout[dst] = keys[i];
-            if constexpr (HAS_V) vout[dst] = ldg_stream(vin + i * 32);
+            const unsigned int pos = s_boff[bid[i]] + s_wcnt[warp][bid[i]] + ranks[i];
+            s_keys[pos] = keys[i];
+            s_bid[pos] = bid[i];
+            if constexpr (HAS_V) s_vals[pos] = ldg_stream(vin + i * 32);
         }
+    }
+    __syncthreads();
+    for (int i = tid; i < valid; i += RX_THREADS) {
+        const int b = s_bid[i];
+        const long long dst = s_dst[b] + (i - (int)s_boff[b]);
+        static_cast<K *>(p.dst_keys[b])[dst] = s_keys[i];
+        if constexpr (HAS_V) static_cast<unsigned long long *>(p.dst_vals[b])[dst] = s_vals[i];
     }
 }
 
+static size_t scatter_smem(int kb, bool has_v) { return (size_t)PT_TILE * (kb + 1) + 16 + (has_v ? (size_t)PT_TILE * 8 : 0); }
+
+// phase: 1 = count + scan (leaves the per-tile prefixes in the workspace), 2 = scatter, 3 = both
 template <class K>
-static int32_t run_partition(void *ws, size_t wsb, PartParams p, bool has_v, cudaStream_t st, size_t *query) {
+static int32_t run_partition(void *ws, size_t wsb, PartParams p, bool has_v, int phase, cudaStream_t st, size_t *query) {
     p.tiles = cdiv(p.n, PT_TILE);
     Carver c(ws);
     long long *tile_counts = c.take<long long>((size_t)p.G * p.tiles);
@@ -188,14 +215,45 @@ static int32_t run_partition(void *ws, size_t wsb, PartParams p, bool has_v, cud
     if (!ws) return B200_INVALID_VALUE;
     if (p.tiles > 2147483647LL) return B200_INVALID_VALUE;
     p.tile_counts = tile_counts;
-    partition_count_kernel<K><<<(unsigned int)p.tiles, RX_THREADS, 0, st>>>(p);
-    B200_CHECK_LAUNCH();
-    partition_scan_kernel<<<p.G, 256, 0, st>>>(p);
-    B200_CHECK_LAUNCH();
-    if (has_v) partition_scatter_kernel<K, true><<<(unsigned int)p.tiles, RX_THREADS, 0, st>>>(p);
-    else partition_scatter_kernel<K, false><<<(unsigned int)p.tiles, RX_THREADS, 0, st>>>(p);
-    B200_CHECK_LAUNCH();
+    if (phase & 1) {
+        partition_count_kernel<K><<<(unsigned int)p.tiles, RX_THREADS, 0, st>>>(p);
+        B200_CHECK_LAUNCH();
+        partition_scan_kernel<<<p.G, 256, 0, st>>>(p);
+        B200_CHECK_LAUNCH();
+    }
+    if (phase & 2) {
+        const size_t smem = scatter_smem((int)sizeof(K), has_v);
+        static thread_local bool attr_set[64][2];
+        int dev = 0;
+        B200_CUDA_TRY(cudaGetDevice(&dev));
+        if (has_v) {
+            auto kern = partition_scatter_kernel<K, true>;
+            if (dev >= 0 && dev < 64 && !attr_set[dev][1]) {
+                B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_set[dev][1] = true;
+            }
+            kern<<<(unsigned int)p.tiles, RX_THREADS, smem, st>>>(p);
+        } else {
+            auto kern = partition_scatter_kernel<K, false>;
+            if (dev >= 0 && dev < 64 && !attr_set[dev][0]) {
+                B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_set[dev][0] = true;
+            }
+            kern<<<(unsigned int)p.tiles, RX_THREADS, smem, st>>>(p);
+        }
+        B200_CHECK_LAUNCH();
+    }
     return B200_OK;
+}
+
+template <class... Args> static int32_t run_partition_kb(int kb, Args... args) {
+    switch (kb) {
+        case 1: return run_partition<uint8_t>(args...);
+        case 2: return run_partition<uint16_t>(args...);
+        case 4: return run_partition<uint32_t>(args...);
+        case 8: return run_partition<uint64_t>(args...);
+        default: return B200_UNSUPPORTED;
+    }
 }
 
 // same transform as the sort (api_sort.cu make_xform), NaNs canonical so that they all go last
@@ -231,36 +289,65 @@ int32_t b200_partition_workspace_bytes(int64_t n, int32_t nbuckets, size_t *byte
     if (n == 0) return B200_OK;
     PartParams p{};
     p.n = n; p.G = nbuckets;
-    return run_partition<uint32_t>(nullptr, 0, p, false, nullptr, bytes);
+    return run_partition<uint32_t>(nullptr, 0, p, false, 3, nullptr, bytes);
 }
 
-int32_t b200_partition(void *workspace, size_t workspace_bytes, const void *keys_in, void *keys_out,
-                       const void *payload_in, void *payload_out, int32_t dtype_key, int64_t n,
-                       const void *splitters, int32_t nbuckets, int32_t descending, void *bucket_counts_dev,
-                       b200_stream_t stream) {
+static int32_t partition_common(void *workspace, size_t workspace_bytes, const void *keys_in, const void *payload_in,
+                                int32_t dtype_key, int64_t n, const void *splitters, int32_t nbuckets,
+                                int32_t descending, void *bucket_counts_dev, int phase, void *const *dst_keys,
+                                void *const *dst_payload, const int64_t *dst_base, int local_bases,
+                                b200_stream_t stream) {
     using namespace b200;
     if (n < 0 || nbuckets < 1 || nbuckets > PT_MAXB || !bucket_counts_dev) return B200_INVALID_VALUE;
     SortXform xf; int kb;
     if (!part_xform(dtype_key, descending, xf, kb)) return B200_UNSUPPORTED;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (n == 0) {
-        B200_CUDA_TRY(cudaMemsetAsync(bucket_counts_dev, 0, sizeof(long long) * nbuckets, st));
+        if (phase & 1) B200_CUDA_TRY(cudaMemsetAsync(bucket_counts_dev, 0, sizeof(long long) * nbuckets, st));
         return B200_OK;
     }
-    if (!keys_in || !keys_out || (nbuckets > 1 && !splitters) || ((payload_in == nullptr) != (payload_out == nullptr)))
-        return B200_INVALID_VALUE;
+    if (!keys_in || (nbuckets > 1 && !splitters)) return B200_INVALID_VALUE;
     PartParams p{};
-    p.keys_in = keys_in; p.keys_out = keys_out; p.vals_in = payload_in; p.vals_out = payload_out;
+    p.keys_in = keys_in; p.vals_in = payload_in;
     p.splitters = splitters; p.bucket_counts = static_cast<long long *>(bucket_counts_dev);
-    p.n = n; p.G = nbuckets; p.xf = xf;
+    p.n = n; p.G = nbuckets; p.xf = xf; p.local_bases = local_bases;
     const bool has_v = payload_in != nullptr;
-    switch (kb) {
-        case 1: return run_partition<uint8_t>(workspace, workspace_bytes, p, has_v, st, nullptr);
-        case 2: return run_partition<uint16_t>(workspace, workspace_bytes, p, has_v, st, nullptr);
-        case 4: return run_partition<uint32_t>(workspace, workspace_bytes, p, has_v, st, nullptr);
-        case 8: return run_partition<uint64_t>(workspace, workspace_bytes, p, has_v, st, nullptr);
-        default: return B200_UNSUPPORTED;
+    if (phase & 2) {
+        if (!dst_keys || (has_v && !dst_payload)) return B200_INVALID_VALUE;
+        for (int b = 0; b < nbuckets; ++b) {
+            if (!dst_keys[b] || (has_v && !dst_payload[b])) return B200_INVALID_VALUE;
+            p.dst_keys[b] = dst_keys[b];
+            p.dst_vals[b] = has_v ? dst_payload[b] : nullptr;
+            p.dst_base[b] = dst_base ? dst_base[b] : 0;
+        }
     }
+    return run_partition_kb(kb, workspace, workspace_bytes, p, has_v, phase, st, (size_t *)nullptr);
+}
+
+int32_t b200_partition(void *workspace, size_t workspace_bytes, const void *keys_in, void *keys_out,
+                       const void *payload_in, void *payload_out, int32_t dtype_key, int64_t n,
+                       const void *splitters, int32_t nbuckets, int32_t descending, void *bucket_counts_dev,
+                       b200_stream_t stream) {
+    if (n > 0 && (!keys_out || ((payload_in == nullptr) != (payload_out == nullptr)))) return B200_INVALID_VALUE;
+    void *dk[16], *dv[16];
+    for (int b = 0; b < 16; ++b) { dk[b] = keys_out; dv[b] = payload_out; }
+    return partition_common(workspace, workspace_bytes, keys_in, payload_in, dtype_key, n, splitters, nbuckets, descending,
+                            bucket_counts_dev, 3, dk, dv, nullptr, 1, stream);
+}
+
+int32_t b200_partition_count(void *workspace, size_t workspace_bytes, const void *keys_in, int32_t dtype_key, int64_t n,
+                             const void *splitters, int32_t nbuckets, int32_t descending, void *bucket_counts_dev,
+                             b200_stream_t stream) {
+    return partition_common(workspace, workspace_bytes, keys_in, nullptr, dtype_key, n, splitters, nbuckets, descending,
+                            bucket_counts_dev, 1, nullptr, nullptr, nullptr, 0, stream);
+}
+
+int32_t b200_partition_scatter(void *workspace, size_t workspace_bytes, const void *keys_in, const void *payload_in,
+                               int32_t dtype_key, int64_t n, const void *splitters, int32_t nbuckets,
+                               int32_t descending, void *bucket_counts_dev, void *const *dst_keys,
+                               void *const *dst_payload, const int64_t *dst_base, b200_stream_t stream) {
+    return partition_common(workspace, workspace_bytes, keys_in, payload_in, dtype_key, n, splitters, nbuckets, descending,
+                            bucket_counts_dev, 2, dst_keys, dst_payload, dst_base, 0, stream);
 }
 
 }  // extern "C"

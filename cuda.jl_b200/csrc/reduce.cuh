@@ -29,7 +29,10 @@ constexpr int RC_UNROLL = 4;      // independent vector loads in flight per thre
 #define B200_REDUCE_VB 32         // bytes per streaming load: 16 (LDG.E.128) or 32 (LDG.E.256)
 #endif
 constexpr int RS_THREADS = 256;   // strided kernels
-constexpr int RS_UNROLL = 8;
+#ifndef B200_RS_UNROLL
+#define B200_RS_UNROLL 8
+#endif
+constexpr int RS_UNROLL = B200_RS_UNROLL;
 
 template <int VB> struct VecOf;
 template <> struct VecOf<16> { using type = Vec16; __device__ static Vec16 load(const void *p) { return ldg_stream16(p); } };

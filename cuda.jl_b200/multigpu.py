@@ -80,6 +80,41 @@ class DeviceOps:
                                       nbuckets, 1 if rev else 0, counts.pointer, current_stream_handle(dev)))
         return kout, pout, counts
 
+    def partition_count(self, keys, splitters, nbuckets, rev):
+        """Phase 1 of the fused partition + exchange: bucket totals (device Int64[nbuckets]); the returned
+        workspace keeps the per-tile prefixes for partition_scatter."""
+        import ctypes
+        from . import _lib
+        from .cuarray import Workspace
+        lib = _lib.load()
+        dev = keys.buf.device
+        counts = CuArray.undef(dt.I64, (nbuckets,), dev)
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.b200_partition_workspace_bytes(keys.length, nbuckets, ctypes.byref(nbytes)))
+        ws = Workspace(nbytes.value, dev)
+        _lib.check(lib.b200_partition_count(ws.ptr, ws.nbytes, keys.pointer if keys.length else None, keys.eltype,
+                                            keys.length, splitters.pointer if splitters.length else None, nbuckets,
+                                            1 if rev else 0, counts.pointer, current_stream_handle(dev)))
+        return counts, ws
+
+    def partition_scatter(self, ws, keys, payload, splitters, nbuckets, rev, counts, dst_key_ptrs, dst_payload_ptrs,
+                          dst_base):
+        """Phase 2: bucket b is written straight to dst_key_ptrs[b][dst_base[b]:] — peer memory over NVLink."""
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        if keys.length == 0:
+            return
+        PtrArr = ctypes.c_void_p * nbuckets
+        I64Arr = ctypes.c_int64 * nbuckets
+        dk = PtrArr(*[int(x) for x in dst_key_ptrs])
+        dv = PtrArr(*[int(x) for x in dst_payload_ptrs]) if payload is not None else None
+        db = I64Arr(*[int(x) for x in dst_base])
+        _lib.check(lib.b200_partition_scatter(ws.ptr, ws.nbytes, keys.pointer, payload.pointer if payload is not None else None,
+                                              keys.eltype, keys.length, splitters.pointer if splitters.length else None,
+                                              nbuckets, 1 if rev else 0, counts.pointer, dk, dv, db,
+                                              current_stream_handle(keys.buf.device)))
+
     def lower_bound(self, sorted_keys, needles, rev):
         from . import _lib
         lib = _lib.load()
@@ -258,6 +293,61 @@ def _splitters(c_sorted, rev, group, ops):
 
 
 MAX_PARTITION_BUCKETS = 16
+FUSED_EXCHANGE = _os.environ.get("B200_FUSED_EXCHANGE", "1") != "0"
+_SYMM = {}     # (group id, tag) -> (uint8 symmetric tensor, handle); grown on demand, reused across calls
+
+
+def _symm_buffer(tag, nbytes, dev, group):
+    """A symmetric (P2P-mapped on every rank) receive buffer of at least nbytes; collective."""
+    import torch.distributed._symmetric_memory as symm_mem
+    g = group if group is not None else dist.group.WORLD
+    key = (id(g), tag)
+    cur = _SYMM.get(key)
+    if cur is None or cur[0].numel() < nbytes:
+        size = int(nbytes * 1.25) + (1 << 20)
+        t = symm_mem.empty(size, dtype=torch.uint8, device=dev)
+        hdl = symm_mem.rendezvous(t, g)
+        _SYMM[key] = (t, hdl)
+    return _SYMM[key]
+
+
+def _fused_partition_exchange(shard, payload, spl, rev, group, ops):
+    """Partition + all-to-all in ONE kernel: the ranked scatter of b200_partition_scatter stores every
+    bucket directly into the destination rank's receive buffer (symmetric memory, NVLink peer stores,
+    full 128-byte lines), instead of writing buckets locally and handing them to NCCL.
+    Returns (keys CuArray, payload CuArray | None) or None when the path is unavailable."""
+    G, r = _world(group)
+    dev = shard.buf.device
+    ksz = dt.SIZES[shard.eltype]
+    counts, ws = ops.partition_count(shard, spl, G, rev)
+    allc = torch.empty(G * G, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allc, counts.typed(), group=group)
+    cm = allc.view(G, G).cpu().numpy()                      # cm[src, dst]
+    n_recv_all = cm.sum(axis=0)
+    cap = int(n_recv_all.max())                             # same on every rank: the buffers grow collectively
+    kbuf, khdl = _symm_buffer("keys", cap * ksz, dev, group)
+    pbuf = phdl = None
+    if payload is not None:
+        pbuf, phdl = _symm_buffer("payload", cap * 8, dev, group)
+    dst_base = cm[:r, :].sum(axis=0) if r > 0 else np.zeros(G, dtype=np.int64)
+    khdl.barrier()                                          # nobody still reads its receive buffer from a previous call
+    ops.partition_scatter(ws, shard, payload, spl, G, rev, counts, list(khdl.buffer_ptrs),
+                          list(phdl.buffer_ptrs) if phdl is not None else None, dst_base)
+    khdl.barrier()                                          # every rank's peer stores have landed
+    n_recv = int(n_recv_all[r])
+    keys = CuArray(kbuf[:n_recv * ksz].clone(), (n_recv,), shard.eltype)
+    pay = CuArray(pbuf[:n_recv * 8].clone(), (n_recv,), dt.I64) if payload is not None else None
+    return keys, pay, cm
+
+
+def _fused_available(shard, ops):
+    if not (FUSED_EXCHANGE and shard.buf.is_cuda and hasattr(ops, "partition_count")):
+        return False
+    try:
+        import torch.distributed._symmetric_memory  # noqa: F401
+        return True
+    except Exception:
+        return False
 
 
 def _sample_unsorted(c, group):
@@ -285,9 +375,12 @@ def dist_sort(shard, rev=False, group=None, ops=None):
     spl = _splitters(shard, rev, group, ops)            # regular samples of the unsorted shard
     if spl is None:
         return shard.copy(), np.zeros((G, G), dtype=np.int64)
-    parted, _, counts = ops.partition(shard, None, spl, G, rev)
-    bounds = np.concatenate([[0], np.cumsum(counts.to_host().astype(np.int64))])
-    (recv,), cmat = _exchange(parted, bounds, group)
+    if _fused_available(shard, ops):
+        recv, _, cmat = _fused_partition_exchange(shard, None, spl, rev, group, ops)
+    else:
+        parted, _, counts = ops.partition(shard, None, spl, G, rev)
+        bounds = np.concatenate([[0], np.cumsum(counts.to_host().astype(np.int64))])
+        (recv,), cmat = _exchange(parted, bounds, group)
     ops.sort_keys(recv, rev)
     return recv, cmat
 
@@ -327,9 +420,12 @@ def dist_sortperm(shard, rev=False, group=None, ops=None):
         spl = _splitters(shard, rev, group, ops)
         if spl is None:
             return payload
-        pk, pp, counts = ops.partition(shard, payload, spl, G, rev)
-        bounds = np.concatenate([[0], np.cumsum(counts.to_host().astype(np.int64))])
-        (rk, rp), _ = _exchange(pk, bounds, group, extra=pp)
+        if _fused_available(shard, ops):
+            rk, rp, _ = _fused_partition_exchange(shard, payload, spl, rev, group, ops)
+        else:
+            pk, pp, counts = ops.partition(shard, payload, spl, G, rev)
+            bounds = np.concatenate([[0], np.cumsum(counts.to_host().astype(np.int64))])
+            (rk, rp), _ = _exchange(pk, bounds, group, extra=pp)
         ops.sort_pairs(rk, rp, rev)
         return rp
     keys = shard.copy()

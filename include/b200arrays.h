@@ -225,6 +225,21 @@ int32_t b200_partition(void *workspace, size_t workspace_bytes, const void *keys
                        const void *splitters, int32_t nbuckets, int32_t descending,
                        void *bucket_counts_dev, b200_stream_t stream);
 
+/* Two-phase form for the fused partition + exchange of the multi-GPU sort: `count` leaves the
+ * per-tile prefixes in the workspace and the bucket totals in bucket_counts_dev; after the ranks
+ * have exchanged their totals, `scatter` (same workspace, same inputs) writes bucket b straight to
+ * dst_keys[b] (+ dst_payload[b]) starting at element dst_base[b] — the destinations are the
+ * ranks' receive buffers mapped over NVLink (symmetric memory), so the all-to-all is the
+ * kernel's own coalesced peer stores.  dst_* are HOST arrays of nbuckets entries. */
+int32_t b200_partition_count(void *workspace, size_t workspace_bytes, const void *keys_in, int32_t dtype_key,
+                             int64_t n, const void *splitters, int32_t nbuckets, int32_t descending,
+                             void *bucket_counts_dev, b200_stream_t stream);
+int32_t b200_partition_scatter(void *workspace, size_t workspace_bytes, const void *keys_in,
+                               const void *payload_in, int32_t dtype_key, int64_t n, const void *splitters,
+                               int32_t nbuckets, int32_t descending, void *bucket_counts_dev,
+                               void *const *dst_keys, void *const *dst_payload, const int64_t *dst_base,
+                               b200_stream_t stream);
+
 /* ---- select: findall(::CuArray{Bool}) (indexing.jl:26-66) --------------- */
 /* Writes the 1-based linear indices (dtype_index I32/I64) of the non-zero flags
  * to `indices` in order and the number found to *count_dev (device int64).

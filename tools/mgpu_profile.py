@@ -19,6 +19,11 @@ def T():
 
 for rep in range(3):
     dist.barrier(); t0 = T()
+    srt, _ = mg.dist_sort(K); t1 = T()
+    if rank == 0 and rep == 2:
+        print(f"dist_sort (default path, fused={mg.FUSED_EXCHANGE}) n/rank 2^{int(np.log2(big))} x {world}: {1e3*(t1-t0):.2f} ms  {big*world/(t1-t0)/1e9:.1f} Gkeys/s", flush=True)
+for rep in range(3):
+    dist.barrier(); t0 = T()
     spl = mg._splitters(K, False, None, ops); t1 = T()
     parted, _, counts = ops.partition(K, None, spl, world, False); t2 = T()
     bounds = np.concatenate([[0], np.cumsum(counts.to_host().astype(np.int64))]); t3 = T()
