@@ -276,3 +276,32 @@ def test_partition_by_splitters(b, dtype, nb, rev):
         k2, p2, c2 = ops.partition(b.CuArray(a), None, b.CuArray(spl), nb, rev)
         assert p2 is None
         np.testing.assert_array_equal(bits(b.Array(k2)), bits(a[order]))
+
+
+@pytest.mark.parametrize("dtype", ["uint32", "float32", "int64", "uint8"])
+@pytest.mark.parametrize("nb", [2, 8, 16])
+def test_partition_two_phase_scatter(b, dtype, nb):
+    """b200_partition_count + b200_partition_scatter: every bucket goes to its own destination buffer at a
+    caller-chosen element offset (the multi-GPU sort points these at peer receive buffers)."""
+    ops = b.multigpu.DeviceOps()
+    for n in (1, 4097, 250_007):
+        a = rand(dtype, n)
+        spl = oracle.sort(rand(dtype, nb - 1))
+        pay = np.arange(n, dtype=np.int64)
+        ka, sa = b.CuArray(a), b.CuArray(spl)
+        counts, ws = ops.partition_count(ka, sa, nb, False)
+        ke, se = oracle.total_order_key(a), oracle.total_order_key(spl)
+        bid = np.searchsorted(se, ke, side="right")
+        want = np.bincount(bid, minlength=nb).astype(np.int64)
+        np.testing.assert_array_equal(b.Array(counts), want)
+        base = [3 * i + 1 for i in range(nb)]
+        dk = [b.CuArray(np.zeros(int(want[i]) + base[i] + 2, dtype=a.dtype)) for i in range(nb)]
+        dp = [b.CuArray(np.full(int(want[i]) + base[i] + 2, -1, dtype=np.int64)) for i in range(nb)]
+        ops.partition_scatter(ws, ka, b.CuArray(pay), sa, nb, False, counts,
+                              [d.pointer for d in dk], [d.pointer for d in dp], base)
+        for i in range(nb):
+            sel = np.nonzero(bid == i)[0]
+            gotk, gotp = b.Array(dk[i]), b.Array(dp[i])
+            np.testing.assert_array_equal(bits(gotk[base[i]:base[i] + len(sel)]), bits(a[sel]))
+            np.testing.assert_array_equal(gotp[base[i]:base[i] + len(sel)], pay[sel])
+            assert (gotp[:base[i]] == -1).all() and (gotp[base[i] + len(sel):] == -1).all()   # nothing outside the slot
