@@ -80,7 +80,7 @@ def test_ops_1d(b, dtype, op):
 def test_bitwise(b, dtype, op):
     A = rand(dtype, (70001,))
     if op == "and":
-        A = A | npdt(dtype).type(0x0F0F0F0F)
+        A = A | np.uint64(0x0F0F0F0F).astype(npdt(dtype))
     check(b, "identity", op, A, None)
     check(b, "identity", op, np.asfortranarray(A[:69993].reshape(7, 9999)), 2)
 
@@ -89,6 +89,30 @@ def test_bitwise(b, dtype, op):
 def test_sum_abs2(b, dtype):
     check(b, "abs2", "add_sum", rand(dtype, (50001,)), None)
     check(b, "abs2", "add", rand(dtype, (129, 65)), 1)
+
+
+SMALL_INTS = ["int8", "uint8", "int16", "uint16"]
+
+
+@pytest.mark.parametrize("dtype", SMALL_INTS)
+def test_small_integers(b, dtype):
+    """Int8/UInt8/Int16/UInt16: sum widens to (U)Int64 (Base.add_sum), reduce(+/*), maximum, minimum, &, | keep the
+    element type and wrap; the contiguous sum runs on the IDP.4A / IDP.2A path."""
+    for n in (1, 31, 4097, (1 << 22) + 5):
+        A = rand(dtype, (n,))
+        check(b, "identity", "add_sum", A, None)
+        check(b, "identity", "add_sum", A[3:] if n > 3 else A, None)          # unaligned head
+    A = rand(dtype, (70001,))
+    for op in ("max", "min", "add", "mul", "and", "or", "mul_prod"):
+        check(b, "identity", op, A, None)
+    check(b, "abs2", "add_sum", A, None)
+    M = np.asfortranarray(A[:69993].reshape(7, 9999))
+    for dims in (1, 2):
+        for op in ("add_sum", "max", "add"):
+            check(b, "identity", op, M, dims)
+    M = np.asfortranarray(rand(dtype, (4099, 33)))
+    for dims in (1, 2, (1, 2)):
+        check(b, "identity", "add_sum", M, dims)
 
 
 SHAPES_DIMS = [

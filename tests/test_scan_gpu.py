@@ -119,7 +119,8 @@ def test_bad_kwarg_error_text(b):
         b.scan_(b.add, b.CuArray(np.zeros(5)), b.CuArray(np.zeros(4)), 1)
 
 
-@pytest.mark.parametrize("dtype", ["float16", "bfloat16", "float32", "float64", "int32", "int64", "uint32", "uint64"])
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16", "float32", "float64", "int32", "int64", "uint32", "uint64",
+                                   "int8", "uint8", "int16", "uint16"])
 @pytest.mark.parametrize("n", [4095, 4096, 4097, 100_003, (1 << 21) + 5])
 def test_cumsum_types(b, dtype, n):
     A = rand(dtype, (n,))
@@ -139,7 +140,7 @@ def test_cumsum_types(b, dtype, n):
 
 
 @pytest.mark.parametrize("op", ["max", "min", "mul", "and", "or"])
-@pytest.mark.parametrize("dtype", ["float32", "int32", "uint64", "float64"])
+@pytest.mark.parametrize("dtype", ["float32", "int32", "uint64", "float64", "int8", "uint16"])
 def test_other_ops(b, op, dtype):
     if op in ("and", "or") and dtype.startswith("float"):
         pytest.skip("bitwise on floats")
@@ -147,7 +148,7 @@ def test_other_ops(b, op, dtype):
     if op == "mul" and oracle.is_float(npdt(dtype)):
         A = (1 + (A - 0.5) * 1e-3).astype(npdt(dtype))[:5000]
     if op == "and":
-        A = A | npdt(dtype).type(0x00FF00FF)
+        A = A | np.uint64(0x00FF00FF).astype(npdt(dtype))
     check_scan(b, op, A)
     check_scan(b, op, np.asfortranarray(A[:69993 if A.size > 69993 else 4998].reshape(3, -1)), dims=2)
 
