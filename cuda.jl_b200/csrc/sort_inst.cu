@@ -1,6 +1,7 @@
 // sort_inst.cu — one translation unit per key width (-DB200_KEY_BYTES=1|2|4|8).
 // Host orchestration of the onesweep passes for keys / sortperm / pairs.
 #include "sort_pipe.cuh"
+#include "sort_ctr.cuh"
 #include "sort_block.cuh"
 #include "sort_host.h"
 #include <cstdlib>
@@ -56,7 +57,42 @@ template <class V, class LookT> static int32_t launch_pipe(const OnesweepParams 
     return B200_OK;
 }
 
+// Counter-ranked pass (sort_ctr.cuh) for keys-only sorts of 32-bit keys: 0 = off, 1 = 128 threads x 64 keys,
+// 2 = 64 threads x 128 keys.
+static int ctr_mode() {
+#if B200_KEY_BYTES == 4
+    static const int mode = [] { const char *e = getenv("B200_SORT_CTR"); return e ? atoi(e) : 0; }();
+    return mode;
+#else
+    return 0;
+#endif
+}
+constexpr int CTR_TILE = 8192;
+
+#if B200_KEY_BYTES == 4
+template <class LookT, int NT, int ITEMS> static int32_t launch_ctr(const OnesweepParams &p, int64_t tiles, cudaStream_t st) {
+    auto kern = radix_onesweep_ctr_kernel<LookT, NT, ITEMS>;
+    constexpr size_t smem = ctr_smem_bytes<NT, ITEMS>();
+    static thread_local bool attr_set[64];
+    int dev = 0;
+    B200_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[dev] = true;
+    }
+    kern<<<(unsigned int)tiles, NT, smem, st>>>(p);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+#endif
+
 template <class V, class LookT> static int32_t launch_pass(const OnesweepParams &p, int64_t tiles, cudaStream_t st) {
+#if B200_KEY_BYTES == 4
+    if constexpr (!PayTraits<V>::HAS) {
+        if (ctr_mode() == 1) return launch_ctr<LookT, 128, 64>(p, tiles, st);
+        if (ctr_mode() == 2) return launch_ctr<LookT, 64, 128>(p, tiles, st);
+    }
+#endif
     static const bool use_pipe = getenv("B200_SORT_PIPE") != nullptr;   // persistent variant: measured slower (fewer warps per SM)
     if (use_pipe && tiles >= 2 && (reinterpret_cast<uintptr_t>(p.keys_in) % 16) == 0 && pipe_smem<V>() <= 200 * 1024)
         return launch_pipe<V, LookT>(p, tiles, st);
@@ -85,8 +121,12 @@ template <class LookT> static int32_t dispatch_pass(const OnesweepParams &p, int
 
 int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
     const int64_t n = c.n;
-    const int64_t tiles = cdiv(n, c.mode == SORT_KEYS ? tile_for<NoPayload>() : tile_for<uint32_t>());
-    const bool wide = n >= (1LL << 30);                    // 30-bit counts no longer hold every prefix
+    const int64_t max_tiles = cdiv(n, c.mode == SORT_KEYS ? tile_for<NoPayload>() : tile_for<uint32_t>());
+    const int64_t tiles = (c.mode == SORT_KEYS && ctr_mode() && !c.query) ? cdiv(n, CTR_TILE) : max_tiles;
+    // 32-bit status words carry 30-bit counts.  Every prefix that is ever READ belongs to a tile before the last
+    // one and is therefore < n, so n == 2^30 still fits (only the last tile's own inclusive value can reach 2^30,
+    // and nobody looks back at the last tile).
+    const bool wide = n > (1LL << 30);
     const size_t look_bytes = wide ? 8 : 4;
     // payload width carried through the passes
     int pay = 0;
@@ -97,7 +137,7 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
     unsigned long long *ghist = w.take<unsigned long long>(P * RX_RADIX);
     unsigned long long *bins = w.take<unsigned long long>(P * RX_RADIX);
     unsigned long long *ticket = w.take<unsigned long long>(1);
-    char *status = w.take<char>((size_t)tiles * RX_RADIX * look_bytes);
+    char *status = w.take<char>((size_t)max_tiles * RX_RADIX * look_bytes);
     char *kbuf0 = w.take<char>((size_t)n * sizeof(K));
     char *kbuf1 = c.mode == SORT_PERM ? w.take<char>((size_t)n * sizeof(K)) : nullptr;
     char *vbuf0 = pay ? w.take<char>((size_t)n * pay) : nullptr;
