@@ -351,14 +351,28 @@ __global__ void __launch_bounds__(RS_THREADS) reduce_strided_kernel(ReduceParams
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (active && y == 0) {
-        acc_t f[VN];
+    // last CTA of the column tile: fold the S partials, every (x, y) thread taking the slices y, y+TY, ...
+    // (a fixed assignment, so the result is deterministic), then the TY rows through shared memory
+    acc_t f[VN];
 #pragma unroll
-        for (int k = 0; k < VN; ++k) f[k] = Op::identity();
-        for (int ss = 0; ss < S; ++ss)
+    for (int k = 0; k < VN; ++k) f[k] = Op::identity();
+    if (active) {
+        for (int ss = y; ss < S; ss += TY)
 #pragma unroll
             for (int k = 0; k < VN; ++k)
                 f[k] = Op::apply(f[k], ld_cg_any(partials + (int64_t)ss * BX * VN + x * VN + k));
+    }
+    if (TY > 1) {
+#pragma unroll
+        for (int k = 0; k < VN; ++k) s_acc[(y * BX + x) * VN + k] = f[k];
+        __syncthreads();
+        if (y == 0) {
+            for (int yy = 1; yy < TY; ++yy)
+#pragma unroll
+                for (int k = 0; k < VN; ++k) f[k] = Op::apply(f[k], s_acc[(yy * BX + x) * VN + k]);
+        }
+    }
+    if (active && y == 0) {
 #pragma unroll
         for (int k = 0; k < VN; ++k) store_result<Tout, Op>(out, o0 + k, f[k], p.init_mode);
     }
@@ -424,7 +438,10 @@ static inline ReducePlan plan_reduce(int64_t pre, int64_t red, int64_t post, int
         const int64_t groups = outputs / vn;
         // measured on B200 (16384^2, sum over dims=2): ~4.3 CTAs per SM of 256 threads is the sweet spot
         // (F32: BX=64,TY=4,S=10 -> 6.1 TB/s vs 5.6 TB/s at 8 CTAs/SM; BF16: BX=32,TY=8,S=10 -> 5.6 vs 4.9 TB/s)
-        const int bx = groups >= 4096 ? 64 : 32;
+        int bx = groups >= 4096 ? 64 : 32;
+        // few columns (sum(A; dims=2) on 3 x 1_000_000): lanes along the columns would idle, so shrink the
+        // column tile and give the freed lanes to the rows (a warp then reads 32/bx consecutive rows)
+        while (bx > 1 && bx / 2 >= groups) bx >>= 1;
         const int64_t min_rows = 16;                // rows per (s, y) worker, at least
         int ty = RS_THREADS / bx;
         while (ty > 1 && red / ty < min_rows) ty >>= 1;

@@ -1032,6 +1032,129 @@ __global__ void __launch_bounds__(256) scan_strided_lb_kernel(ScanParams p, int6
     }
 }
 
+// Strided scan for FEW long columns (pre * post <= 128, e.g. accumulate(A; dims=2) on a 3 x 1_000_000
+// matrix, the reference's own "L" benchmark shape, perf/array.jl:8-9,72-90).  The 256-column tiling above
+// would keep 3 lanes of 256 busy, so a CTA here owns `rtc` consecutive row tiles of ALL columns: thread
+// (rtl, c) scans SS_ROWS rows of column c in registers, the per-thread aggregates are combined across the
+// CTA's row tiles in shared memory, and one thread per column runs the look-back over the preceding CTAs
+// (one status slot per (CTA, column)).
+template <class Tin, class Tout, class Op>
+__global__ void __launch_bounds__(256) scan_fewcols_kernel(ScanParams p, int cols, int rtc, int64_t nctas) {
+    using A = typename Op::acc_t;
+    constexpr int NW = StatusWords<A>::NW;
+    extern __shared__ __align__(16) unsigned char s_fc_raw[];
+    A *s_agg = reinterpret_cast<A *>(s_fc_raw);     // [rtc][cols]
+    A *s_tot = s_agg + rtc * cols;                  // [cols] column totals of this CTA
+    A *s_pref = s_tot + cols;                       // [cols] exclusive prefix of this CTA
+    __shared__ unsigned long long s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(p.ticket, 1ull);
+    __syncthreads();
+    const int64_t g = (int64_t)s_ticket;
+    const int c = threadIdx.x % cols, rtl = threadIdx.x / cols;
+    const bool active = rtl < rtc;
+    const int64_t j = c / p.pre, i = c - j * p.pre;
+    const int64_t r0 = (g * rtc + rtl) * SS_ROWS;
+    int rows = 0;
+    if (active && r0 < p.n) rows = (int)((p.n - r0) < SS_ROWS ? (p.n - r0) : SS_ROWS);
+    const Tin *in = static_cast<const Tin *>(p.in) + i + p.pre * (r0 + p.n * j);
+    Tout *out = static_cast<Tout *>(p.out) + i + p.pre * (r0 + p.n * j);
+    A v[SS_ROWS];
+#pragma unroll
+    for (int r = 0; r < SS_ROWS; ++r) v[r] = r < rows ? cvt<A>(ld_coh(in + p.pre * r)) : Op::identity();
+#pragma unroll
+    for (int r = 1; r < SS_ROWS; ++r) v[r] = Op::apply(v[r - 1], v[r]);
+    const A agg = v[SS_ROWS - 1];
+    if (active) s_agg[rtl * cols + c] = agg;
+    __syncthreads();
+    A local = Op::identity();                       // this column's aggregate over the CTA's earlier row tiles
+    if (active)
+        for (int k = 0; k < rtl; ++k) local = Op::apply(local, s_agg[k * cols + c]);
+    if (active && rtl == rtc - 1) s_tot[c] = Op::apply(local, agg);
+    __syncthreads();
+    if (threadIdx.x < cols) {                       // rtl == 0: one look-back chain per column
+        const A total = s_tot[c];
+        uint64_t *slots = p.status + (int64_t)c * NW;
+        const int64_t gstride = (int64_t)cols * NW;
+        A prefix;
+        if (g == 0) {
+            prefix = p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity();
+            if (nctas > 1) publish<A>(slots, SC_INCLUSIVE, Op::apply(prefix, total));
+        } else {
+            publish<A>(slots + g * gstride, SC_PARTIAL, total);
+            prefix = Op::identity();
+            int64_t u = g - 1;
+            while (true) {
+                A val;
+                uint32_t flag;
+                do { flag = peek_slot<A>(slots + u * gstride, val); } while (flag == SC_INVALID);
+                prefix = Op::apply(val, prefix);
+                if (flag == SC_INCLUSIVE) break;
+                --u;
+            }
+            publish<A>(slots + g * gstride, SC_INCLUSIVE, Op::apply(prefix, total));
+        }
+        s_pref[c] = prefix;
+    }
+    __syncthreads();
+    if (rows == 0) return;
+    const A prefix = Op::apply(s_pref[c], local);
+    if (!p.exclusive) {
+#pragma unroll
+        for (int r = 0; r < SS_ROWS; ++r)
+            if (r < rows) out[p.pre * r] = cvt<Tout>(Op::apply(prefix, v[r]));
+    } else {
+        out[0] = cvt<Tout>(prefix);
+#pragma unroll
+        for (int r = 1; r < SS_ROWS; ++r)
+            if (r < rows) out[p.pre * r] = cvt<Tout>(Op::apply(prefix, v[r - 1]));
+    }
+}
+
+// One warp per contiguous segment, for many short-to-medium segments (accumulate(A; dims=1) on a
+// 512 x 1000 matrix, perf/array.jl:76): no tickets, no look-back; the warp walks its segment in chunks of
+// 32 * EPC elements with a running carry, the next chunk's loads issued before the current chunk's shuffles.
+template <class Tin, class Tout, class Op, int EPC>
+__global__ void __launch_bounds__(256) scan_warpseg_kernel(ScanParams p) {
+    using A = typename Op::acc_t;
+    const int lane = threadIdx.x & 31;
+    const int64_t seg = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (seg >= p.post) return;
+    const Tin *tin = static_cast<const Tin *>(p.in) + seg * p.n;
+    Tout *tout = static_cast<Tout *>(p.out) + seg * p.n;
+    constexpr int STEP = 32 * EPC;
+    A carry = p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity();
+    A nxt[EPC];
+    load_chunk<Tin, A, Op, EPC>(tin, (int64_t)lane * EPC, p.n, nxt);
+    for (int64_t base = 0; base < p.n; base += STEP) {
+        A v[EPC];
+#pragma unroll
+        for (int e = 0; e < EPC; ++e) v[e] = nxt[e];
+        if (base + STEP < p.n) load_chunk<Tin, A, Op, EPC>(tin, base + STEP + (int64_t)lane * EPC, p.n, nxt);
+#pragma unroll
+        for (int e = 1; e < EPC; ++e) v[e] = Op::apply(v[e - 1], v[e]);
+        A csum = v[EPC - 1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            A up = shfl_up_any(csum, d);
+            if (lane >= d) csum = Op::apply(up, csum);
+        }
+        const A excl = shfl_up_any(csum, 1);
+        const A tot = shfl_idx_any(csum, 31);
+        const A pre = lane == 0 ? carry : Op::apply(carry, excl);
+        A o[EPC];
+        if (!p.exclusive) {
+#pragma unroll
+            for (int e = 0; e < EPC; ++e) o[e] = Op::apply(pre, v[e]);
+        } else {
+            o[0] = pre;
+#pragma unroll
+            for (int e = 1; e < EPC; ++e) o[e] = Op::apply(pre, v[e - 1]);
+        }
+        store_chunk<Tout, A, EPC>(tout, base + (int64_t)lane * EPC, p.n, o);
+        carry = Op::apply(carry, tot);
+    }
+}
+
 // ------------------------------------------------------------------ host
 template <class Tin, class Tout> struct ScanShape {
     static constexpr int WIDE = sizeof(Tin) > sizeof(Tout) ? sizeof(Tin) : sizeof(Tout);
@@ -1057,6 +1180,34 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
         memcpy(&iv, init_host, sizeof(Tout));
         A a = cvt<A>(iv);
         memcpy(&p.init_bits, &a, sizeof(A));
+    }
+    if (pre == 1 && n <= 128 && post >= 32LL * devinfo().sm_count) {
+        // very many very short contiguous segments (accumulate(A; dims=1) on 3 x 1_000_000): a tile per
+        // segment would launch a look-back chain for 3 elements; one thread per segment instead
+        if (query_bytes) { *query_bytes = 0; return B200_OK; }
+        const int64_t grid = cdiv(post, 256);
+        if (grid > 2147483647LL) return B200_INVALID_VALUE;
+        scan_strided_kernel<Tin, Tout, Op><<<(unsigned int)grid, 256, 0, stream>>>(p);
+        B200_CHECK_LAUNCH();
+        return B200_OK;
+    }
+    if (pre > 1 && pre * post <= 128 && n >= 4 * SS_ROWS) {
+        const int cols = (int)(pre * post);
+        const int rtc = 256 / cols;                                    // row tiles per CTA
+        const int64_t nctas = cdiv(n, (int64_t)rtc * SS_ROWS);
+        Carver c(ws);
+        unsigned long long *ticket = c.take<unsigned long long>(1);
+        uint64_t *status = c.take<uint64_t>((size_t)(nctas * cols * NW));
+        if (query_bytes) { *query_bytes = c.bytes(); return B200_OK; }
+        if (c.bytes() > ws_bytes) return B200_WORKSPACE_TOO_SMALL;
+        if (ws == nullptr) return B200_INVALID_VALUE;
+        if (nctas > 2147483647LL) return B200_INVALID_VALUE;
+        p.status = status; p.ticket = ticket;
+        B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, c.bytes(), stream));
+        const size_t smem = (size_t)(rtc * cols + 2 * cols) * sizeof(A);
+        scan_fewcols_kernel<Tin, Tout, Op><<<(unsigned int)nctas, 256, smem, stream>>>(p, cols, rtc, nctas);
+        B200_CHECK_LAUNCH();
+        return B200_OK;
     }
     if (pre > 1) {
         const int64_t cols = pre * post;
@@ -1099,6 +1250,15 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
     if (query) { *query_bytes = c.bytes(); return B200_OK; }
     if (c.bytes() > ws_bytes) return B200_WORKSPACE_TOO_SMALL;
     if (ws == nullptr) return B200_INVALID_VALUE;
+    if (post >= 4LL * devinfo().sm_count && n <= 8192) {
+        // enough segments to give every SM several warps, each short enough for one warp: no tile machinery
+        const int64_t wgrid = cdiv(post, 8);
+        if (wgrid > 2147483647LL) return B200_INVALID_VALUE;
+        if (vec) scan_warpseg_kernel<Tin, Tout, Op, S::EPC><<<(unsigned int)wgrid, 256, 0, stream>>>(p);
+        else scan_warpseg_kernel<Tin, Tout, Op, 1><<<(unsigned int)wgrid, 256, 0, stream>>>(p);
+        B200_CHECK_LAUNCH();
+        return B200_OK;
+    }
     const int64_t tile = vec ? S::TILE_VEC : S::TILE_SCALAR;
     p.tiles_per_seg = cdiv(n, tile);
     p.status = status; p.ticket = ticket;

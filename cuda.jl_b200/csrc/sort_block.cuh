@@ -26,10 +26,11 @@ struct BlockSortParams {
     int32_t linear;      // sortperm: 1-based linear index into the whole array instead of the segment
 };
 
-template <class K, bool PERM>
+// ITEMS keys per thread: 16 (segments up to 4096) or 4 (up to 1024: a quarter of the ranking work, e.g. the
+// reference's own sort(A; dims=1) benchmark on 512 x 1000, perf/array.jl:151)
+template <class K, bool PERM, int ITEMS>
 __global__ void __launch_bounds__(RX_THREADS) radix_block_sort_kernel(BlockSortParams p) {
-    constexpr int ITEMS = RB_ITEMS;
-    constexpr int TILE = RB_TILE;
+    constexpr int TILE = RX_THREADS * ITEMS;
     constexpr int WARP_ITEMS = 32 * ITEMS;
     constexpr int P = (int)sizeof(K);
     extern __shared__ __align__(16) unsigned char s_raw[];

@@ -215,30 +215,28 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
 }
 
 
+template <bool PERM, int ITEMS> static int32_t launch_block_sort(const BlockSortParams &bp, int64_t nseg, cudaStream_t st) {
+    constexpr int TILE = RX_THREADS * ITEMS;
+    const size_t smem = (size_t)RX_WARPS * RX_RADIX * 4 + (size_t)TILE * sizeof(K) + (PERM ? (size_t)TILE * 2 : 0);
+    auto kern = radix_block_sort_kernel<K, PERM, ITEMS>;
+    static thread_local bool attr_set[64];
+    int dev = 0;
+    B200_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[dev] = true;
+    }
+    kern<<<(unsigned int)nseg, RX_THREADS, smem, st>>>(bp);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
 int32_t B200_CAT(block_sort_k, B200_KEY_BYTES)(const BlockSortParams &bp, int perm, int64_t nseg, cudaStream_t st) {
     if (nseg == 0) return B200_OK;
     if (nseg > 2147483647LL) return B200_INVALID_VALUE;
-    const size_t smem = (size_t)RX_WARPS * RX_RADIX * 4 + (size_t)RB_TILE * sizeof(K) + (perm ? (size_t)RB_TILE * 2 : 0);
-    static thread_local bool attr_set[64][2];
-    int dev = 0;
-    B200_CUDA_TRY(cudaGetDevice(&dev));
-    if (perm) {
-        auto kern = radix_block_sort_kernel<K, true>;
-        if (dev >= 0 && dev < 64 && !attr_set[dev][1]) {
-            B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set[dev][1] = true;
-        }
-        kern<<<(unsigned int)nseg, RX_THREADS, smem, st>>>(bp);
-    } else {
-        auto kern = radix_block_sort_kernel<K, false>;
-        if (dev >= 0 && dev < 64 && !attr_set[dev][0]) {
-            B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set[dev][0] = true;
-        }
-        kern<<<(unsigned int)nseg, RX_THREADS, smem, st>>>(bp);
-    }
-    B200_CHECK_LAUNCH();
-    return B200_OK;
+    const bool small = bp.n <= RX_THREADS * 4;
+    if (perm) return small ? launch_block_sort<true, 4>(bp, nseg, st) : launch_block_sort<true, RB_ITEMS>(bp, nseg, st);
+    return small ? launch_block_sort<false, 4>(bp, nseg, st) : launch_block_sort<false, RB_ITEMS>(bp, nseg, st);
 }
 
 int32_t B200_CAT(lower_bound_k, B200_KEY_BYTES)(const void *sorted, int64_t n, const void *needles, int64_t m,

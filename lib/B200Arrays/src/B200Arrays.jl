@@ -7,6 +7,7 @@
 #   mapreduce.jl      GPUArrays.mapreducedim! methods   (replaces CUDACore/src/mapreduce.jl:168)
 #   accumulate.jl     CUDACore.scan! methods            (replaces CUDACore/src/accumulate.jl:135)
 #   sorting.jl        Base.sort!/sortperm!/partialsort! (replaces CUDACore/src/sorting.jl:1003-1070)
+#   indexing.jl       Base.findall(::CuArray{Bool})     (replaces CUDACore/src/indexing.jl:26-66)
 #
 # NOTE: no Julia toolchain exists in the build image, so this package has never been
 # executed there; the Python mirror in cuda.jl_b200/ drives the same C ABI in the tests.
@@ -31,6 +32,7 @@ include("libb200arrays.jl")
 include("mapreduce.jl")
 include("accumulate.jl")
 include("sorting.jl")
+include("indexing.jl")
 
 function __init__()
     CUDACore.functional() || return

@@ -5,8 +5,9 @@
 function CUDACore.scan!(f::OP, output::CuArray{To}, input::CuArray{Ti};
                         dims::Integer, init=nothing, neutral=GPUArrays.neutral_element(f, To)) where
                         {OP<:GraftOps,To<:ReduceTypes,Ti<:ReduceTypes}
-    enabled() || return invoke(CUDACore.scan!, Tuple{Function,CUDACore.AnyCuArray,CUDACore.AnyCuArray},
-                               f, output, input; dims, init, neutral)
+    reference() = invoke(CUDACore.scan!, Tuple{Function,CUDACore.AnyCuArray,CUDACore.AnyCuArray},
+                         f, output, input; dims, init, neutral)
+    enabled() || return reference()
     dims > 0 || throw(ArgumentError("dims must be a positive integer"))          # accumulate.jl:137
     axes(output) == axes(input) || throw(DimensionMismatch("shape of B must match A"))
     dims > ndims(input) && return copyto!(output, input)
@@ -15,6 +16,7 @@ function CUDACore.scan!(f::OP, output::CuArray{To}, input::CuArray{Ti};
     pre, n, post = prod(sz[1:dims-1]), sz[dims], prod(sz[dims+1:end])
     din, dout, opc = dtype_code(Ti), dtype_code(To), op_code(f)
     bytes = b200_scan_workspace_bytes(din, dout, opc, pre, n, post)
+    bytes === nothing && return reference()                     # (Ti, To, op) not compiled into the library
     initref = init === nothing ? nothing : Ref{To}(convert(To, something(init)))
     GC.@preserve initref with_ws(bytes) do ws, nb
         ptr = initref === nothing ? C_NULL : Base.unsafe_convert(Ptr{Cvoid}, Base.cconvert(Ptr{To}, initref))

@@ -9,6 +9,7 @@ struct B200ArraysError <: Exception
 end
 
 const B200_OK = Int32(0)
+const B200_UNSUPPORTED = Int32(2)
 const B200_LAUNCH_FAILURE = Int32(4)
 
 function description(err::B200ArraysError)

@@ -19,8 +19,8 @@ dtype_code(::Type{UInt8}) = Int32(10)
 dtype_code(::Type{Int16}) = Int32(11)
 dtype_code(::Type{UInt16}) = Int32(12)
 
-const ReduceTypes = Union{Float16,BFloat16,Float32,Float64,Int32,Int64,UInt32,UInt64,Bool}
-const SortTypes = Union{ReduceTypes,Int8,UInt8,Int16,UInt16}
+const ReduceTypes = Union{Float16,BFloat16,Float32,Float64,Int32,Int64,UInt32,UInt64,Bool,Int8,UInt8,Int16,UInt16}
+const SortTypes = ReduceTypes
 
 # b200_op_t / b200_map_t
 const OP_ADD, OP_MUL, OP_MAX, OP_MIN, OP_AND, OP_OR, OP_EXTREMA = Int32.(0:6)
@@ -28,11 +28,18 @@ const MAP_IDENTITY, MAP_ABS2 = Int32(0), Int32(1)
 const INIT_NEUTRAL, INIT_FROM_OUT = Int32(0), Int32(1)
 const SORTPERM_INDEX = Int32(100)
 
+# The *_workspace_bytes queries double as the "is this (eltype, op) combination compiled in?" probe:
+# B200_UNSUPPORTED -> `nothing`, and the caller `invoke`s the reference method instead of throwing.
+@inline function query_bytes(res::Int32, bytes)
+    res == B200_UNSUPPORTED && return nothing
+    check(res)
+    return Int(bytes[])
+end
+
 function b200_reduce_workspace_bytes(din, dout, op, map, pre, red, post)
     bytes = Ref{Csize_t}(0)
-    check(@ccall libb200arrays[].b200_reduce_workspace_bytes(din::Int32, dout::Int32, op::Int32, map::Int32,
-              pre::Int64, red::Int64, post::Int64, bytes::Ref{Csize_t})::Int32)
-    return Int(bytes[])
+    query_bytes((@ccall libb200arrays[].b200_reduce_workspace_bytes(din::Int32, dout::Int32, op::Int32, map::Int32,
+                     pre::Int64, red::Int64, post::Int64, bytes::Ref{Csize_t})::Int32), bytes)
 end
 
 function b200_reduce(ws, ws_bytes, A, R, din, dout, op, map, pre, red, post, init_mode, s::CuStream)
@@ -44,9 +51,8 @@ end
 
 function b200_scan_workspace_bytes(din, dout, op, pre, n, post)
     bytes = Ref{Csize_t}(0)
-    check(@ccall libb200arrays[].b200_scan_workspace_bytes(din::Int32, dout::Int32, op::Int32,
-              pre::Int64, n::Int64, post::Int64, bytes::Ref{Csize_t})::Int32)
-    return Int(bytes[])
+    query_bytes((@ccall libb200arrays[].b200_scan_workspace_bytes(din::Int32, dout::Int32, op::Int32,
+                     pre::Int64, n::Int64, post::Int64, bytes::Ref{Csize_t})::Int32), bytes)
 end
 
 function b200_scan(ws, ws_bytes, A, B, din, dout, op, exclusive, pre, n, post, init::Ptr{Cvoid}, s::CuStream)

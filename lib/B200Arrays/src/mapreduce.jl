@@ -45,6 +45,7 @@ function GPUArrays.mapreducedim!(f::F, op::OP, R::CuArray{To}, A::CuArray{Ti};
     pre, red, post = dims
     din, dout, opc, mapc = dtype_code(Ti), dtype_code(To), op_code(op), map_code(f)
     bytes = b200_reduce_workspace_bytes(din, dout, opc, mapc, pre, red, post)
+    bytes === nothing && return reference_mapreducedim!(f, op, R, A; init)   # (Ti, To, op) not compiled into the library
     with_ws(bytes) do ws, n
         b200_reduce(ws, n, A, R, din, dout, opc, mapc, pre, red, post,
                     init === nothing ? INIT_FROM_OUT : INIT_NEUTRAL, stream())

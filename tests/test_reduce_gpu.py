@@ -121,6 +121,8 @@ SHAPES_DIMS = [
     ((32, 32, 32), 1), ((32, 32, 32), 2), ((32, 32, 32), 3), ((32, 32, 32), (1, 2)), ((32, 32, 32), (2, 3)),
     ((85, 132, 10), 1), ((1, 70, 50, 20), 3), ((5, 1, 7), 2), ((2, 3, 100000), 2), ((100000, 2), 2),
     ((7, 200000), 1), ((3, 5, 7, 11), (2, 3)),
+    # perf/array.jl:8-9 "L" shapes and neighbours: few long columns (narrow column tiles, parallel final fold)
+    ((3, 1_000_000), 1), ((3, 1_000_000), 2), ((2, 300_001), 2), ((5, 100_000), 2), ((33, 40_000), 2), ((2, 50_000, 3), 2),
 ]
 
 

@@ -170,6 +170,22 @@ def test_dims(b, shape, dims, dtype):
     check_scan(b, "add", rand(dtype, shape), dims=dims)
 
 
+@pytest.mark.parametrize("shape,dims", [((3, 1_000_000), 1), ((3, 1_000_000), 2), ((2, 70_001), 2), ((5, 40_000), 2),
+                                        ((100, 3_001), 2), ((128, 1_000), 2), ((2, 30_000, 3), 2), ((1, 9_999, 7), 2),
+                                        ((17, 300_000), 1), ((128, 5_000), 1), ((129, 5_000), 1)])
+@pytest.mark.parametrize("dtype", ["int64", "float32", "uint8"])
+def test_reference_benchmark_shapes(b, shape, dims, dtype):
+    """perf/array.jl:8-9,72-90 "L" shapes (3 x 1_000_000) and neighbours: very many very short segments
+    (thread per segment) and few long columns (scan_fewcols_kernel), inclusive / exclusive / init."""
+    A = rand(dtype, shape)
+    if dtype == "float32":
+        A = (A * 0.01).astype(np.float32)
+    check_scan(b, "add", A, dims=dims)
+    check_scan(b, "max", A, dims=dims)
+    if shape[0] <= 5:
+        check_scan(b, "add", A, dims=dims, exclusive=True, init=npdt(dtype).type(3))
+
+
 @pytest.mark.parametrize("dtype", ["int64", "float32", "int32", "float64"])
 @pytest.mark.parametrize("n", [1, 5, 4096, 8193, 300_001])
 def test_exclusive(b, dtype, n):
