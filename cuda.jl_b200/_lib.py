@@ -40,6 +40,8 @@ SIGNATURES = {
     "b200_partition": (_i32, [_vp, _sz, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _vp]),
     "b200_partition_count": (_i32, [_vp, _sz, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _vp]),
     "b200_partition_scatter": (_i32, [_vp, _sz, _vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "b200_select_kth_workspace_bytes": (_i32, [_i32, _i64, _c.POINTER(_sz)]),
+    "b200_select_kth": (_i32, [_vp, _sz, _vp, _i32, _i64, _i64, _i32, _vp, _vp]),
     "b200_select_workspace_bytes": (_i32, [_i64, _c.POINTER(_sz)]),
     "b200_select_flagged": (_i32, [_vp, _sz, _vp, _vp, _i32, _vp, _i64, _vp]),
 }

@@ -255,4 +255,32 @@ int32_t b200_search_sorted(const void *sorted_keys, int64_t n, const void *needl
     }
 }
 
+static int32_t select_kth_dispatch(void *ws, size_t wsb, const void *keys, int32_t dtype_key, int64_t n, int64_t k,
+                                   int32_t descending, void *out, b200_stream_t stream, size_t *query) {
+    using namespace b200;
+    SortXform xf; int kb;
+    if (!make_xform(dtype_key, descending, 0, xf, kb)) return B200_UNSUPPORTED;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (kb) {
+        case 1: return select_kth_k1(ws, wsb, keys, n, k, xf, out, st, query);
+        case 2: return select_kth_k2(ws, wsb, keys, n, k, xf, out, st, query);
+        case 4: return select_kth_k4(ws, wsb, keys, n, k, xf, out, st, query);
+        case 8: return select_kth_k8(ws, wsb, keys, n, k, xf, out, st, query);
+        default: return B200_UNSUPPORTED;
+    }
+}
+
+int32_t b200_select_kth_workspace_bytes(int32_t dtype_key, int64_t n, size_t *bytes) {
+    if (!bytes || n < 0) return B200_INVALID_VALUE;
+    *bytes = 0;
+    return select_kth_dispatch(nullptr, 0, nullptr, dtype_key, n, 0, 0, nullptr, nullptr, bytes);
+}
+
+int32_t b200_select_kth(void *workspace, size_t workspace_bytes, const void *keys, int32_t dtype_key, int64_t n,
+                        int64_t k, int32_t descending, void *out_value, b200_stream_t stream) {
+    if (b200::dtype_size(dtype_key) == 0) return B200_UNSUPPORTED;
+    if (n <= 0 || k < 0 || k >= n || !keys || !out_value) return B200_INVALID_VALUE;
+    return select_kth_dispatch(workspace, workspace_bytes, keys, dtype_key, n, k, descending, out_value, stream, nullptr);
+}
+
 }  // extern "C"

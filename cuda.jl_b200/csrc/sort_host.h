@@ -35,5 +35,9 @@ int32_t lower_bound_k1(const void *, int64_t, const void *, int64_t, const SortX
 int32_t lower_bound_k2(const void *, int64_t, const void *, int64_t, const SortXform &, long long *, cudaStream_t);
 int32_t lower_bound_k4(const void *, int64_t, const void *, int64_t, const SortXform &, long long *, cudaStream_t);
 int32_t lower_bound_k8(const void *, int64_t, const void *, int64_t, const SortXform &, long long *, cudaStream_t);
+int32_t select_kth_k1(void *, size_t, const void *, int64_t, int64_t, const SortXform &, void *, cudaStream_t, size_t *);
+int32_t select_kth_k2(void *, size_t, const void *, int64_t, int64_t, const SortXform &, void *, cudaStream_t, size_t *);
+int32_t select_kth_k4(void *, size_t, const void *, int64_t, int64_t, const SortXform &, void *, cudaStream_t, size_t *);
+int32_t select_kth_k8(void *, size_t, const void *, int64_t, int64_t, const SortXform &, void *, cudaStream_t, size_t *);
 
 }  // namespace b200

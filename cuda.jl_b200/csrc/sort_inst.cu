@@ -2,6 +2,7 @@
 // Host orchestration of the onesweep passes for keys / sortperm / pairs.
 #include "sort_pipe.cuh"
 #include "sort_ctr.cuh"
+#include "select_kth.cuh"
 #include "sort_block.cuh"
 #include "sort_host.h"
 #include <cstdlib>
@@ -237,6 +238,33 @@ int32_t B200_CAT(block_sort_k, B200_KEY_BYTES)(const BlockSortParams &bp, int pe
     const bool small = bp.n <= RX_THREADS * 4;
     if (perm) return small ? launch_block_sort<true, 4>(bp, nseg, st) : launch_block_sort<true, RB_ITEMS>(bp, nseg, st);
     return small ? launch_block_sort<false, 4>(bp, nseg, st) : launch_block_sort<false, RB_ITEMS>(bp, nseg, st);
+}
+
+// k-th smallest key of `keys` (0-based k) -> out[0]; workspace = SelectState + one 256-bin histogram per pass.
+int32_t B200_CAT(select_kth_k, B200_KEY_BYTES)(void *ws, size_t wsb, const void *keys, int64_t n, int64_t k,
+                                               const SortXform &xf, void *out, cudaStream_t st, size_t *query) {
+    Carver w(ws);
+    SelectState *state = w.take<SelectState>(1);
+    unsigned int *hist = w.take<unsigned int>(P * RX_RADIX);
+    if (query) { *query = w.bytes(); return B200_OK; }
+    if (w.bytes() > wsb) return B200_WORKSPACE_TOO_SMALL;
+    if (ws == nullptr) return B200_INVALID_VALUE;
+    B200_CUDA_TRY(cudaMemsetAsync(ws, 0, w.bytes(), st));
+    const DevInfo &dev = devinfo();
+    int64_t grid = (int64_t)dev.sm_count * 4;
+    const int64_t need = cdiv(n, 512 * (16 / (int64_t)sizeof(K)));
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    for (int pass = 0; pass < P; ++pass) {
+        const int shift = 8 * (P - 1 - pass);
+        unsigned int *h = hist + pass * RX_RADIX;
+        select_hist_kernel<K><<<(unsigned int)grid, 512, 0, st>>>(static_cast<const K *>(keys), n, xf, shift, state, h);
+        B200_CHECK_LAUNCH();
+        select_pick_kernel<K><<<1, RX_RADIX, 0, st>>>(h, state, shift, pass == 0, (unsigned long long)k, pass == P - 1, xf,
+                                                      static_cast<K *>(out));
+        B200_CHECK_LAUNCH();
+    }
+    return B200_OK;
 }
 
 int32_t B200_CAT(lower_bound_k, B200_KEY_BYTES)(const void *sorted, int64_t n, const void *needles, int64_t m,

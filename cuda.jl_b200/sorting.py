@@ -97,8 +97,26 @@ def partialsort_(c, k, alg=BitonicSort, lt=isless, by=identity, rev=False):
     return _index_k(c, k)
 
 
-def partialsort(c, k, **kw):
-    return partialsort_(c.copy(), k, **kw)
+def partialsort(c, k, alg=BitonicSort, lt=isless, by=identity, rev=False):
+    """Base.partialsort(c, k; kw...) = partialsort!(copy(c), k; kw...).  For a scalar k nothing needs to be
+    sorted or copied: b200_select_kth (MSD radix select, sizeof(T) streaming reads of c) finds the element a
+    stable sort would put at position k.  Ranges go through the full sort like the reference."""
+    if not isinstance(k, (int, np.integer)):
+        return partialsort_(c.copy(), k, alg=alg, lt=lt, by=by, rev=rev)
+    if c.ndims != 1:
+        raise NotGraftedError("partialsort is defined for vectors")
+    _guard(lt, by, alg)
+    if not 1 <= k <= c.length:
+        raise IndexError(f"BoundsError: attempt to access {c.length}-element CuArray at index [{k}]")
+    lib = _lib.load()
+    dev = c.buf.device
+    out = CuArray.undef(c.eltype, (1,), dev)
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(lib.b200_select_kth_workspace_bytes(c.eltype, c.length, ctypes.byref(nbytes)))
+    ws = Workspace(nbytes.value, dev)
+    _lib.check(lib.b200_select_kth(ws.ptr, ws.nbytes, c.pointer, c.eltype, c.length, int(k) - 1, 1 if rev else 0,
+                                   out.pointer, current_stream_handle(dev)))
+    return out.to_host()[0]                                                    # @allowscalar, like the reference
 
 
 def sortperm_(ix, A, initialized=False, alg=BitonicSort, lt=isless, by=identity, rev=False, dims=None):

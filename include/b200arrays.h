@@ -240,6 +240,15 @@ int32_t b200_partition_scatter(void *workspace, size_t workspace_bytes, const vo
                                void *const *dst_keys, void *const *dst_payload, const int64_t *dst_base,
                                b200_stream_t stream);
 
+/* ---- radix select: partialsort(c, k) for a scalar k (sorting.jl:1015-1022) - */
+/* The reference's bitonic partialsort is "full sort, then c[k]".  b200_select_kth writes the
+ * element that a stable sort (isless order, `descending` as in b200_sort_keys) would put at
+ * 0-based position k to out_value[0] (device, element type of the keys) WITHOUT sorting or
+ * modifying `keys`: sizeof(key) streaming reads of the input (MSD radix select). */
+int32_t b200_select_kth_workspace_bytes(int32_t dtype_key, int64_t n, size_t *bytes);
+int32_t b200_select_kth(void *workspace, size_t workspace_bytes, const void *keys, int32_t dtype_key,
+                        int64_t n, int64_t k, int32_t descending, void *out_value, b200_stream_t stream);
+
 /* ---- select: findall(::CuArray{Bool}) (indexing.jl:26-66) --------------- */
 /* Writes the 1-based linear indices (dtype_index I32/I64) of the non-zero flags
  * to `indices` in order and the number found to *count_dev (device int64).

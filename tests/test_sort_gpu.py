@@ -305,3 +305,23 @@ def test_partition_two_phase_scatter(b, dtype, nb):
             np.testing.assert_array_equal(bits(gotk[base[i]:base[i] + len(sel)]), bits(a[sel]))
             np.testing.assert_array_equal(gotp[base[i]:base[i] + len(sel)], pay[sel])
             assert (gotp[:base[i]] == -1).all() and (gotp[base[i] + len(sel):] == -1).all()   # nothing outside the slot
+
+
+@pytest.mark.parametrize("dtype", ["float32", "uint32", "int64", "float64", "float16", "uint8", "int16"])
+@pytest.mark.parametrize("rev", [False, True])
+def test_partialsort_radix_select(b, dtype, rev):
+    """partialsort(c, k) for scalar k through b200_select_kth == sort(c)[k] (the reference: full sort, then
+    c[k], sorting.jl:1015-1022); the input is not modified."""
+    for n in (1, 2, 1000, 4097, 300_003):
+        a = rand(dtype, n)
+        if dtype.startswith("float") and n > 10:
+            a[1] = np.nan; a[2] = -0.0; a[3] = 0.0; a[4] = np.inf; a[5] = -np.inf
+            a[n // 2:n // 2 + n // 8] = a[0]                      # a block of duplicates
+        ref = oracle.sort(a, rev=rev)
+        d = b.CuArray(a)
+        for k in sorted({min(k, n) for k in (1, 2, n // 3 + 1, n // 2 + 1, max(n - 1, 1), n)}):
+            got = b.partialsort(d, k, rev=rev)
+            np.testing.assert_array_equal(bits(np.asarray([got], dtype=a.dtype)), bits(ref[k - 1:k]))
+        np.testing.assert_array_equal(bits(b.Array(d)), bits(a))
+    with pytest.raises(IndexError):
+        b.partialsort(b.CuArray(rand(dtype, 5)), 6)
