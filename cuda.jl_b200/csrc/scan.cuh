@@ -23,6 +23,7 @@
 #pragma once
 #include "ops.cuh"
 #include <cstdlib>
+#include <cstdio>
 
 namespace b200 {
 
@@ -44,6 +45,7 @@ struct ScanParams {
     int32_t exclusive;
     int32_t has_init;
     uint64_t init_bits;            // the Some(x) value, bit pattern of the accumulator type
+    int32_t chain_at;              // scan_pipe_kernel<CHAIN>: pass-2 chunks done before the status prefetch is issued
 };
 
 __device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
@@ -54,6 +56,16 @@ __device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+
+#ifdef B200_SCAN_STATS
+// debug build only (tools/build_variant.sh stats -DB200_SCAN_STATS): where a persistent CTA's time goes
+__device__ unsigned long long g_scan_stats[16];
+#define SC_STAT_T(var) const long long var = clock64()
+#define SC_STAT_ADD(i, v) do { if (threadIdx.x == 0) st_acc[i] += (unsigned long long)(v); } while (0)
+#else
+#define SC_STAT_T(var)
+#define SC_STAT_ADD(i, v)
+#endif
 
 template <class A> struct StatusWords { static constexpr int NW = sizeof(A) > 4 ? 2 : 1; };
 
@@ -528,7 +540,13 @@ __global__ void __launch_bounds__(SC_THREADS) scan_tma_kernel(ScanParams p) {
 //     coalesced 16-byte STGs (the stage is free for the next load right away).
 // Tiles are handed out by an atomic ticket, so a CTA only waits on tiles that some resident
 // CTA already owns.
-template <class Tin, class Tout, class Op, int EPC, int K, int S, int NT, int LOOK>
+// TSTORE (sizeof(Tin) == sizeof(Tout)): pass 2 writes the results back into the stage and one thread
+// hands the whole tile to the TMA unit (cp.async.bulk shared -> global).  With ordinary STGs the SM's
+// LSU queue holds ~64 KB of stores after every pass 2, and the status loads / aggregate publications of
+// warp 0 wait behind them (measured per iteration of ~6500 cycles: ~2600 in the look-back, prefetched
+// status words still not back after ~3400); the bulk store keeps that queue empty.  The stage is refilled
+// one iteration later (ring of S = 4: current, next, loading, draining).
+template <class Tin, class Tout, class Op, int EPC, int K, int S, int NT, int LOOK, bool CHAIN = false, bool TSTORE = false>
 __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
     using A = typename Op::acc_t;
     constexpr int NWARPS = NT / 32;
@@ -547,6 +565,9 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t total = p.tiles_per_seg * p.post;
     const int64_t wbase = (int64_t)warp * WARP_ELEMS;
+#ifdef B200_SCAN_STATS
+    unsigned long long st_acc[16] = {};
+#endif
 
     // thread 0: put ticket g into `stage` and start its load
     auto fill = [&](int stage, long long g) {
@@ -575,7 +596,10 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
         const bool full = valid >= TILE;
         if (valid > TILE) valid = TILE;
         Tin *s_in = reinterpret_cast<Tin *>(s_dyn + stage * STAGE_BYTES);
+        SC_STAT_T(tw0);
         mbar_wait(&s_full[stage], (uint32_t)((s_use[stage] - 1) & 1));
+        SC_STAT_T(tw1);
+        SC_STAT_ADD(1, tw1 - tw0);          // waiting for the tile to land
         A csum[K];
         if (full) {
 #pragma unroll
@@ -648,12 +672,73 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
         return tile_agg;
     };
 
+    // ---- CHAIN mode (warp 0): a CTA's tiles g_0 < g_1 < ... chain through the CTA's OWN previous tile,
+    //   prefix(g_{j+1}) = inclusive(g_j) (+) partial(g_j + 1) (+) ... (+) partial(g_{j+1} - 1),
+    // so nobody ever waits for another tile's INCLUSIVE prefix: only for the aggregates of the tiles between
+    // two of its own tickets (~#CTAs - 1 of them), which their owners publish one iteration before those
+    // tiles' turn.  The status loads are ISSUED right after this CTA published tile g_{j+1}'s aggregate and
+    // CONSUMED an iteration later, so the loaded-L2 round trip (~1.5 us, the critical path of the look-back
+    // variant) overlaps pass 2 of g_j and pass 1 of g_{j+2}.  p.chain_at = how many chunks of pass 2 warp 0
+    // processes before it issues them: later = more of the neighbours' aggregates already published (an
+    // entry that comes back empty costs a full round trip when it is consumed), earlier = longer in flight.
+    A pf_val[LOOK];
+    uint32_t pf_flag[LOOK];
+    int64_t pf_lo = 0, pf_hi = -1;          // status range [lo, hi] (global tile indices) still to be folded
+    int pf_base = 0;                        // 0: segment seed (first tile), 1: identity, 2: this CTA's previous inclusive
+    A incl_own = Op::identity();            // inclusive prefix through this CTA's previous tile
+    auto chain_issue = [&](long long g, long long g_prev, bool have_prev) {
+        const int64_t seg = g / p.tiles_per_seg, seg_start = seg * p.tiles_per_seg;
+        if (g == seg_start) { pf_base = 0; pf_lo = 0; pf_hi = -1; }
+        else if (have_prev && g_prev >= seg_start) { pf_base = 2; pf_lo = g_prev + 1; pf_hi = g - 1; }
+        else { pf_base = 1; pf_lo = seg_start; pf_hi = g - 1; }
+#pragma unroll
+        for (int r = 0; r < LOOK; ++r) {
+            const int64_t idx = pf_hi - (r * 32 + lane);
+            pf_flag[r] = SC_INVALID;
+            pf_val[r] = Op::identity();
+            if (idx >= pf_lo) pf_flag[r] = peek_slot<A>(p.status + idx * NW, pf_val[r]);
+        }
+    };
+    // true when every prefetched status word is valid and the gap fits the prefetch (warp-uniform)
+    auto chain_ready = [&]() -> bool {
+        bool ok = pf_hi - pf_lo < (int64_t)LOOK * 32;
+#pragma unroll
+        for (int r = 0; r < LOOK; ++r) {
+            const int64_t idx = pf_hi - (r * 32 + lane);
+            ok = ok && (idx < pf_lo || pf_flag[r] != SC_INVALID);
+        }
+        return __all_sync(0xffffffffu, ok);
+    };
+    auto chain_consume = [&]() -> A {
+        A val = Op::identity();
+#pragma unroll
+        for (int r = 0; r < LOOK; ++r) {
+            const int64_t idx = pf_hi - (r * 32 + lane);
+            if (idx >= pf_lo) {
+                while (pf_flag[r] == SC_INVALID) pf_flag[r] = peek_slot<A>(p.status + idx * NW, pf_val[r]);
+                val = Op::apply(pf_val[r], val);
+            }
+        }
+        for (int64_t idx = pf_hi - (LOOK * 32 + lane); idx >= pf_lo; idx -= 32) {   // gap wider than the prefetch
+            A v;
+            while (peek_slot<A>(p.status + idx * NW, v) == SC_INVALID) {}
+            val = Op::apply(v, val);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val = Op::apply(val, shfl_xor_any(val, o));
+        const A base = pf_base == 0 ? (p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity())
+                     : pf_base == 1 ? Op::identity() : incl_own;
+        return Op::apply(base, val);
+    };
+    __shared__ int s_chain_ready;
+
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int st = 0; st < S; ++st) { mbar_init(&s_full[st], 1); s_use[st] = 0; }
         fence_proxy_async_smem();
 #pragma unroll
-        for (int st = 0; st < S; ++st) fill(st, (long long)atomicAdd(p.ticket, 1ull));
+        for (int st = 0; st < (TSTORE ? S - 1 : S); ++st) fill(st, (long long)atomicAdd(p.ticket, 1ull));
+        if constexpr (TSTORE) s_tile[S - 1] = total;       // filled at the end of iteration 0
     }
     __syncthreads();
     if (s_tile[0] >= total) return;
@@ -662,7 +747,10 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
     A agg_cur = Op::identity(), agg_nxt = Op::identity();   // meaningful in warp 0
     pass1(0, cpre_cur);
     __syncthreads();
-    if (warp == 0) agg_cur = finish_pass1(0, 0);
+    if (warp == 0) {
+        agg_cur = finish_pass1(0, 0);
+        if constexpr (CHAIN) chain_issue(s_tile[0], 0, false);
+    }
 
     for (int64_t it = 0;; ++it) {
         const int stage = (int)(it % S);
@@ -672,20 +760,49 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
         const bool have_next = s_tile[nxt] < total;
         // ticket for the refill at the end of this iteration: issued now, consumed ~3 us later
         long long next_ticket = 0;
+        SC_STAT_T(t_top);
         if (threadIdx.x == 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);
 
         // ---- pass 1 of the NEXT tile first, so that its aggregate is published a whole iteration
         // before its turn and never waits behind this CTA's own look-back (publishing after the
         // look-back re-creates the serial chain: measured 1.7 TB/s instead of 4.4-5.2 TB/s)
         if (have_next) pass1(nxt, cpre_nxt);
-        __syncthreads();                                   // (A) warp totals of the next tile visible
-        const int64_t seg = g / p.tiles_per_seg, t = g - seg * p.tiles_per_seg;
-        if (warp == 0) {
-            if (have_next) agg_nxt = finish_pass1(nxt, par ^ 1);
-            const A prefix = tile_lookback<Op, LOOK>(p, seg, t, lane, agg_cur, /*publish_partial=*/false);
-            if (lane == 0) s_tile_prefix = prefix;
+        SC_STAT_T(t_p1);
+        if constexpr (CHAIN) {
+            if (warp == 0) {   // status words requested an iteration ago: normally all landed and valid
+                const bool ready = chain_ready();
+                SC_STAT_ADD(7, ready ? 0 : 1);
+                if (ready) {
+                    const A prefix = chain_consume();
+                    incl_own = Op::apply(prefix, agg_cur);
+                    if (lane == 0) s_tile_prefix = prefix;
+                }
+                if (lane == 0) s_chain_ready = ready ? 1 : 0;
+            }
         }
-        __syncthreads();                                   // (B) prefix of the current tile visible
+        SC_STAT_T(t_rdy);
+        __syncthreads();                                   // (A) warp totals of the next tile visible
+        SC_STAT_T(t_a);
+        const int64_t seg = g / p.tiles_per_seg, t = g - seg * p.tiles_per_seg;
+        bool need_b = !CHAIN;
+        if constexpr (CHAIN) need_b = s_chain_ready == 0;  // CTA-uniform
+        if (warp == 0) {
+            // the next tile's aggregate is published BEFORE anything that may wait: a publication gated
+            // behind a wait lets one late tile delay every successor's aggregate (measured: 50x slower)
+            if (have_next) agg_nxt = finish_pass1(nxt, par ^ 1);
+            if constexpr (CHAIN) {
+                if (need_b) {      // some aggregate had not been published when it was prefetched: poll for it now
+                    const A prefix = chain_consume();
+                    incl_own = Op::apply(prefix, agg_cur);
+                    if (lane == 0) s_tile_prefix = prefix;
+                }
+            } else {
+                const A prefix = tile_lookback<Op, LOOK>(p, seg, t, lane, agg_cur, /*publish_partial=*/false);
+                if (lane == 0) s_tile_prefix = prefix;
+            }
+        }
+        if (need_b) __syncthreads();                       // (B) prefix of the current tile visible
+        SC_STAT_T(t_b);
         const A base = Op::apply(s_tile_prefix, s_wexcl[par][warp]);
 
         // ---- pass 2 of the CURRENT tile: apply the prefix, store straight to global
@@ -695,6 +812,9 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
         const Tin *s_in = reinterpret_cast<const Tin *>(s_dyn + stage * STAGE_BYTES);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
+            if constexpr (CHAIN) {
+                if (k == p.chain_at && warp == 0 && have_next) chain_issue(s_tile[nxt], g, true);
+            }
             Tin e[EPC];
             lds_chunk<Tin, EPC>(s_in + wbase + (k * 32 + lane) * EPC, e);
             A run2 = Op::apply(base, cpre_cur[k]);
@@ -705,15 +825,375 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
                 o[q] = p.exclusive ? run2 : nxtv;
                 run2 = nxtv;
             }
-            store_chunk<Tout, A, EPC>(tout, wbase + (k * 32 + lane) * EPC, valid, o);
+            if (TSTORE && valid == TILE) {                 // results replace the inputs in the stage (CTA-uniform branch)
+                if constexpr (TSTORE) {
+                    Tout eo[EPC];
+#pragma unroll
+                    for (int q = 0; q < EPC; ++q) eo[q] = cvt<Tout>(o[q]);
+                    sts_chunk<Tout, EPC>(reinterpret_cast<Tout *>(s_dyn + stage * STAGE_BYTES) + wbase + (k * 32 + lane) * EPC, eo);
+                }
+            } else {
+                store_chunk<Tout, A, EPC>(tout, wbase + (k * 32 + lane) * EPC, valid, o);
+            }
         }
+        if constexpr (CHAIN) {
+            if (p.chain_at >= K && warp == 0 && have_next) chain_issue(s_tile[nxt], g, true);
+        }
+        if constexpr (TSTORE) fence_proxy_async_smem();    // this thread's shared-memory writes -> visible to the TMA unit
+        SC_STAT_T(t_p2);
         __syncthreads();                                   // (C) stage consumed; s_wtot / s_tile_prefix free
-        if (threadIdx.x == 0) fill(stage, next_ticket);
-        if (!have_next) break;
+        SC_STAT_T(t_c);
+        SC_STAT_ADD(0, 1);                 // iterations
+        SC_STAT_ADD(2, t_p1 - t_top);      // ticket + pass 1 (includes [1])
+        SC_STAT_ADD(3, t_rdy - t_p1);      // ready check / early consume (waits for the prefetched loads)
+        SC_STAT_ADD(4, t_a - t_rdy);       // barrier (A)
+        SC_STAT_ADD(5, t_b - t_a);         // publish + look-back / fallback + barrier (B)
+        SC_STAT_ADD(6, t_p2 - t_b);        // pass 2
+        SC_STAT_ADD(8, t_c - t_p2);        // barrier (C)
+        if constexpr (TSTORE) {
+            if (threadIdx.x == 0) {
+                // one bulk group per iteration (empty for a ragged tile), so "at most one group still reading"
+                // means the stage stored an iteration ago is free for the next load
+                if (valid == TILE) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(tout), "r"(smem_u32(s_dyn + stage * STAGE_BYTES)), "r"((uint32_t)STAGE_BYTES) : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                fill((int)((it + S - 1) % S), next_ticket);
+            }
+            if (!have_next) {
+                if (threadIdx.x == 0) tma_store_wait_read();   // shared memory must outlive the last bulk read
+                break;
+            }
+        } else {
+            if (threadIdx.x == 0) fill(stage, next_ticket);
+            if (!have_next) break;
+        }
 #pragma unroll
         for (int k = 0; k < K; ++k) cpre_cur[k] = cpre_nxt[k];
         agg_cur = agg_nxt;
     }
+#ifdef B200_SCAN_STATS
+    if (threadIdx.x == 0)
+        for (int i = 0; i < 16; ++i) if (st_acc[i]) atomicAdd(&g_scan_stats[i], st_acc[i]);
+#endif
+}
+
+// ------------------------------------------------------------------ self-chained pipeline, pass 1 two tiles ahead
+// Same ring and the same CHAIN arithmetic as scan_pipe_kernel<CHAIN>, but with four stages and pass 1 running
+// TWO tiles ahead of pass 2.  Under a saturated memory system a status word needs ~1.7 us to come back and a
+// publication about as long to become visible (measured with B200_SCAN_STATS: prefetched words not back after
+// 3300 cycles, 10-16 % of them still empty), which is a whole iteration; publishing two iterations early gives
+// every consumer's prefetch a full iteration of slack on both sides.
+template <class Tin, class Tout, class Op, int EPC, int K, int NT, int LOOK>
+__global__ void __launch_bounds__(NT + 32) scan_chain2_kernel(ScanParams p) {
+    constexpr int S = 4;
+    constexpr bool CHAIN = true;
+    using A = typename Op::acc_t;
+    constexpr int NWARPS = NT / 32;
+    constexpr int NW = StatusWords<A>::NW;
+    constexpr int WARP_ELEMS = 32 * EPC * K;
+    constexpr int TILE = NWARPS * WARP_ELEMS;
+    constexpr size_t STAGE_BYTES = (size_t)TILE * sizeof(Tin);
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    __shared__ __align__(8) uint64_t s_full[S];
+    __shared__ long long s_tile[S];        // ticket held by each stage
+    __shared__ int s_use[S];               // how many times the stage has been armed (barrier parity)
+    __shared__ long long s_seg[S], s_tt[S];  // segment and tile-in-segment of each stage's ticket (divided once, by the control warp)
+    __shared__ A s_wexcl[3][NWARPS];       // warp-exclusive prefixes inside the tile: [tile sequence % 3][warp]
+    __shared__ A s_wtot[NWARPS];
+    __shared__ A s_tile_prefix;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool ctl = warp == NWARPS;       // warp NWARPS: control (tickets, loads, publications, prefixes); 0..NWARPS-1: compute
+    const int64_t total = p.tiles_per_seg * p.post;
+    const int64_t wbase = (int64_t)warp * WARP_ELEMS;
+#ifdef B200_SCAN_STATS
+    unsigned long long st_acc[16] = {};
+#endif
+
+    // thread 0: put ticket g into `stage` and start its load
+    auto fill = [&](int stage, long long g) {
+        s_tile[stage] = g;
+        s_use[stage] += 1;
+        if (g < total) {
+            const int64_t seg = g / p.tiles_per_seg, t = g - seg * p.tiles_per_seg;
+            s_seg[stage] = seg; s_tt[stage] = t;
+            if (p.n - t * TILE >= TILE) {
+                mbar_expect_tx(&s_full[stage], (uint32_t)STAGE_BYTES);
+                tma_load_1d(s_dyn + stage * STAGE_BYTES, static_cast<const Tin *>(p.in) + seg * p.n + t * TILE,
+                            (uint32_t)STAGE_BYTES, &s_full[stage]);
+            } else {
+                mbar_arrive(&s_full[stage]);   // ragged tail: loaded with ordinary loads in pass 1
+            }
+        }
+    };
+
+    // Pass 1 over the tile in `stage` (blocks until its data has landed): chunk sums, K warp
+    // scans -> chunk-exclusive prefixes inside the warp (returned in cpre), warp totals to smem.
+    // After the caller's __syncthreads, finish_pass1 (warp 0) turns the warp totals into
+    // warp-exclusive prefixes and PUBLISHES the tile aggregate — one tile ahead of its turn.
+    auto pass1 = [&](int stage, A (&cpre)[K]) {
+        const int64_t seg = s_seg[stage], t = s_tt[stage];
+        int64_t valid = p.n - t * TILE;
+        const bool full = valid >= TILE;
+        if (valid > TILE) valid = TILE;
+        Tin *s_in = reinterpret_cast<Tin *>(s_dyn + stage * STAGE_BYTES);
+        SC_STAT_T(tw0);
+        mbar_wait(&s_full[stage], (uint32_t)((s_use[stage] - 1) & 1));
+        SC_STAT_T(tw1);
+        SC_STAT_ADD(1, tw1 - tw0);          // waiting for the tile to land
+        A csum[K];
+        if (full) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                Tin e[EPC];
+                lds_chunk<Tin, EPC>(s_in + wbase + (k * 32 + lane) * EPC, e);
+                A acc = cvt<A>(e[0]);
+#pragma unroll
+                for (int q = 1; q < EPC; ++q) acc = Op::apply(acc, cvt<A>(e[q]));
+                csum[k] = acc;
+            }
+        } else {
+            const Tin *tin = static_cast<const Tin *>(p.in) + seg * p.n + t * TILE;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                A v[EPC];
+                load_chunk<Tin, A, Op, EPC>(tin, wbase + (k * 32 + lane) * EPC, valid, v);
+                Tin e[EPC];
+                A acc = v[0];
+                e[0] = cvt<Tin>(v[0]);
+#pragma unroll
+                for (int q = 1; q < EPC; ++q) { acc = Op::apply(acc, v[q]); e[q] = cvt<Tin>(v[q]); }
+                csum[k] = acc;
+                sts_chunk<Tin, EPC>(s_in + wbase + (k * 32 + lane) * EPC, e);   // own chunk only
+            }
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                A up = shfl_up_any(csum[k], d);
+                if (lane >= d) csum[k] = Op::apply(up, csum[k]);
+            }
+        }
+        A run = Op::identity();
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            A excl = shfl_up_any(csum[k], 1);
+            A rtot = shfl_idx_any(csum[k], 31);
+            cpre[k] = lane == 0 ? run : Op::apply(run, excl);
+            run = Op::apply(run, rtot);
+        }
+        if (lane == 0) s_wtot[warp] = run;
+    };
+    // warp 0 only, after a __syncthreads that follows pass1(stage); returns the tile aggregate
+    auto finish_pass1 = [&](int stage, int parity) -> A {
+        const int64_t seg = s_seg[stage], t = s_tt[stage];
+        A wincl = lane < NWARPS ? s_wtot[lane] : Op::identity();
+#pragma unroll
+        for (int d = 1; d < NWARPS; d <<= 1) {
+            A up = shfl_up_any(wincl, d);
+            if (lane >= d) wincl = Op::apply(up, wincl);
+        }
+        const A tile_agg = shfl_idx_any(wincl, NWARPS - 1);
+        A wexcl = shfl_up_any(wincl, 1);
+        if (lane == 0) wexcl = Op::identity();
+        if (lane < NWARPS) s_wexcl[parity][lane] = wexcl;
+        if (lane == 0) {
+            uint64_t *slots = p.status + seg * p.tiles_per_seg * NW;
+            if (t == 0) {
+                if (p.tiles_per_seg > 1) {
+                    const A seed = p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity();
+                    publish<A>(slots, SC_INCLUSIVE, Op::apply(seed, tile_agg));
+                }
+            } else {
+                publish<A>(slots + t * NW, SC_PARTIAL, tile_agg);
+            }
+        }
+        return tile_agg;
+    };
+
+    // ---- CHAIN mode (warp 0): a CTA's tiles g_0 < g_1 < ... chain through the CTA's OWN previous tile,
+    //   prefix(g_{j+1}) = inclusive(g_j) (+) partial(g_j + 1) (+) ... (+) partial(g_{j+1} - 1),
+    // so nobody ever waits for another tile's INCLUSIVE prefix: only for the aggregates of the tiles between
+    // two of its own tickets (~#CTAs - 1 of them), which their owners publish one iteration before those
+    // tiles' turn.  The status loads are ISSUED right after this CTA published tile g_{j+1}'s aggregate and
+    // CONSUMED an iteration later, so the loaded-L2 round trip (~1.5 us, the critical path of the look-back
+    // variant) overlaps pass 2 of g_j and pass 1 of g_{j+2}.  p.chain_at = how many chunks of pass 2 warp 0
+    // processes before it issues them: later = more of the neighbours' aggregates already published (an
+    // entry that comes back empty costs a full round trip when it is consumed), earlier = longer in flight.
+    A pf_val[LOOK];
+    uint32_t pf_flag[LOOK];
+    int64_t pf_lo = 0, pf_hi = -1;          // status range [lo, hi] (global tile indices) still to be folded
+    int pf_base = 0;                        // 0: segment seed (first tile), 1: identity, 2: this CTA's previous inclusive
+    A incl_own = Op::identity();            // inclusive prefix through this CTA's previous tile
+    auto chain_issue = [&](long long g, long long t_in_seg, long long g_prev, bool have_prev) {
+        const int64_t seg_start = g - t_in_seg;
+        if (g == seg_start) { pf_base = 0; pf_lo = 0; pf_hi = -1; }
+        else if (have_prev && g_prev >= seg_start) { pf_base = 2; pf_lo = g_prev + 1; pf_hi = g - 1; }
+        else { pf_base = 1; pf_lo = seg_start; pf_hi = g - 1; }
+#pragma unroll
+        for (int r = 0; r < LOOK; ++r) {
+            const int64_t idx = pf_hi - (r * 32 + lane);
+            pf_flag[r] = SC_INVALID;
+            pf_val[r] = Op::identity();
+            if (idx >= pf_lo) pf_flag[r] = peek_slot<A>(p.status + idx * NW, pf_val[r]);
+        }
+    };
+    // true when every prefetched status word is valid and the gap fits the prefetch (warp-uniform)
+    auto chain_ready = [&]() -> bool {
+        bool ok = pf_hi - pf_lo < (int64_t)LOOK * 32;
+#pragma unroll
+        for (int r = 0; r < LOOK; ++r) {
+            const int64_t idx = pf_hi - (r * 32 + lane);
+            ok = ok && (idx < pf_lo || pf_flag[r] != SC_INVALID);
+        }
+        return __all_sync(0xffffffffu, ok);
+    };
+    auto chain_consume = [&]() -> A {
+        A val = Op::identity();
+#pragma unroll
+        for (int r = 0; r < LOOK; ++r) {
+            const int64_t idx = pf_hi - (r * 32 + lane);
+            if (idx >= pf_lo) {
+                while (pf_flag[r] == SC_INVALID) pf_flag[r] = peek_slot<A>(p.status + idx * NW, pf_val[r]);
+                val = Op::apply(pf_val[r], val);
+            }
+        }
+        for (int64_t idx = pf_hi - (LOOK * 32 + lane); idx >= pf_lo; idx -= 32) {   // gap wider than the prefetch
+            A v;
+            while (peek_slot<A>(p.status + idx * NW, v) == SC_INVALID) {}
+            val = Op::apply(v, val);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val = Op::apply(val, shfl_xor_any(val, o));
+        const A base = pf_base == 0 ? (p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity())
+                     : pf_base == 1 ? Op::identity() : incl_own;
+        return Op::apply(base, val);
+    };
+    __shared__ int s_chain_ready;
+
+    const bool boss = threadIdx.x == NT;   // control warp, lane 0
+    if (boss) {
+#pragma unroll
+        for (int st = 0; st < S; ++st) { mbar_init(&s_full[st], 1); s_use[st] = 0; }
+        fence_proxy_async_smem();
+#pragma unroll
+        for (int st = 0; st < S; ++st) fill(st, (long long)atomicAdd(p.ticket, 1ull));
+    }
+    __syncthreads();
+    if (s_tile[0] >= total) return;
+
+    // cpre0 / agg0: current tile, cpre1 / agg1: next tile, cpre2 / agg2: the tile after that
+    A cpre0[K], cpre1[K], cpre2[K];
+    A agg0 = Op::identity(), agg1 = Op::identity(), agg2 = Op::identity();   // meaningful in the control warp
+    if (!ctl) pass1(0, cpre0);
+    __syncthreads();
+    if (ctl) {
+        agg0 = finish_pass1(0, 0);
+        chain_issue(s_tile[0], s_tt[0], 0, false);
+    }
+    __syncthreads();                                       // s_wtot free again
+    if (s_tile[1] < total) {
+        if (!ctl) pass1(1, cpre1);
+        __syncthreads();
+        if (ctl) agg1 = finish_pass1(1, 1);
+        __syncthreads();
+    }
+
+    // compute and control warps meet at these barriers from different call sites: a named barrier with an
+    // explicit thread count instead of __syncthreads()
+    auto cta_bar = [] { asm volatile("bar.sync 1, %0;" :: "n"(NT + 32) : "memory"); };
+    for (int64_t it = 0;; ++it) {
+        const int stage = (int)(it % S);
+        const int st1 = (int)((it + 1) % S), st2 = (int)((it + 2) % S);
+        const long long g = s_tile[stage];
+        const bool have1 = s_tile[st1] < total;
+        const bool have2 = have1 && s_tile[st2] < total;
+        const int64_t seg = s_seg[stage], t = s_tt[stage];
+        if (ctl) {
+            // ================= control warp: everything serial, overlapped with the compute warps' passes
+            long long next_ticket = 0;
+            if (lane == 0) next_ticket = (long long)atomicAdd(p.ticket, 1ull);
+            SC_STAT_T(t_top);
+            const bool ready = chain_ready();              // status words requested an iteration ago
+            if (ready) {
+                const A prefix = chain_consume();
+                incl_own = Op::apply(prefix, agg0);
+                if (lane == 0) s_tile_prefix = prefix;
+            }
+            if (lane == 0) s_chain_ready = ready ? 1 : 0;
+            SC_STAT_T(t_rdy);
+            cta_bar();                               // (A)
+            SC_STAT_T(t_a);
+            if (have2) agg2 = finish_pass1(st2, (int)((it + 2) % 3));     // published before anything that may wait
+            if (!ready) {
+                const A prefix = chain_consume();
+                incl_own = Op::apply(prefix, agg0);
+                if (lane == 0) s_tile_prefix = prefix;
+                cta_bar();                           // (B)
+            }
+            if (have1) chain_issue(s_tile[st1], s_tt[st1], g, true);
+            SC_STAT_T(t_b);
+            cta_bar();                               // (C)
+            SC_STAT_T(t_c);
+            if (lane == 0) {
+#ifdef B200_SCAN_STATS
+                st_acc[0] += 1; st_acc[7] += ready ? 0 : 1;
+                st_acc[3] += (unsigned long long)(t_rdy - t_top);   // ready check + consume
+                st_acc[4] += (unsigned long long)(t_a - t_rdy);     // waiting for pass 1 at (A)
+                st_acc[5] += (unsigned long long)(t_b - t_a);       // publish + fallback + issue
+                st_acc[8] += (unsigned long long)(t_c - t_b);       // waiting for pass 2 at (C)
+#endif
+                fill(stage, next_ticket);
+            }
+            if (!have1) break;
+            agg0 = agg1; agg1 = agg2;
+        } else {
+            // ================= compute warps
+            SC_STAT_T(t_top);
+            if (have2) pass1(st2, cpre2);
+            SC_STAT_T(t_p1);
+            cta_bar();                               // (A) warp totals of tile it+2 / prefix of tile it visible
+            SC_STAT_T(t_a);
+            if (s_chain_ready == 0) cta_bar();       // (B) CTA-uniform
+            const A base = Op::apply(s_tile_prefix, s_wexcl[it % 3][warp]);
+            int64_t valid = p.n - t * TILE;
+            if (valid > TILE) valid = TILE;
+            Tout *tout = static_cast<Tout *>(p.out) + seg * p.n + t * TILE;
+            const Tin *s_in = reinterpret_cast<const Tin *>(s_dyn + stage * STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                Tin e[EPC];
+                lds_chunk<Tin, EPC>(s_in + wbase + (k * 32 + lane) * EPC, e);
+                A run2 = Op::apply(base, cpre0[k]);
+                A o[EPC];
+#pragma unroll
+                for (int q = 0; q < EPC; ++q) {
+                    const A nxtv = Op::apply(run2, cvt<A>(e[q]));
+                    o[q] = p.exclusive ? run2 : nxtv;
+                    run2 = nxtv;
+                }
+                store_chunk<Tout, A, EPC>(tout, wbase + (k * 32 + lane) * EPC, valid, o);
+            }
+            SC_STAT_T(t_p2);
+            cta_bar();                               // (C) stage consumed; s_wtot / s_tile_prefix free
+            SC_STAT_T(t_c);
+            SC_STAT_ADD(2, t_p1 - t_top);                  // pass 1 (thread 0)
+            SC_STAT_ADD(9, t_a - t_p1);                    // waiting at (A)
+            SC_STAT_ADD(6, t_p2 - t_a);                    // pass 2
+            SC_STAT_ADD(10, t_c - t_p2);                   // waiting at (C)
+            if (!have1) break;
+#pragma unroll
+            for (int k = 0; k < K; ++k) { cpre0[k] = cpre1[k]; cpre1[k] = cpre2[k]; }
+        }
+    }
+#ifdef B200_SCAN_STATS
+    if (lane == 0 && (warp == 0 || ctl))
+        for (int i = 0; i < 16; ++i) if (st_acc[i]) atomicAdd(&g_scan_stats[i], st_acc[i]);
+#endif
 }
 
 // ------------------------------------------------------------------ warp-specialised pipeline
@@ -1268,15 +1748,11 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
     const size_t clear = (size_t)((char *)(status + post * p.tiles_per_seg * NW) - (char *)ticket);
     B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, clear, stream));
     if (vec) {
-        // one persistent 512-thread CTA per SM, 3 stages of a 16-KiB-per-warp-group tile: with
-        // <= #SM tiles in flight one 160-wide look-back window usually reaches an inclusive prefix
-#ifndef B200_SCAN_STAGES
-#define B200_SCAN_STAGES 3
-#endif
-        // measured on B200 (cumsum 2^30): Float32 5.2 TB/s with one 512-thread CTA per SM and a 160-wide
-        // window vs 4.4 TB/s with two 256-thread CTAs; Int64 4.8 TB/s with two 256-thread CTAs vs 4.5 TB/s
+        // Persistent CTAs over a ring of TMA-loaded stages.  Measured on B200 (cumsum 2^30):
+        //   look-back, STG stores:  Float32 5.3 TB/s (one 512-thread CTA per SM, 96-wide window),
+        //                           Int64 4.8 TB/s (two 256-thread CTAs per SM)
+        //   see DESIGN.md section 4 for the self-chained (CHAIN) and bulk-store (TSTORE) variants
         constexpr bool kWide = sizeof(A) > 4;
-        constexpr int kStages = B200_SCAN_STAGES;
 #ifndef B200_SCAN_NT_NARROW
 #define B200_SCAN_NT_NARROW 512
 #endif
@@ -1286,29 +1762,130 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
 #ifndef B200_SCAN_NT_WIDE
 #define B200_SCAN_NT_WIDE 256
 #endif
-        constexpr int kThreads = kWide ? B200_SCAN_NT_WIDE : B200_SCAN_NT_NARROW;
-        constexpr int kK = kWide ? S::K : B200_SCAN_K_NARROW;
 #ifndef B200_SCAN_LOOK_NARROW
 #define B200_SCAN_LOOK_NARROW 3
 #endif
-        constexpr int kLook = kWide ? 4 : B200_SCAN_LOOK_NARROW;
-        constexpr int64_t kTile = (int64_t)kThreads * S::EPC * kK;
-        constexpr size_t smem = (size_t)kTile * sizeof(Tin) * kStages;
-        static const bool use_ws = getenv("B200_SCAN_WS") != nullptr;   // warp-specialised variant: opt-in (measured slower)
-        auto kern = use_ws ? scan_pipe_ws_kernel<Tin, Tout, Op, S::EPC, kK, kStages, (kThreads > 992 ? 992 : kThreads), kLook>
-                           : scan_pipe_kernel<Tin, Tout, Op, S::EPC, kK, kStages, kThreads, kLook>;
-        static thread_local int attr_dev_mask[64];  // cudaFuncSetAttribute once per (thread, device, instantiation)
+#ifndef B200_SCAN_CHAIN_AT
+#define B200_SCAN_CHAIN_AT 4
+#endif
+#ifndef B200_SCAN_CHAIN_CTAS
+#define B200_SCAN_CHAIN_CTAS 2
+#endif
+        // Variant selection.  Default: scan_chain2_kernel for accumulators of up to 32 bits, look-back + STG for 64-bit
+        // ones.  B200_SCAN_CHAIN=0 / 2 forces look-back / chain2 for every type.  The other experiments (single-ahead
+        // chain, bulk-store ring, look-back in its own warp) are only compiled with -DB200_SCAN_EXPERIMENTS
+        // (B200_SCAN_CHAIN=1, B200_SCAN_TSTORE=1, B200_SCAN_WS=1); measurements in DESIGN.md section 4.
+        static const char *chain_env = getenv("B200_SCAN_CHAIN");
+#ifdef B200_SCAN_EXPERIMENTS
+        static const bool use_ws = getenv("B200_SCAN_WS") != nullptr;
+        static const bool use_chain = chain_env && chain_env[0] == '1';
+        constexpr bool kSameSize = sizeof(Tin) == sizeof(Tout);
+        static const bool use_tstore = kSameSize && !use_ws && getenv("B200_SCAN_TSTORE") && getenv("B200_SCAN_TSTORE")[0] == '1';
+#else
+        constexpr bool use_ws = false, use_chain = false, kSameSize = false, use_tstore = false;
+#endif
+        static const int chain_at = getenv("B200_SCAN_CHAIN_AT") ? atoi(getenv("B200_SCAN_CHAIN_AT")) : B200_SCAN_CHAIN_AT;
+        p.chain_at = chain_at < 0 ? 0 : chain_at;
         int dev = 0;
         B200_CUDA_TRY(cudaGetDevice(&dev));
-        if (dev >= 0 && dev < 64 && !attr_dev_mask[dev]) {
-            B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_dev_mask[dev] = 1;
+        // one launch shape = (threads, chunk rows K, stages, CTAs per SM cap); the kernel variant is picked inside
+        auto launch = [&](auto nt_c, auto k_c, auto st_c, auto tstore_c) -> int32_t {
+            constexpr int kThreads = decltype(nt_c)::value, kK = decltype(k_c)::value, kStages = decltype(st_c)::value;
+            constexpr bool kTstore = decltype(tstore_c)::value;
+            constexpr int kLook = kWide ? 4 : B200_SCAN_LOOK_NARROW;
+            constexpr int64_t kTile = (int64_t)kThreads * S::EPC * kK;
+            constexpr size_t smem = (size_t)kTile * sizeof(Tin) * kStages;
+            constexpr int kFit = (200 * 1024) / (int)smem > 0 ? (200 * 1024) / (int)smem : 1;   // CTAs per SM by shared memory
+            constexpr int kChainCtas = kFit < B200_SCAN_CHAIN_CTAS ? kFit : B200_SCAN_CHAIN_CTAS;
+            constexpr int kRows = (148 * kChainCtas * 5 / 4 + 31) / 32;     // 6 or 12 rows of 32 status words (gap + 25 %)
+            void (*kern)(ScanParams);
+#ifdef B200_SCAN_EXPERIMENTS
+            if constexpr (kTstore)
+                kern = use_chain ? scan_pipe_kernel<Tin, Tout, Op, S::EPC, kK, kStages, kThreads, kRows, true, true>
+                                 : scan_pipe_kernel<Tin, Tout, Op, S::EPC, kK, kStages, kThreads, kLook, false, true>;
+            else
+                kern = use_ws ? scan_pipe_ws_kernel<Tin, Tout, Op, S::EPC, kK, kStages, (kThreads > 992 ? 992 : kThreads), kLook>
+                     : use_chain ? scan_pipe_kernel<Tin, Tout, Op, S::EPC, kK, kStages, kThreads, kRows, true>
+                                 : scan_pipe_kernel<Tin, Tout, Op, S::EPC, kK, kStages, kThreads, kLook>;
+#else
+            (void)kRows;
+            kern = scan_pipe_kernel<Tin, Tout, Op, S::EPC, kK, kStages, kThreads, kLook>;
+#endif
+            static thread_local int attr_dev_mask[64][4];  // cudaFuncSetAttribute once per (thread, device, variant)
+            const int variant = (use_ws ? 2 : 0) + (use_chain ? 1 : 0);
+            if (dev >= 0 && dev < 64 && !attr_dev_mask[dev][variant]) {
+                B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_dev_mask[dev][variant] = 1;
+            }
+            p.tiles_per_seg = cdiv(n, kTile);
+            const int64_t ptiles = p.tiles_per_seg * post;
+            int64_t pgrid = (int64_t)devinfo().sm_count * (use_chain && !use_ws ? kChainCtas : kFit);
+            if (pgrid > ptiles) pgrid = ptiles;
+#ifdef B200_SCAN_STATS
+            unsigned long long zero[16] = {};
+            cudaMemcpyToSymbol(g_scan_stats, zero, sizeof(zero));
+#endif
+            kern<<<(unsigned int)pgrid, use_ws && !kTstore ? kThreads + 32 : kThreads, smem, stream>>>(p);
+#ifdef B200_SCAN_STATS
+            cudaStreamSynchronize(stream);
+            unsigned long long h[16];
+            cudaMemcpyFromSymbol(h, g_scan_stats, sizeof(h));
+            if (h[0]) fprintf(stderr, "[scan stats] chain=%d tstore=%d grid=%lld tiles=%lld iters=%llu | cycles/iter: mbar-wait %.0f  ticket+pass1 %.0f  ready %.0f  barA %.0f  "
+                    "publish+lookback+barB %.0f  pass2 %.0f  barC %.0f | fallbacks %.1f%%\n", (int)use_chain, (int)kTstore, (long long)pgrid, (long long)ptiles, h[0],
+                    (double)h[1] / h[0], (double)h[2] / h[0], (double)h[3] / h[0], (double)h[4] / h[0], (double)h[5] / h[0],
+                    (double)h[6] / h[0], (double)h[8] / h[0], 100.0 * h[7] / h[0]);
+#endif
+            return B200_OK;
+        };
+        using std::integral_constant;
+        int32_t rc;
+        static const bool use_chain2 = chain_env ? chain_env[0] == '2' : !kWide;
+        if (use_chain2) {
+#ifndef B200_SCAN_CHAIN2_K
+#define B200_SCAN_CHAIN2_K 6
+#endif
+            constexpr int kThreads = 480, kK = B200_SCAN_CHAIN2_K;   // 15 compute warps + 1 control warp = 512 threads (128 registers each)
+            constexpr int64_t kTile = (int64_t)kThreads * S::EPC * kK;
+            constexpr size_t smem = (size_t)kTile * sizeof(Tin) * 4;
+            constexpr int kFit = (200 * 1024) / (int)smem > 0 ? (200 * 1024) / (int)smem : 1;
+            constexpr int kCtas = kFit < 2 ? kFit : 2;
+            constexpr int kRows = (148 * kCtas * 5 / 4 + 31) / 32;
+            auto kern = scan_chain2_kernel<Tin, Tout, Op, S::EPC, kK, kThreads, kRows>;
+            static thread_local int attr2_dev_mask[64];
+            if (dev >= 0 && dev < 64 && !attr2_dev_mask[dev]) {
+                B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr2_dev_mask[dev] = 1;
+            }
+            p.tiles_per_seg = cdiv(n, kTile);
+            const int64_t ptiles = p.tiles_per_seg * post;
+            int64_t pgrid = (int64_t)devinfo().sm_count * kCtas;
+            if (pgrid > ptiles) pgrid = ptiles;
+#ifdef B200_SCAN_STATS
+            unsigned long long zero[16] = {};
+            cudaMemcpyToSymbol(g_scan_stats, zero, sizeof(zero));
+#endif
+            kern<<<(unsigned int)pgrid, kThreads + 32, smem, stream>>>(p);
+#ifdef B200_SCAN_STATS
+            cudaStreamSynchronize(stream);
+            unsigned long long h[16];
+            cudaMemcpyFromSymbol(h, g_scan_stats, sizeof(h));
+            if (h[0]) fprintf(stderr, "[scan stats] chain2 grid=%lld tiles=%lld iters=%llu | compute cycles/iter: mbar-wait %.0f  pass1 %.0f  wait(A) %.0f  pass2 %.0f  wait(C) %.0f"
+                    " | control: ready+consume %.0f  wait(A) %.0f  publish+fallback+issue %.0f  wait(C) %.0f | fallbacks %.1f%%\n", (long long)pgrid, (long long)ptiles, h[0],
+                    (double)h[1] / h[0], (double)h[2] / h[0], (double)h[9] / h[0], (double)h[6] / h[0], (double)h[10] / h[0],
+                    (double)h[3] / h[0], (double)h[4] / h[0], (double)h[5] / h[0], (double)h[8] / h[0], 100.0 * h[7] / h[0]);
+#endif
+            rc = B200_OK;
+        } else
+        if constexpr (kSameSize) {
+            // bulk-store ring: 4 stages of 512 x EPC x 7 elements (57344 bytes for 4- and 8-byte types), one CTA per SM
+            if (use_tstore) rc = launch(integral_constant<int, 512>{}, integral_constant<int, 7>{}, integral_constant<int, 4>{}, std::true_type{});
+            else rc = launch(integral_constant<int, (kWide ? B200_SCAN_NT_WIDE : B200_SCAN_NT_NARROW)>{},
+                             integral_constant<int, (kWide ? S::K : B200_SCAN_K_NARROW)>{}, integral_constant<int, 3>{}, std::false_type{});
+        } else {
+            rc = launch(integral_constant<int, (kWide ? B200_SCAN_NT_WIDE : B200_SCAN_NT_NARROW)>{},
+                        integral_constant<int, (kWide ? S::K : B200_SCAN_K_NARROW)>{}, integral_constant<int, 3>{}, std::false_type{});
         }
-        p.tiles_per_seg = cdiv(n, kTile);
-        const int64_t ptiles = p.tiles_per_seg * post;
-        int64_t pgrid = (int64_t)devinfo().sm_count * ((200 * 1024) / (int64_t)smem > 0 ? (200 * 1024) / (int64_t)smem : 1);
-        if (pgrid > ptiles) pgrid = ptiles;
-        kern<<<(unsigned int)pgrid, use_ws ? kThreads + 32 : kThreads, smem, stream>>>(p);
+        if (rc != B200_OK) return rc;
     }
     else scan_contig_kernel<Tin, Tout, Op, 1, S::K1><<<(unsigned int)grid, SC_THREADS, 0, stream>>>(p);
     B200_CHECK_LAUNCH();
