@@ -906,6 +906,7 @@ __global__ void __launch_bounds__(NT + 32) scan_chain2_kernel(ScanParams p) {
     __shared__ A s_tile_prefix;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto chunk_of = [&](int kk) { return (kk * 32 + lane) * EPC; };
     const bool ctl = warp == NWARPS;       // warp NWARPS: control (tickets, loads, publications, prefixes); 0..NWARPS-1: compute
     const int64_t total = p.tiles_per_seg * p.post;
     const int64_t wbase = (int64_t)warp * WARP_ELEMS;
@@ -949,7 +950,7 @@ __global__ void __launch_bounds__(NT + 32) scan_chain2_kernel(ScanParams p) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 Tin e[EPC];
-                lds_chunk<Tin, EPC>(s_in + wbase + (k * 32 + lane) * EPC, e);
+                lds_chunk<Tin, EPC>(s_in + wbase + chunk_of(k), e);
                 A acc = cvt<A>(e[0]);
 #pragma unroll
                 for (int q = 1; q < EPC; ++q) acc = Op::apply(acc, cvt<A>(e[q]));
@@ -960,14 +961,14 @@ __global__ void __launch_bounds__(NT + 32) scan_chain2_kernel(ScanParams p) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 A v[EPC];
-                load_chunk<Tin, A, Op, EPC>(tin, wbase + (k * 32 + lane) * EPC, valid, v);
+                load_chunk<Tin, A, Op, EPC>(tin, wbase + chunk_of(k), valid, v);
                 Tin e[EPC];
                 A acc = v[0];
                 e[0] = cvt<Tin>(v[0]);
 #pragma unroll
                 for (int q = 1; q < EPC; ++q) { acc = Op::apply(acc, v[q]); e[q] = cvt<Tin>(v[q]); }
                 csum[k] = acc;
-                sts_chunk<Tin, EPC>(s_in + wbase + (k * 32 + lane) * EPC, e);   // own chunk only
+                sts_chunk<Tin, EPC>(s_in + wbase + chunk_of(k), e);   // own chunk only
             }
         }
 #pragma unroll
@@ -1167,7 +1168,7 @@ __global__ void __launch_bounds__(NT + 32) scan_chain2_kernel(ScanParams p) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 Tin e[EPC];
-                lds_chunk<Tin, EPC>(s_in + wbase + (k * 32 + lane) * EPC, e);
+                lds_chunk<Tin, EPC>(s_in + wbase + chunk_of(k), e);
                 A run2 = Op::apply(base, cpre0[k]);
                 A o[EPC];
 #pragma unroll
@@ -1176,7 +1177,7 @@ __global__ void __launch_bounds__(NT + 32) scan_chain2_kernel(ScanParams p) {
                     o[q] = p.exclusive ? run2 : nxtv;
                     run2 = nxtv;
                 }
-                store_chunk<Tout, A, EPC>(tout, wbase + (k * 32 + lane) * EPC, valid, o);
+                store_chunk<Tout, A, EPC>(tout, wbase + chunk_of(k), valid, o);
             }
             SC_STAT_T(t_p2);
             cta_bar();                               // (C) stage consumed; s_wtot / s_tile_prefix free
@@ -1720,7 +1721,9 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
     const bool seg_ok = post == 1 || (n % S::EPC == 0);
     const bool aligned = query || ((reinterpret_cast<uintptr_t>(in) % (S::EPC * sizeof(Tin))) == 0 &&
                                    (reinterpret_cast<uintptr_t>(out) % (S::EPC * sizeof(Tout))) == 0);
-    const bool vec = seg_ok && aligned && S::EPC > 1;
+    // the persistent kernels load tiles with cp.async.bulk: global source 16-byte aligned for every segment
+    const bool tma_ok = query || ((reinterpret_cast<uintptr_t>(in) % 16) == 0 && (post == 1 || (n * sizeof(Tin)) % 16 == 0));
+    const bool vec = seg_ok && aligned && S::EPC > 1 && tma_ok;
     // workspace is sized for the scalar tiling (smaller tiles => more status words) so that
     // the query does not depend on pointer alignment
     const int64_t tps_max = cdiv(n, (int64_t)(S::TILE_SCALAR < S::TILE_VEC ? S::TILE_SCALAR : S::TILE_VEC));
@@ -1771,8 +1774,8 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
 #ifndef B200_SCAN_CHAIN_CTAS
 #define B200_SCAN_CHAIN_CTAS 2
 #endif
-        // Variant selection.  Default: scan_chain2_kernel for accumulators of up to 32 bits, look-back + STG for 64-bit
-        // ones.  B200_SCAN_CHAIN=0 / 2 forces look-back / chain2 for every type.  The other experiments (single-ahead
+        // Variant selection.  Default: scan_chain2_kernel (measured on B200, cumsum 2^30: Float32 6.14 TB/s vs 5.28 with
+        // the look-back kernel, Int64 4.87 vs 4.82).  B200_SCAN_CHAIN=0 selects the look-back kernel.  The other experiments (single-ahead
         // chain, bulk-store ring, look-back in its own warp) are only compiled with -DB200_SCAN_EXPERIMENTS
         // (B200_SCAN_CHAIN=1, B200_SCAN_TSTORE=1, B200_SCAN_WS=1); measurements in DESIGN.md section 4.
         static const char *chain_env = getenv("B200_SCAN_CHAIN");
@@ -1839,10 +1842,10 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
         };
         using std::integral_constant;
         int32_t rc;
-        static const bool use_chain2 = chain_env ? chain_env[0] == '2' : !kWide;
+        static const bool use_chain2 = chain_env ? chain_env[0] == '2' : true;
         if (use_chain2) {
 #ifndef B200_SCAN_CHAIN2_K
-#define B200_SCAN_CHAIN2_K 6
+#define B200_SCAN_CHAIN2_K 7
 #endif
             constexpr int kThreads = 480, kK = B200_SCAN_CHAIN2_K;   // 15 compute warps + 1 control warp = 512 threads (128 registers each)
             constexpr int64_t kTile = (int64_t)kThreads * S::EPC * kK;

@@ -25,7 +25,17 @@ constexpr int RX_RADIX = 256;
 #ifndef B200_RX_MATCH_MASK
 #define B200_RX_MATCH_MASK 0x8888   // items 3, 7, 11, 15 of every 16
 #endif
-constexpr int RX_LOOK = 4;   // predecessor tiles inspected per look-back round trip
+#ifndef B200_RX_LOOK
+#define B200_RX_LOOK 4
+#endif
+constexpr int RX_LOOK = B200_RX_LOOK;   // predecessor tiles inspected per look-back round trip
+// The ranking loop's warp-level ordering points: __syncwarp() costs an issue slot (SASS NOP) per call; the warp runs
+// converged here (predicated store, no branch), so a compiler barrier is enough when B200_RX_NOSYNCWARP is set.
+#ifdef B200_RX_NOSYNCWARP
+#define RX_WARP_ORDER() asm volatile("" ::: "memory")
+#else
+#define RX_WARP_ORDER() __syncwarp()
+#endif
 
 template <int KB> struct KeyOf;
 template <> struct KeyOf<1> { using type = uint8_t; };
@@ -318,9 +328,9 @@ __global__ void __launch_bounds__(RX_THREADS) radix_onesweep_kernel(OnesweepPara
         const unsigned int below = __popc(lower);
         volatile unsigned int *ctr = whist + digit;
         const unsigned int old = *ctr;
-        __syncwarp();
+        RX_WARP_ORDER();
         if (lower == 0u) *ctr = old + __popc(peers);
-        __syncwarp();
+        RX_WARP_ORDER();
         ranks[i] = (unsigned short)(old + below);
     }
     __syncthreads();

@@ -82,6 +82,18 @@ function b200_sortperm(ws, ws_bytes, keys, perm, dkey, dindex, n, nseg, descendi
               linear::Int32, s::CUDACore.CUstream)::Int32)
 end
 
+function b200_select_kth_workspace_bytes(dkey, n)
+    bytes = Ref{Csize_t}(0)
+    check(@ccall libb200arrays[].b200_select_kth_workspace_bytes(dkey::Int32, n::Int64, bytes::Ref{Csize_t})::Int32)
+    return Int(bytes[])
+end
+
+function b200_select_kth(ws, ws_bytes, keys, dkey, n, k, descending, out, s::CuStream)
+    initialize_context()
+    check(@gcsafe_ccall libb200arrays[].b200_select_kth(ws::CuPtr{Cvoid}, ws_bytes::Csize_t, keys::CuPtr{Cvoid},
+              dkey::Int32, n::Int64, k::Int64, descending::Int32, out::CuPtr{Cvoid}, s::CUDACore.CUstream)::Int32)
+end
+
 function b200_sort_dims_workspace_bytes(dkey, sortperm, pre, n, post)
     bytes = Ref{Csize_t}(0)
     check(@ccall libb200arrays[].b200_sort_dims_workspace_bytes(dkey::Int32, sortperm::Int32, pre::Int64, n::Int64,

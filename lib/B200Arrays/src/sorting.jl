@@ -49,4 +49,20 @@ function Base.sortperm(c::CuVector{T}; kwargs...) where {T<:SortTypes}
 end
 
 # partialsort!(c, k, ::BitonicSortAlg) = sort! + copy(c[k]) (sorting.jl:1015-1020) reaches the
-# sort! method above unchanged; nothing to override.
+# sort! method above unchanged (it must leave `c` sorted); nothing to override.
+#
+# Base.partialsort(c, k; kw...) = partialsort!(copy(c), k; kw...): for a scalar k neither the copy nor the
+# sort is needed — b200_select_kth (MSD radix select: sizeof(T) streaming reads of c, c untouched) returns the
+# element a stable sort would put at position k.  Ranges and custom lt/by keep the reference path.
+function Base.partialsort(c::CuVector{T}, k::Integer; lt=isless, by=identity, rev::Bool=false) where {T<:SortTypes}
+    if !enabled() || lt !== isless || by !== identity
+        return invoke(partialsort, Tuple{AbstractVector,Union{Integer,OrdinalRange}}, c, k; lt, by, rev)
+    end
+    checkbounds(c, k)
+    out = CuVector{T}(undef, 1)
+    bytes = b200_select_kth_workspace_bytes(dtype_code(T), length(c))
+    with_ws(bytes) do ws, nb
+        b200_select_kth(ws, nb, c, dtype_code(T), length(c), Int64(k - firstindex(c)), Int32(rev), out, stream())
+    end
+    return CUDACore.@allowscalar out[1]
+end

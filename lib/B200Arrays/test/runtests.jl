@@ -11,6 +11,9 @@ include(joinpath(CUDA_TEST, "setup.jl"))
     # A/B: same inputs through the reference kernels
     x = CUDA.rand(Float32, 1 << 20)
     s_graft = sum(x); p_graft = Array(sortperm(x)); c_graft = Array(cumsum(x))
+    k_graft = [partialsort(x, k) for k in (1, 1 << 19, 1 << 20)]           # radix select, x untouched
+    @test k_graft == sort(Array(x))[[1, 1 << 19, 1 << 20]]
+    @test partialsort(x, 7; rev=true) == sort(Array(x); rev=true)[7]
     B200Arrays.enable!(false)
     @test sum(x) ≈ s_graft
     @test Array(sortperm(x)) == p_graft

@@ -210,6 +210,13 @@ def test_unaligned_view(b):
     np.testing.assert_array_equal(b.Array(b.accumulate(b.add, v)), oracle.accumulate("add", base[1:]))
     M = rand("int32", (4099, 5))                                # odd segment length: segments unaligned
     check_scan(b, "add", M, dims=1)
+    # widening scans: the input chunk is narrower than 16 bytes, so an 8-byte-aligned Int32 view or 8-byte-multiple
+    # segments pass the chunk test but must not reach the bulk-load (16-byte) kernels
+    out = b.CuArray.undef(b.dtypes.I64, (base.size - 2,))
+    v8 = b.CuArray(d.buf[8:], (base.size - 2,), d.eltype)
+    np.testing.assert_array_equal(b.Array(b.cumsum_(out, v8)), np.cumsum(base[2:].astype(np.int64)))
+    M2 = rand("int32", (70_002, 3))                             # 280008-byte segments: 8- but not 16-byte multiples
+    check_scan(b, "add", M2, dims=1, out_name="int64")
 
 
 @pytest.mark.parametrize("n", [0, 1, 5, 4095, 4096, 4097, 100_003, (1 << 22) + 11])
