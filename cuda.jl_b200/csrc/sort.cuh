@@ -170,6 +170,8 @@ struct OnesweepParams {
     int32_t gen_payload;              // first sortperm pass: payload = element index
     int32_t index_dtype;              // last sortperm pass: store index_base + payload as this dtype; -1: raw payload
     int64_t index_base;               // 1 for per-segment 1-based indices (+ segment offset when linear)
+    int32_t unstable_ok;              // keys-only FIRST pass: equal keys are indistinguishable and no earlier pass has
+                                      // established an order, so ranks inside a digit may come from shared-memory atomics
 };
 
 template <class LookT> struct LookBits;
@@ -200,7 +202,9 @@ template <class K> __device__ __forceinline__ unsigned int digit_of(K key, int s
 template <class V> struct PayTraits { static constexpr bool HAS = true; using type = V; };
 template <> struct PayTraits<NoPayload> { static constexpr bool HAS = false; using type = uint32_t; };
 
-template <class K, class V, class LookT, int ITEMS>
+// ARANK (keys-only FIRST pass, p.unstable_ok): ranks inside a digit come from shared-memory atomics.  A separate
+// instantiation: with both ranking loops in one kernel it needs 76 registers instead of 63 (3 CTAs per SM, -9 %).
+template <class K, class V, class LookT, int ITEMS, bool ARANK = false>
 __global__ void __launch_bounds__(RX_THREADS) radix_onesweep_kernel(OnesweepParams p) {
     using LB = LookBits<LookT>;
     constexpr bool HAS_V = PayTraits<V>::HAS;
@@ -289,6 +293,27 @@ __global__ void __launch_bounds__(RX_THREADS) radix_onesweep_kernel(OnesweepPara
     // ~140 Gkeys/s (ncu: sm__inst_executed_pipe_adu 78%); VOTE issues at 2 per cycle per SM.
     unsigned short ranks[ITEMS];
     const unsigned int lt_mask = (1u << lane) - 1u;
+    if constexpr (ARANK) {
+        // one ATOMS per key (LSU pipe) instead of ~37 ALU/ADU instructions: the returned old count is a unique rank
+        // among this warp's keys of the digit, and the counter ends up as the warp's digit count like below
+        if (full) {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i)
+                ranks[i] = (unsigned short)atomicAdd(whist + digit_of<K>(keys[i], p.shift), 1u);
+        } else {
+            // ragged tile: the padding (all in digit 255, highest element indices) must rank after every real key;
+            // per item the real lanes' atomics are issued before the padding lanes' (same warp: program order)
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const bool real = idx0 + i * 32 < valid;
+                unsigned int r = 0;
+                if (real) r = atomicAdd(whist + digit_of<K>(keys[i], p.shift), 1u);
+                __syncwarp();
+                if (!real) r = atomicAdd(whist + RX_RADIX - 1, 1u);
+                ranks[i] = (unsigned short)r;
+            }
+        }
+    } else
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         const unsigned int digit = digit_of<K>(keys[i], p.shift);

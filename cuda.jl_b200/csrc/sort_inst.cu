@@ -97,11 +97,24 @@ template <class V, class LookT> static int32_t launch_pass(const OnesweepParams 
     static const bool use_pipe = getenv("B200_SORT_PIPE") != nullptr;   // persistent variant: measured slower (fewer warps per SM)
     if (use_pipe && tiles >= 2 && (reinterpret_cast<uintptr_t>(p.keys_in) % 16) == 0 && pipe_smem<V>() <= 200 * 1024)
         return launch_pipe<V, LookT>(p, tiles, st);
-    auto kern = radix_onesweep_kernel<K, V, LookT, ItemsFor<V>::value>;
     const size_t smem = onesweep_smem<V>();
-    static thread_local bool attr_set[64];
     int dev = 0;
     B200_CUDA_TRY(cudaGetDevice(&dev));
+    if constexpr (!PayTraits<V>::HAS) {
+        if (p.unstable_ok) {
+            auto akern = radix_onesweep_kernel<K, V, LookT, ItemsFor<V>::value, true>;
+            static thread_local bool aattr_set[64];
+            if (dev >= 0 && dev < 64 && !aattr_set[dev]) {
+                B200_CUDA_TRY(cudaFuncSetAttribute(akern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                aattr_set[dev] = true;
+            }
+            akern<<<(unsigned int)tiles, RX_THREADS, smem, st>>>(p);
+            B200_CHECK_LAUNCH();
+            return B200_OK;
+        }
+    }
+    auto kern = radix_onesweep_kernel<K, V, LookT, ItemsFor<V>::value>;
+    static thread_local bool attr_set[64];
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
         B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[dev] = true;
@@ -181,6 +194,8 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
         p.ticket = ticket;
         p.xf = c.xf;
         p.encode_in = pass == 0;
+        static const bool no_atomic_rank = getenv("B200_SORT_STABLE_FIRST") != nullptr;   // A/B switch
+        p.unstable_ok = pass == 0 && c.mode == SORT_KEYS && !no_atomic_rank;
         p.decode_out = (pass == P - 1) && c.mode != SORT_PERM;
         p.store_keys = !(pass == P - 1 && c.mode == SORT_PERM);
         p.gen_payload = (pass == 0 && c.mode == SORT_PERM);
