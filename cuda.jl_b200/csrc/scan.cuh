@@ -67,6 +67,15 @@ __device__ unsigned long long g_scan_stats[16];
 #define SC_STAT_ADD(i, v)
 #endif
 
+// Segment of global tile index g.  Persistent kernels evaluate this on their critical path (the control warp of
+// scan_chain2_kernel once per ticket; measured: a 64-bit division there cost 7 % of the whole cumsum), so the common
+// cases avoid the ~100-instruction 64-bit divide: one segment -> 0, indices below 2^32 -> 32-bit divide.
+__device__ __forceinline__ int64_t seg_of_tile(int64_t g, const ScanParams &p) {
+    if (p.post == 1) return 0;
+    if (((uint64_t)g | (uint64_t)p.tiles_per_seg) <= 0xFFFFFFFFull) return (int64_t)((uint32_t)g / (uint32_t)p.tiles_per_seg);
+    return g / p.tiles_per_seg;
+}
+
 template <class A> struct StatusWords { static constexpr int NW = sizeof(A) > 4 ? 2 : 1; };
 
 template <class A> __device__ __forceinline__ void publish(uint64_t *slot, uint32_t flag, A value) {
@@ -574,7 +583,7 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
         s_tile[stage] = g;
         s_use[stage] += 1;
         if (g < total) {
-            const int64_t seg = g / p.tiles_per_seg, t = g - seg * p.tiles_per_seg;
+            const int64_t seg = seg_of_tile(g, p), t = g - seg * p.tiles_per_seg;
             if (p.n - t * TILE >= TILE) {
                 mbar_expect_tx(&s_full[stage], (uint32_t)STAGE_BYTES);
                 tma_load_1d(s_dyn + stage * STAGE_BYTES, static_cast<const Tin *>(p.in) + seg * p.n + t * TILE,
@@ -591,7 +600,7 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
     // warp-exclusive prefixes and PUBLISHES the tile aggregate — one tile ahead of its turn.
     auto pass1 = [&](int stage, A (&cpre)[K]) {
         const long long g = s_tile[stage];
-        const int64_t seg = g / p.tiles_per_seg, t = g - seg * p.tiles_per_seg;
+        const int64_t seg = seg_of_tile(g, p), t = g - seg * p.tiles_per_seg;
         int64_t valid = p.n - t * TILE;
         const bool full = valid >= TILE;
         if (valid > TILE) valid = TILE;
@@ -647,7 +656,7 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
     // warp 0 only, after a __syncthreads that follows pass1(stage); returns the tile aggregate
     auto finish_pass1 = [&](int stage, int parity) -> A {
         const long long g = s_tile[stage];
-        const int64_t seg = g / p.tiles_per_seg, t = g - seg * p.tiles_per_seg;
+        const int64_t seg = seg_of_tile(g, p), t = g - seg * p.tiles_per_seg;
         A wincl = lane < NWARPS ? s_wtot[lane] : Op::identity();
 #pragma unroll
         for (int d = 1; d < NWARPS; d <<= 1) {
@@ -687,7 +696,7 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
     int pf_base = 0;                        // 0: segment seed (first tile), 1: identity, 2: this CTA's previous inclusive
     A incl_own = Op::identity();            // inclusive prefix through this CTA's previous tile
     auto chain_issue = [&](long long g, long long g_prev, bool have_prev) {
-        const int64_t seg = g / p.tiles_per_seg, seg_start = seg * p.tiles_per_seg;
+        const int64_t seg = seg_of_tile(g, p), seg_start = seg * p.tiles_per_seg;
         if (g == seg_start) { pf_base = 0; pf_lo = 0; pf_hi = -1; }
         else if (have_prev && g_prev >= seg_start) { pf_base = 2; pf_lo = g_prev + 1; pf_hi = g - 1; }
         else { pf_base = 1; pf_lo = seg_start; pf_hi = g - 1; }
@@ -783,7 +792,7 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
         SC_STAT_T(t_rdy);
         __syncthreads();                                   // (A) warp totals of the next tile visible
         SC_STAT_T(t_a);
-        const int64_t seg = g / p.tiles_per_seg, t = g - seg * p.tiles_per_seg;
+        const int64_t seg = seg_of_tile(g, p), t = g - seg * p.tiles_per_seg;
         bool need_b = !CHAIN;
         if constexpr (CHAIN) need_b = s_chain_ready == 0;  // CTA-uniform
         if (warp == 0) {
@@ -920,7 +929,7 @@ __global__ void __launch_bounds__(NT + 32) scan_chain2_kernel(ScanParams p) {
         s_use[stage] += 1;
         if (g < total) {
             int64_t seg = 0, t = g;                        // one segment: no 64-bit division on the control warp's path
-            if (p.post != 1) { seg = g / p.tiles_per_seg; t = g - seg * p.tiles_per_seg; }
+            if (p.post != 1) { seg = seg_of_tile(g, p); t = g - seg * p.tiles_per_seg; }
             s_seg[stage] = seg; s_tt[stage] = t;
             if (p.n - t * TILE >= TILE) {
                 mbar_expect_tx(&s_full[stage], (uint32_t)STAGE_BYTES);
@@ -1780,6 +1789,9 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
 #ifndef B200_SCAN_CHAIN_CTAS
 #define B200_SCAN_CHAIN_CTAS 2
 #endif
+#ifndef B200_SCAN_CHAIN2_K
+#define B200_SCAN_CHAIN2_K 7
+#endif
         // Variant selection.  Default: scan_chain2_kernel (measured on B200, cumsum 2^30: Float32 6.14 TB/s vs 5.28 with
         // the look-back kernel, Int64 4.87 vs 4.82).  B200_SCAN_CHAIN=0 selects the look-back kernel.  The other experiments (single-ahead
         // chain, bulk-store ring, look-back in its own warp) are only compiled with -DB200_SCAN_EXPERIMENTS
@@ -1849,11 +1861,16 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
         };
         using std::integral_constant;
         int32_t rc;
-        static const bool use_chain2 = chain_env ? chain_env[0] == '2' : true;
+        // Several segments: a segment's last tile is usually ragged and ragged tiles take the slow (LDG) path of pass 1, so
+        // pick the tiling that wastes less of its last tile (16384 x 16384 Float32 along dims=1: the look-back kernel's
+        // 16384-element tile fits exactly, chain2's 13440 would leave every second tile ragged).
+        constexpr int64_t kTileChain2 = (int64_t)480 * S::EPC * B200_SCAN_CHAIN2_K;
+        constexpr int64_t kTileLook = (int64_t)(kWide ? B200_SCAN_NT_WIDE : B200_SCAN_NT_NARROW) * S::EPC * (kWide ? S::K : B200_SCAN_K_NARROW);
+        const int64_t pad2 = cdiv(n, kTileChain2) * kTileChain2 - n, pad1 = cdiv(n, kTileLook) * kTileLook - n;
+        const bool chain2_fits = post == 1 || pad2 <= pad1 || pad2 * 8 <= n;      // at most 12.5 % of a segment in a ragged tile
+        static const int chain_force = chain_env ? (chain_env[0] == '2' ? 2 : 0) : -1;
+        const bool use_chain2 = chain_force >= 0 ? chain_force == 2 : chain2_fits;
         if (use_chain2) {
-#ifndef B200_SCAN_CHAIN2_K
-#define B200_SCAN_CHAIN2_K 7
-#endif
             constexpr int kThreads = 480, kK = B200_SCAN_CHAIN2_K;   // 15 compute warps + 1 control warp = 512 threads (128 registers each)
             constexpr int64_t kTile = (int64_t)kThreads * S::EPC * kK;
             constexpr size_t smem = (size_t)kTile * sizeof(Tin) * 4;

@@ -204,8 +204,13 @@ template <> struct PayTraits<NoPayload> { static constexpr bool HAS = false; usi
 
 // ARANK (keys-only FIRST pass, p.unstable_ok): ranks inside a digit come from shared-memory atomics.  A separate
 // instantiation: with both ranking loops in one kernel it needs 76 registers instead of 63 (3 CTAs per SM, -9 %).
+// minimum CTAs per SM requested for the atomic-ranked instantiation (0 = compiler default = 64 registers, 4 CTAs).
+// NB: an explicit 1 lets ptxas use 115 registers for the ballot-ranked kernel (measured: 16.4 -> 20.2 ms), hence 0.
+#ifndef B200_RX_ARANK_CTAS
+#define B200_RX_ARANK_CTAS 0
+#endif
 template <class K, class V, class LookT, int ITEMS, bool ARANK = false>
-__global__ void __launch_bounds__(RX_THREADS) radix_onesweep_kernel(OnesweepParams p) {
+__global__ void __launch_bounds__(RX_THREADS, (ARANK ? B200_RX_ARANK_CTAS : 0)) radix_onesweep_kernel(OnesweepParams p) {
     using LB = LookBits<LookT>;
     constexpr bool HAS_V = PayTraits<V>::HAS;
     using VT = typename PayTraits<V>::type;

@@ -1,7 +1,4 @@
 cd /root/repo
-run() { name=$1; shift
-  env "$@" timeout 300 python tools/scan_chain_probe.py $MODES > gpurun_out/scan_v_$name.log 2>&1; echo "rc $name $?"
-  sed -i "s/^\[/[$name /" gpurun_out/scan_v_$name.log; }
-MODES="check time" run at2 B200_SCAN_CHAIN_AT=2
-MODES="time" run at1 B200_SCAN_CHAIN_AT=1
-grep -h "CHECK\|cumsum\|MISMATCH\|BAD\|Error" gpurun_out/scan_v_at2.log gpurun_out/scan_v_at1.log
+timeout 900 python -m pytest tests/test_scan_gpu.py tests/test_fullsize_gpu.py -x -q -m gpu > gpurun_out/scan_tests.log 2>&1; echo "rc tests $?"; tail -2 gpurun_out/scan_tests.log
+timeout 300 python tools/microbench.py scan_dims scan > gpurun_out/microbench_scan_c.log 2>&1; echo "rc micro $?"; cat gpurun_out/microbench_scan_c.log
+B200_SCAN_CHAIN=2 timeout 300 python tools/microbench.py scan_dims > gpurun_out/microbench_scan_c2.log 2>&1; echo "forced chain2:"; cat gpurun_out/microbench_scan_c2.log

@@ -1,5 +1,5 @@
 cd /root/repo
-timeout 300 python tools/sort_probe.py 30 2>&1 | sed "s/^/[atomic-first] /"
-B200_SORT_STABLE_FIRST=1 timeout 300 python tools/sort_probe.py 30 2>&1 | sed "s/^/[stable-first] /"
-timeout 300 python tools/sort_probe.py 26 2>&1 | sed "s/^/[atomic-first] /"
-timeout 900 python -m pytest tests/test_sort_gpu.py -x -q -m gpu 2>&1 | tail -3
+for v in "" _v5; do
+  B200ARRAYS_LIB=$PWD/cuda.jl_b200/libb200arrays$v.so timeout 300 python tools/sort_probe.py 30 2>&1 | sed "s/^/[lib$v] /"
+done
+timeout 300 python tools/microbench.py scan_dims 2>&1 | head -4
