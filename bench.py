@@ -143,7 +143,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 # ============================================================================ product arm
@@ -329,7 +329,7 @@ def run_product(args, rank, world, local_rank):
         "cpu_baseline": cpu,
         "extras": extras,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -504,6 +504,9 @@ def run_extras(b, dt, torch, dev, peak):
     return out
 
 
+_REAL_STDOUT = sys.stdout
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -515,6 +518,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # the contract is ONE JSON line on stdout: libraries that write to file descriptor 1 themselves (NCCL prints its
+    # version banner there when NCCL_DEBUG is set) are sent to stderr; the JSON line goes to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
