@@ -14,6 +14,16 @@
 //   strided (pre > 1): one thread per column marching along n (coalesced across
 //           columns).  [SURVEY §8 f2: look-back chains for strided scans are "next".]
 //
+// Kernels (host selection in launch_scan at the end of this file):
+//   scan_chain2_kernel      default for contiguous scans: persistent CTAs, TMA ring, self-chained prefixes,
+//                           control warp; 6.5 TB/s on cumsum 2^30 Float32
+//   scan_pipe_kernel        decoupled look-back in a persistent TMA ring; used when its tile fits the segments
+//                           better (several segments) or with B200_SCAN_CHAIN=0; CHAIN / TSTORE template
+//                           variants and scan_pipe_ws_kernel are measured experiments (-DB200_SCAN_EXPERIMENTS)
+//   scan_contig_kernel      LSU fallback for unaligned inputs; scan_tma_kernel: first TMA cut, kept for reference
+//   scan_warpseg_kernel     many short contiguous segments, one warp each
+//   scan_strided_lb_kernel / scan_fewcols_kernel / scan_strided_kernel   scans along a non-leading dimension
+//
 // Tile status words live in the caller's workspace: {flag:32 | payload:32} packed in
 // one 64-bit word per 32 bits of the accumulator, written/read with relaxed
 // gpu-scope 64-bit accesses (single-copy atomic), so no fences are needed; a
