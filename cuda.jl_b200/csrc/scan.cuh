@@ -1045,22 +1045,42 @@ __global__ void __launch_bounds__(NT + 32) scan_chain2_kernel(ScanParams p) {
     // variant) overlaps pass 2 of g_j and pass 1 of g_{j+2}.  p.chain_at = how many chunks of pass 2 warp 0
     // processes before it issues them: later = more of the neighbours' aggregates already published (an
     // entry that comes back empty costs a full round trip when it is consumed), earlier = longer in flight.
-    A pf_val[LOOK];
-    uint32_t pf_flag[LOOK];
+    // Status words are kept AS LOADED and decoded only when they are folded: issuing the prefetch must not touch the
+    // loaded registers, otherwise the warp waits one L2 round trip per row right there (first cut: flag tests inside
+    // the issue loop, behind per-row branches: ~300 cycles x 6 rows on the control warp's path).  Lanes beyond the
+    // range read the tile's own slot (always a valid address) so that the loads need no branch.
+    uint64_t pf_raw[LOOK][NW];
+    int pf_n = 0;                           // entries of [lo, hi] covered by the prefetch rows
     int64_t pf_lo = 0, pf_hi = -1;          // status range [lo, hi] (global tile indices) still to be folded
     int pf_base = 0;                        // 0: segment seed (first tile), 1: identity, 2: this CTA's previous inclusive
     A incl_own = Op::identity();            // inclusive prefix through this CTA's previous tile
+    auto decode = [&](const uint64_t (&raw)[NW], A &value) -> uint32_t {
+        uint32_t w[NW];
+        uint32_t flag = (uint32_t)(raw[0] >> 32);
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+            if ((uint32_t)(raw[q] >> 32) != flag) flag = SC_INVALID;
+            w[q] = (uint32_t)raw[q];
+        }
+        memcpy(&value, w, sizeof(A));
+        return flag;
+    };
     auto chain_issue = [&](long long g, long long t_in_seg, long long g_prev, bool have_prev) {
         const int64_t seg_start = g - t_in_seg;
         if (g == seg_start) { pf_base = 0; pf_lo = 0; pf_hi = -1; }
         else if (have_prev && g_prev >= seg_start) { pf_base = 2; pf_lo = g_prev + 1; pf_hi = g - 1; }
         else { pf_base = 1; pf_lo = seg_start; pf_hi = g - 1; }
+        const int64_t span = pf_hi - pf_lo + 1;
+        pf_n = (int)(span < 0 ? 0 : span > LOOK * 32 ? LOOK * 32 : span);
 #pragma unroll
         for (int r = 0; r < LOOK; ++r) {
-            const int64_t idx = pf_hi - (r * 32 + lane);
-            pf_flag[r] = SC_INVALID;
-            pf_val[r] = Op::identity();
-            if (idx >= pf_lo) pf_flag[r] = peek_slot<A>(p.status + idx * NW, pf_val[r]);
+            const int e = r * 32 + lane;
+            const uint64_t *slot = p.status + (e < pf_n ? pf_hi - e : (int64_t)g) * NW;
+            if constexpr (NW == 2) {
+                asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(pf_raw[r][0]), "=l"(pf_raw[r][NW - 1]) : "l"(slot) : "memory");
+            } else {
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(pf_raw[r][0]) : "l"(slot) : "memory");
+            }
         }
     };
     // true when every prefetched status word is valid and the gap fits the prefetch (warp-uniform)
@@ -1068,8 +1088,8 @@ __global__ void __launch_bounds__(NT + 32) scan_chain2_kernel(ScanParams p) {
         bool ok = pf_hi - pf_lo < (int64_t)LOOK * 32;
 #pragma unroll
         for (int r = 0; r < LOOK; ++r) {
-            const int64_t idx = pf_hi - (r * 32 + lane);
-            ok = ok && (idx < pf_lo || pf_flag[r] != SC_INVALID);
+            A v;
+            if (r * 32 + lane < pf_n) ok = ok && decode(pf_raw[r], v) != SC_INVALID;
         }
         return __all_sync(0xffffffffu, ok);
     };
@@ -1077,10 +1097,12 @@ __global__ void __launch_bounds__(NT + 32) scan_chain2_kernel(ScanParams p) {
         A val = Op::identity();
 #pragma unroll
         for (int r = 0; r < LOOK; ++r) {
-            const int64_t idx = pf_hi - (r * 32 + lane);
-            if (idx >= pf_lo) {
-                while (pf_flag[r] == SC_INVALID) pf_flag[r] = peek_slot<A>(p.status + idx * NW, pf_val[r]);
-                val = Op::apply(pf_val[r], val);
+            const int e = r * 32 + lane;
+            if (e < pf_n) {
+                A v;
+                uint32_t flag = decode(pf_raw[r], v);
+                while (flag == SC_INVALID) flag = peek_slot<A>(p.status + (pf_hi - e) * NW, v);
+                val = Op::apply(v, val);
             }
         }
         for (int64_t idx = pf_hi - (LOOK * 32 + lane); idx >= pf_lo; idx -= 32) {   // gap wider than the prefetch
@@ -1884,8 +1906,9 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
             constexpr int kThreads = 480, kK = B200_SCAN_CHAIN2_K;   // 15 compute warps + 1 control warp = 512 threads (128 registers each)
             constexpr int64_t kTile = (int64_t)kThreads * S::EPC * kK;
             constexpr size_t smem = (size_t)kTile * sizeof(Tin) * 4;
-            constexpr int kFit = (200 * 1024) / (int)smem > 0 ? (200 * 1024) / (int)smem : 1;
-            constexpr int kCtas = kFit < 2 ? kFit : 2;
+            // one CTA per SM for every type pair: the tile is sized by the OUTPUT bytes a CTA stores per iteration, and a
+            // second CTA would double the status words the control warp holds in registers (12 rows: spills)
+            constexpr int kCtas = 1;
             constexpr int kRows = (148 * kCtas * 5 / 4 + 31) / 32;
             auto kern = scan_chain2_kernel<Tin, Tout, Op, S::EPC, kK, kThreads, kRows>;
             static thread_local int attr2_dev_mask[64];
