@@ -16,7 +16,7 @@
 //
 // Kernels (host selection in launch_scan at the end of this file):
 //   scan_chain2_kernel      default for contiguous scans: persistent CTAs, TMA ring, self-chained prefixes,
-//                           control warp; 6.5 TB/s on cumsum 2^30 Float32
+//                           control warp; 6.6 TB/s on cumsum 2^30 Float32
 //   scan_pipe_kernel        decoupled look-back in a persistent TMA ring; used when its tile fits the segments
 //                           better (several segments) or with B200_SCAN_CHAIN=0; CHAIN / TSTORE template
 //                           variants and scan_pipe_ws_kernel are measured experiments (-DB200_SCAN_EXPERIMENTS)
@@ -1824,8 +1824,8 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
 #ifndef B200_SCAN_CHAIN2_K
 #define B200_SCAN_CHAIN2_K 7
 #endif
-        // Variant selection.  Default: scan_chain2_kernel (measured on B200, cumsum 2^30: Float32 6.14 TB/s vs 5.28 with
-        // the look-back kernel, Int64 4.87 vs 4.82).  B200_SCAN_CHAIN=0 selects the look-back kernel.  The other experiments (single-ahead
+        // Variant selection.  Default: scan_chain2_kernel (measured on B200, cumsum 2^30: Float32 6.58 TB/s vs 5.28 with
+        // the look-back kernel, Int64 5.65 vs 4.82).  B200_SCAN_CHAIN=0 selects the look-back kernel.  The other experiments (single-ahead
         // chain, bulk-store ring, look-back in its own warp) are only compiled with -DB200_SCAN_EXPERIMENTS
         // (B200_SCAN_CHAIN=1, B200_SCAN_TSTORE=1, B200_SCAN_WS=1); measurements in DESIGN.md section 4.
         static const char *chain_env = getenv("B200_SCAN_CHAIN");
