@@ -15,6 +15,9 @@ region).  `extras` carries the other north-star configurations measured in the s
 N > 1 (torchrun): every rank owns one 16384 x 16384 column block of a 16384 x (16384*N) matrix
 (weak scaling).  dims=1 sums need no exchange; dims=2 sums allreduce the 16384-vector of row
 sums; maximum / count allreduce a scalar (NCCL).  value = bytes of all ranks / max-over-ranks time.
+After the headline measurement the same launch times the sharded configs[2..4] paths (`extras.sharded`: cumsum and
+sort! / sortperm of 2^30 elements in total, mapreduce(abs2, +) / extrema over 2^30 BFloat16 per GPU); they are guarded
+by a watchdog and an exception handler so that they can never cost the JSON line (`--no-extras` skips them).
 
 `--impl reference` times the reference's CPU path (Base Julia semantics restated in
 oracle/oracle_cpu.c — the reference itself is Julia and no julia binary exists in this image)
@@ -289,11 +292,12 @@ def run_product(args, rank, world, local_rank):
     extras = {}
     if not args.no_extras and world == 1:
         extras = run_extras(b, dt, torch, dev, peak)
+    run_sharded = not args.no_extras and world > 1
 
-    if rank != 0:
+    if rank != 0 and not run_sharded:
         return
     # ---- cpu baseline (bounded sample of the same workload, host cores of this box)
-    cpu = cpu_baseline_sample()
+    cpu = cpu_baseline_sample() if rank == 0 else None
     dom = max(per_op.items(), key=lambda kv: kv[1]["ms"]) if per_op else (None, None)
     traffic = None
     try:
@@ -329,6 +333,10 @@ def run_product(args, rank, world, local_rank):
         "cpu_baseline": cpu,
         "extras": extras,
     }
+    if run_sharded:
+        # SURVEY section 8e paths (sharded scan / sample sort / 2^30-per-GPU BF16 reductions) in the same launch, so that the
+        # driver's 2/4/8-GPU runs carry them.  They come AFTER the headline measurement and can never cost the JSON line.
+        finish_with_sharded_extras(line, rank, lambda: run_extras_sharded(b, dt, torch, dist, dev, rank, world, peak))
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -431,6 +439,92 @@ def run_comparators(b, dt, torch, dev):
     torch.cuda.empty_cache()
     out["_labels"] = {"reference_algorithm": "restatement of CUDA.jl's algorithm + launch structure in CUDA C++ (nvcc, not Julia-JIT): "
                                             "bench/baselines/ref_algos.cu", "torch": "torch 2.11 (CUB) library comparator"}
+    return out
+
+
+def finish_with_sharded_extras(line, rank, fn, timeout=None):
+    """Runs fn() (the sharded extras, collective: every rank calls it), stores its result in line["extras"], prints the
+    JSON line on rank 0 and ends the process with status 0 — whatever fn does: an exception is recorded in the line, and a
+    watchdog prints the line without the extras if fn has not returned after `timeout` seconds (a rank stuck in a
+    collective must not hold the headline numbers back).  Never returns."""
+    timeout = float(os.environ.get("B200_BENCH_SHARDED_TIMEOUT", "150")) if timeout is None else timeout
+    lock = threading.Lock()
+    state = {"printed": False}
+
+    def emit(extras):
+        with lock:
+            if state["printed"]:
+                return
+            state["printed"] = True
+            if rank == 0:
+                line["extras"] = {"sharded": extras}
+                print(json.dumps(line), file=_REAL_STDOUT, flush=True)
+        os._exit(0)       # not sys.exit: a failed extra may have left a collective half done
+
+    dog = threading.Timer(timeout, emit, args=("timeout: the headline numbers above are complete",))
+    dog.daemon = True
+    dog.start()
+    try:
+        res = fn()
+    except BaseException as e:  # reported, never fatal for the headline
+        res = f"failed: {type(e).__name__}: {e}"
+    emit(res)
+
+
+def run_extras_sharded(b, dt, torch, dist, dev, rank, world, peak):
+    """configs[2..4] on `world` GPUs (one process per GPU, NCCL): cumsum and sort! / sortperm of 2^30 elements in total
+    (strong scaling), mapreduce(abs2, +) / extrema over 2^30 BFloat16 per GPU (weak scaling, 2^33 on 8 GPUs).  Device
+    time between CUDA events on every rank, max over ranks."""
+    from b200arrays import multigpu as mg
+    out = {}
+
+    def timed(fn, reps=3):
+        fn()
+        best = None
+        for _ in range(reps):
+            dist.barrier(); torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record(); e.synchronize()
+            t = torch.tensor([s.elapsed_time(e)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = float(t.item()) if best is None else min(best, float(t.item()))
+        return best
+
+    def item(name, fn, fmt, reps=3):
+        # every rank runs the same code on the same shapes, so a failure is the same on all of them: record it and go on
+        try:
+            out[name] = fmt(timed(fn, reps))
+        except Exception as e:
+            out[name] = {"failed": f"{type(e).__name__}: {e}"}
+
+    total = 1 << 30
+    n = total // world
+    g = torch.Generator(device=dev); g.manual_seed(0xB200 + 100 + rank)
+    V = torch.rand(n, device=dev, generator=g, dtype=torch.float32)
+    cV = b.CuArray.from_torch(V)
+    item("cumsum 2^30 Float32 total", lambda: mg.dist_accumulate(b.add, cV),
+         lambda ms: {"ms": ms, "GB/s": 8 * total / ms / 1e6, "per_gpu_frac_of_measured_peak": 8 * total / ms / 1e6 / world / peak,
+                     "note": "shard-local reduce + all-gather of the shard totals + scan with the carry: 3N traffic for 2N algorithmic bytes"})
+    item("sort! 2^30 Float32 total", lambda: mg.dist_sort(cV), lambda ms: {"ms": ms, "Gkeys/s": total / ms / 1e6})
+    item("sortperm 2^30 Float32 total", lambda: mg.dist_sortperm(cV), lambda ms: {"ms": ms, "Gkeys/s": total / ms / 1e6}, reps=2)
+    del V, cV
+    torch.cuda.empty_cache()
+    I = torch.randint(-2**20, 2**20, (n,), device=dev, generator=g, dtype=torch.int64)
+    cI = b.CuArray.from_torch(I)
+    item("cumsum 2^30 Int64 total", lambda: mg.dist_accumulate(b.add, cI),
+         lambda ms: {"ms": ms, "GB/s": 16 * total / ms / 1e6, "per_gpu_frac_of_measured_peak": 16 * total / ms / 1e6 / world / peak})
+    del I, cI
+    U = torch.randint(-2**31, 2**31 - 1, (n,), device=dev, generator=g, dtype=torch.int32)
+    cU = b.CuArray.from_torch(U, (n,), dt.U32)
+    item("sort! 2^30 UInt32 total", lambda: mg.dist_sort(cU), lambda ms: {"ms": ms, "Gkeys/s": total / ms / 1e6})
+    del U, cU
+    torch.cuda.empty_cache()
+    H = torch.randn(1 << 30, device=dev, generator=g, dtype=torch.float32).to(torch.bfloat16)
+    cH = b.CuArray.from_torch(H)
+    item(f"mapreduce(abs2,+) 2^30 BFloat16 per GPU x {world}", lambda: mg.dist_mapreduce(b.abs2, b.add, cH),
+         lambda ms: {"ms": ms, "GB/s": 2.0 * (1 << 30) * world / ms / 1e6, "per_gpu_frac_of_measured_peak": 2.0 * (1 << 30) / ms / 1e6 / peak})
+    item(f"extrema 2^30 BFloat16 per GPU x {world}", lambda: mg.dist_extrema(cH),
+         lambda ms: {"ms": ms, "GB/s": 2 * 2.0 * (1 << 30) * world / ms / 1e6, "note": "two passes (min, max), one allreduce each"})
     return out
 
 

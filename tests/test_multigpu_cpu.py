@@ -189,3 +189,38 @@ def test_sample_sort(world, case):
         np.testing.assert_array_equal(perm, oracle.sortperm(full, rev=rev))       # stable across ranks
     np.testing.assert_array_equal(np.concatenate([r["perm_u"] for r in res]), oracle.sortperm(u))
     assert all(r["empty"].size == 0 for r in res)
+
+
+# ---- bench.py: the sharded extras can never cost the headline JSON line ----------------------------
+@pytest.mark.parametrize("mode", ["ok", "raise", "hang"])
+def test_bench_sharded_extras_guard(mode):
+    """bench.py --gpus N runs the sharded configs AFTER the headline measurement; whatever they do (return, raise,
+    hang in a collective) rank 0 must still print exactly one JSON line and exit 0."""
+    import json
+    import subprocess
+    import sys
+    code = f"""
+import sys, time
+sys.path.insert(0, {ROOT!r})
+import bench
+line = {{"metric": "m", "value": 1.0, "extras": {{}}}}
+def fn():
+    if {mode!r} == "raise": raise RuntimeError("boom")
+    if {mode!r} == "hang": time.sleep(60)
+    return {{"cumsum": {{"ms": 1.0}}}}
+bench.finish_with_sharded_extras(line, 0, fn, timeout=1.0)
+print("not reached")
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["value"] == 1.0
+    sh = d["extras"]["sharded"]
+    if mode == "ok":
+        assert sh == {"cumsum": {"ms": 1.0}}
+    elif mode == "raise":
+        assert sh.startswith("failed: RuntimeError: boom")
+    else:
+        assert sh.startswith("timeout")
