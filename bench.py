@@ -161,9 +161,13 @@ def run_product(args, rank, world, local_rank):
     lib = b._lib.load()            # fails loudly when the extension is missing
     assert lib.b200_check_device() == 0, "not an sm_100 device"
     dist = None
-    if world > 1:
+    # B200_BENCH_FORCE_SHARDED=1: run the N > 1 code path (process group, sharded extras) on ONE GPU — a smoke test
+    force_sharded = world == 1 and os.environ.get("B200_BENCH_FORCE_SHARDED") == "1"
+    if world > 1 or force_sharded:
         import torch.distributed as dist_
         dist = dist_
+        if force_sharded:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29577")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     peak, peak_src = measured_peak()
@@ -290,9 +294,9 @@ def run_product(args, rank, world, local_rank):
     torch.cuda.empty_cache()
 
     extras = {}
-    if not args.no_extras and world == 1:
+    if not args.no_extras and world == 1 and not force_sharded:
         extras = run_extras(b, dt, torch, dev, peak)
-    run_sharded = not args.no_extras and world > 1
+    run_sharded = not args.no_extras and (world > 1 or force_sharded)
 
     if rank != 0 and not run_sharded:
         return
@@ -497,7 +501,8 @@ def run_extras_sharded(b, dt, torch, dist, dev, rank, world, peak):
         except Exception as e:
             out[name] = {"failed": f"{type(e).__name__}: {e}"}
 
-    total = 1 << 30
+    lg = int(os.environ.get("B200_BENCH_SHARDED_LOG2N", "30"))      # smoke tests use a smaller size; the names below say 2^30
+    total = 1 << lg
     n = total // world
     g = torch.Generator(device=dev); g.manual_seed(0xB200 + 100 + rank)
     V = torch.rand(n, device=dev, generator=g, dtype=torch.float32)
@@ -519,12 +524,12 @@ def run_extras_sharded(b, dt, torch, dist, dev, rank, world, peak):
     item("sort! 2^30 UInt32 total", lambda: mg.dist_sort(cU), lambda ms: {"ms": ms, "Gkeys/s": total / ms / 1e6})
     del U, cU
     torch.cuda.empty_cache()
-    H = torch.randn(1 << 30, device=dev, generator=g, dtype=torch.float32).to(torch.bfloat16)
+    H = torch.randn(total, device=dev, generator=g, dtype=torch.float32).to(torch.bfloat16)
     cH = b.CuArray.from_torch(H)
     item(f"mapreduce(abs2,+) 2^30 BFloat16 per GPU x {world}", lambda: mg.dist_mapreduce(b.abs2, b.add, cH),
-         lambda ms: {"ms": ms, "GB/s": 2.0 * (1 << 30) * world / ms / 1e6, "per_gpu_frac_of_measured_peak": 2.0 * (1 << 30) / ms / 1e6 / peak})
+         lambda ms: {"ms": ms, "GB/s": 2.0 * total * world / ms / 1e6, "per_gpu_frac_of_measured_peak": 2.0 * total / ms / 1e6 / peak})
     item(f"extrema 2^30 BFloat16 per GPU x {world}", lambda: mg.dist_extrema(cH),
-         lambda ms: {"ms": ms, "GB/s": 2 * 2.0 * (1 << 30) * world / ms / 1e6, "note": "two passes (min, max), one allreduce each"})
+         lambda ms: {"ms": ms, "GB/s": 2 * 2.0 * total * world / ms / 1e6, "note": "two passes (min, max), one allreduce each"})
     return out
 
 
