@@ -209,18 +209,23 @@ template <> struct PayTraits<NoPayload> { static constexpr bool HAS = false; usi
 #ifndef B200_RX_ARANK_CTAS
 #define B200_RX_ARANK_CTAS 0
 #endif
-template <class K, class V, class LookT, int ITEMS, bool ARANK = false>
-__global__ void __launch_bounds__(RX_THREADS, (ARANK ? B200_RX_ARANK_CTAS : 0)) radix_onesweep_kernel(OnesweepParams p) {
+// NT = threads per CTA (256, or 512 as an experiment: the per-digit bookkeeping and the look-back are done by 256
+// threads per TILE, so a 512-thread tile halves their cost per key; B200_SORT_NT=512, keys-only, not yet measured).
+template <class K, class V, class LookT, int ITEMS, bool ARANK = false, int NT = RX_THREADS>
+__global__ void __launch_bounds__(NT, (ARANK ? B200_RX_ARANK_CTAS : 0)) radix_onesweep_kernel(OnesweepParams p) {
     using LB = LookBits<LookT>;
     constexpr bool HAS_V = PayTraits<V>::HAS;
     using VT = typename PayTraits<V>::type;
-    constexpr int TILE = RX_THREADS * ITEMS;
+    constexpr int TILE = NT * ITEMS;
     constexpr int WARP_ITEMS = 32 * ITEMS;
+    constexpr int NWARPS = NT / 32;
+    constexpr int DWARPS = RX_RADIX / 32;        // warps whose threads own one digit each
+    static_assert(NT >= RX_RADIX && NT % 32 == 0, "one thread per digit");
 
     extern __shared__ __align__(16) unsigned char s_raw[];
     // layout: [warp hist 8*256 u32][digit offset 256 u32][global base 256 i64][keys TILE][vals TILE]
     unsigned int *s_whist = reinterpret_cast<unsigned int *>(s_raw);
-    unsigned int *s_doff = s_whist + RX_WARPS * RX_RADIX;
+    unsigned int *s_doff = s_whist + NWARPS * RX_RADIX;
     // global index of the tile's first key of each digit, minus its shared-memory position;
     // 32-bit when n < 2^30 (LookT == uint32_t), which saves 64-bit address arithmetic per key
     using BaseT = typename std::conditional<sizeof(LookT) == 4, int, long long>::type;
@@ -229,12 +234,13 @@ __global__ void __launch_bounds__(RX_THREADS, (ARANK ? B200_RX_ARANK_CTAS : 0)) 
     K *s_keys = reinterpret_cast<K *>(s_gbase_raw + RX_RADIX);
     VT *s_vals = reinterpret_cast<VT *>(reinterpret_cast<unsigned char *>(s_keys) + ((TILE * sizeof(K) + 15) / 16) * 16);
     __shared__ unsigned long long s_ticket;
-    __shared__ unsigned int s_wsum[RX_WARPS];
+    __shared__ unsigned int s_wsum[DWARPS];
 #if B200_RX_ATOMOR_MASK
     __shared__ unsigned int s_match[RX_WARPS][RX_RADIX];   // per-warp peer-mask table for the atomic-or matched items
 #endif
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool dthread = NT == RX_RADIX || tid < RX_RADIX;   // this thread owns digit `tid`
     if (tid == 0) s_ticket = atomicAdd(p.ticket, 1ull);
     // zero this warp's digit counters while the ticket is in flight
     unsigned int *whist = s_whist + warp * RX_RADIX;
@@ -282,14 +288,16 @@ __global__ void __launch_bounds__(RX_THREADS, (ARANK ? B200_RX_ARANK_CTAS : 0)) 
     constexpr bool EARLY_COUNTS = HAS_V;
     if constexpr (EARLY_COUNTS) {
         unsigned int *s_bhist = s_doff;                 // reused below as the digit-offset table
-        s_bhist[tid] = 0;
+        if (dthread) s_bhist[tid] = 0;
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) atomicAdd(&s_bhist[digit_of<K>(keys[i], p.shift)], 1u);
         __syncthreads();
-        unsigned int c = s_bhist[tid];
-        if (tid == RX_RADIX - 1) c -= (unsigned int)(TILE - valid);
-        st_relaxed<LookT>(status + t * RX_RADIX + tid, (LookT)((t > 0 ? LB::PARTIAL : LB::INCLUSIVE) | (LookT)c));
+        if (dthread) {
+            unsigned int c = s_bhist[tid];
+            if (tid == RX_RADIX - 1) c -= (unsigned int)(TILE - valid);
+            st_relaxed<LookT>(status + t * RX_RADIX + tid, (LookT)((t > 0 ? LB::PARTIAL : LB::INCLUSIVE) | (LookT)c));
+        }
     }
 
     // ---- rank inside the warp: stable by (item, lane) = element order.
@@ -366,18 +374,22 @@ __global__ void __launch_bounds__(RX_THREADS, (ARANK ? B200_RX_ARANK_CTAS : 0)) 
     __syncthreads();
 
     // ---- per digit (thread d): offsets of each warp inside the digit run, tile count
-    const int d = tid;
+    const int d = dthread ? tid : 0;
     unsigned int tile_count = 0;
+    if (dthread) {
 #pragma unroll
-    for (int w = 0; w < RX_WARPS; ++w) {
-        const unsigned int c = s_whist[w * RX_RADIX + d];
-        s_whist[w * RX_RADIX + d] = tile_count;
-        tile_count += c;
+        for (int w = 0; w < NWARPS; ++w) {
+            const unsigned int c = s_whist[w * RX_RADIX + d];
+            s_whist[w * RX_RADIX + d] = tile_count;
+            tile_count += c;
+        }
     }
     const unsigned int pad = (unsigned int)(TILE - valid);
     const unsigned int real_count = (d == RX_RADIX - 1) ? tile_count - pad : tile_count;
-    if constexpr (!EARLY_COUNTS)   // keys-only: publish here; tile 0 knows its inclusive prefix already
-        st_relaxed<LookT>(status + t * RX_RADIX + d, (LookT)((t > 0 ? LB::PARTIAL : LB::INCLUSIVE) | (LookT)real_count));
+    if constexpr (!EARLY_COUNTS) {  // keys-only: publish here; tile 0 knows its inclusive prefix already
+        if (dthread)
+            st_relaxed<LookT>(status + t * RX_RADIX + d, (LookT)((t > 0 ? LB::PARTIAL : LB::INCLUSIVE) | (LookT)real_count));
+    }
 
     // exclusive scan of tile_count over the 256 digits -> start of each digit run in shared memory
     unsigned int incl = tile_count;
@@ -386,15 +398,17 @@ __global__ void __launch_bounds__(RX_THREADS, (ARANK ? B200_RX_ARANK_CTAS : 0)) 
         const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += up;
     }
-    if (lane == 31) s_wsum[warp] = incl;
+    if (lane == 31 && dthread) s_wsum[warp] = incl;
     __syncthreads();
     unsigned int wbase = 0;
 #pragma unroll
-    for (int w = 0; w < RX_WARPS; ++w) wbase += (w < warp) ? s_wsum[w] : 0u;
+    for (int w = 0; w < DWARPS; ++w) wbase += (w < warp) ? s_wsum[w] : 0u;
     const unsigned int doff = wbase + incl - tile_count;
     // fold the digit run's start into every warp's offset: the scatter then needs one lookup
+    if (dthread) {
 #pragma unroll
-    for (int w = 0; w < RX_WARPS; ++w) s_whist[w * RX_RADIX + d] += doff;
+        for (int w = 0; w < NWARPS; ++w) s_whist[w * RX_RADIX + d] += doff;
+    }
     __syncthreads();
 
     // ---- scatter keys (and payload) into shared memory, sorted by digit
@@ -418,7 +432,7 @@ __global__ void __launch_bounds__(RX_THREADS, (ARANK ? B200_RX_ARANK_CTAS : 0)) 
 
     // ---- decoupled look-back for digit d
     unsigned long long excl = 0;
-    if (t > 0) {
+    if (t > 0 && dthread) {
         int64_t u = t - 1;
         bool done = false;
         while (!done) {
@@ -444,7 +458,7 @@ __global__ void __launch_bounds__(RX_THREADS, (ARANK ? B200_RX_ARANK_CTAS : 0)) 
         }
         st_relaxed<LookT>(status + t * RX_RADIX + d, (LookT)(LB::INCLUSIVE | (LookT)(excl + real_count)));
     }
-    s_gbase[d] = (BaseT)((long long)(p.bins[d] + excl) - (long long)doff);
+    if (dthread) s_gbase[d] = (BaseT)((long long)(p.bins[d] + excl) - (long long)doff);
     __syncthreads();
 
     // ---- write out: consecutive threads -> consecutive addresses inside each digit run.
@@ -456,7 +470,7 @@ __global__ void __launch_bounds__(RX_THREADS, (ARANK ? B200_RX_ARANK_CTAS : 0)) 
         constexpr int kMode = decltype(mode_c)::value;   // 0: keys as is, 1: keys decoded, 2: no keys
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) {
-            const int i = tid + k * RX_THREADS;
+            const int i = tid + k * NT;
             if (kFull || i < valid) {
                 const K key = s_keys[i];
                 const BaseT dst = s_gbase[digit_of<K>(key, p.shift)] + i;

@@ -58,6 +58,18 @@ template <class V, class LookT> static int32_t launch_pipe(const OnesweepParams 
     return B200_OK;
 }
 
+// 512-thread tiles for keys-only sorts of 32-bit keys (experiment, B200_SORT_NT=512; see radix_onesweep_kernel's NT).
+static bool wide_cta() {
+#if B200_KEY_BYTES == 4
+    static const bool on = [] { const char *e = getenv("B200_SORT_NT"); return e && atoi(e) == 512; }();
+    return on;
+#else
+    return false;
+#endif
+}
+constexpr int WIDE_NT = 512;
+constexpr int WIDE_TILE = WIDE_NT * ItemsFor<NoPayload>::value;
+
 // Counter-ranked pass (sort_ctr.cuh) for keys-only sorts of 32-bit keys: 0 = off, 1 = 128 threads x 64 keys,
 // 2 = 64 threads x 128 keys.
 static int ctr_mode() {
@@ -100,6 +112,25 @@ template <class V, class LookT> static int32_t launch_pass(const OnesweepParams 
     const size_t smem = onesweep_smem<V>();
     int dev = 0;
     B200_CUDA_TRY(cudaGetDevice(&dev));
+#if B200_KEY_BYTES == 4
+    if constexpr (!PayTraits<V>::HAS) {
+        if (wide_cta()) {
+            constexpr size_t wsmem = (size_t)(WIDE_NT / 32) * RX_RADIX * 4 + RX_RADIX * 4 + RX_RADIX * 8 + (size_t)WIDE_TILE * sizeof(K);
+            auto k0 = radix_onesweep_kernel<K, V, LookT, ItemsFor<V>::value, false, WIDE_NT>;
+            auto k1 = radix_onesweep_kernel<K, V, LookT, ItemsFor<V>::value, true, WIDE_NT>;
+            static thread_local bool wattr_set[64];
+            if (dev >= 0 && dev < 64 && !wattr_set[dev]) {
+                B200_CUDA_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+                B200_CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+                wattr_set[dev] = true;
+            }
+            if (p.unstable_ok) k1<<<(unsigned int)tiles, WIDE_NT, wsmem, st>>>(p);
+            else k0<<<(unsigned int)tiles, WIDE_NT, wsmem, st>>>(p);
+            B200_CHECK_LAUNCH();
+            return B200_OK;
+        }
+    }
+#endif
     if constexpr (!PayTraits<V>::HAS) {
         if (p.unstable_ok) {
             auto akern = radix_onesweep_kernel<K, V, LookT, ItemsFor<V>::value, true>;
@@ -136,7 +167,8 @@ template <class LookT> static int32_t dispatch_pass(const OnesweepParams &p, int
 int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
     const int64_t n = c.n;
     const int64_t max_tiles = cdiv(n, c.mode == SORT_KEYS ? tile_for<NoPayload>() : tile_for<uint32_t>());
-    const int64_t tiles = (c.mode == SORT_KEYS && ctr_mode() && !c.query) ? cdiv(n, CTR_TILE) : max_tiles;
+    const int64_t tiles = (c.mode == SORT_KEYS && ctr_mode() && !c.query) ? cdiv(n, CTR_TILE)
+                        : (c.mode == SORT_KEYS && wide_cta() && !c.query) ? cdiv(n, WIDE_TILE) : max_tiles;
     // 32-bit status words carry 30-bit counts.  Every prefix that is ever READ belongs to a tile before the last
     // one and is therefore < n, so n == 2^30 still fits (only the last tile's own inclusive value can reach 2^30,
     // and nobody looks back at the last tile).
