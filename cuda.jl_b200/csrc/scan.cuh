@@ -18,8 +18,8 @@
 //   scan_chain2_kernel      default for contiguous scans: persistent CTAs, TMA ring, self-chained prefixes,
 //                           control warp; 6.6 TB/s on cumsum 2^30 Float32
 //   scan_pipe_kernel        decoupled look-back in a persistent TMA ring; used when its tile fits the segments
-//                           better (several segments) or with B200_SCAN_CHAIN=0; CHAIN / TSTORE template
-//                           variants and scan_pipe_ws_kernel are measured experiments (-DB200_SCAN_EXPERIMENTS)
+//                           better (several segments) or with B200_SCAN_CHAIN=0; scan_pipe_ws_kernel (look-back in
+//                           its own warp, B200_SCAN_WS=1) is a measured experiment
 //   scan_contig_kernel      LSU fallback for unaligned inputs; scan_tma_kernel: first TMA cut, kept for reference
 //   scan_warpseg_kernel     many short contiguous segments, one warp each
 //   scan_strided_lb_kernel / scan_fewcols_kernel / scan_strided_kernel   scans along a non-leading dimension
@@ -55,7 +55,7 @@ struct ScanParams {
     int32_t exclusive;
     int32_t has_init;
     uint64_t init_bits;            // the Some(x) value, bit pattern of the accumulator type
-    int32_t chain_at;              // scan_pipe_kernel<CHAIN>: pass-2 chunks done before the status prefetch is issued
+    int32_t chain_at;              // scan_chain2_kernel: 0 = status prefetch before barrier (A), 1 = after the publication
 };
 
 __device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
@@ -559,13 +559,7 @@ __global__ void __launch_bounds__(SC_THREADS) scan_tma_kernel(ScanParams p) {
 //     coalesced 16-byte STGs (the stage is free for the next load right away).
 // Tiles are handed out by an atomic ticket, so a CTA only waits on tiles that some resident
 // CTA already owns.
-// TSTORE (sizeof(Tin) == sizeof(Tout)): pass 2 writes the results back into the stage and one thread
-// hands the whole tile to the TMA unit (cp.async.bulk shared -> global).  With ordinary STGs the SM's
-// LSU queue holds ~64 KB of stores after every pass 2, and the status loads / aggregate publications of
-// warp 0 wait behind them (measured per iteration of ~6500 cycles: ~2600 in the look-back, prefetched
-// status words still not back after ~3400); the bulk store keeps that queue empty.  The stage is refilled
-// one iteration later (ring of S = 4: current, next, loading, draining).
-template <class Tin, class Tout, class Op, int EPC, int K, int S, int NT, int LOOK, bool CHAIN = false, bool TSTORE = false>
+template <class Tin, class Tout, class Op, int EPC, int K, int S, int NT, int LOOK>
 __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
     using A = typename Op::acc_t;
     constexpr int NWARPS = NT / 32;
@@ -691,73 +685,12 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
         return tile_agg;
     };
 
-    // ---- CHAIN mode (warp 0): a CTA's tiles g_0 < g_1 < ... chain through the CTA's OWN previous tile,
-    //   prefix(g_{j+1}) = inclusive(g_j) (+) partial(g_j + 1) (+) ... (+) partial(g_{j+1} - 1),
-    // so nobody ever waits for another tile's INCLUSIVE prefix: only for the aggregates of the tiles between
-    // two of its own tickets (~#CTAs - 1 of them), which their owners publish one iteration before those
-    // tiles' turn.  The status loads are ISSUED right after this CTA published tile g_{j+1}'s aggregate and
-    // CONSUMED an iteration later, so the loaded-L2 round trip (~1.5 us, the critical path of the look-back
-    // variant) overlaps pass 2 of g_j and pass 1 of g_{j+2}.  p.chain_at = how many chunks of pass 2 warp 0
-    // processes before it issues them: later = more of the neighbours' aggregates already published (an
-    // entry that comes back empty costs a full round trip when it is consumed), earlier = longer in flight.
-    A pf_val[LOOK];
-    uint32_t pf_flag[LOOK];
-    int64_t pf_lo = 0, pf_hi = -1;          // status range [lo, hi] (global tile indices) still to be folded
-    int pf_base = 0;                        // 0: segment seed (first tile), 1: identity, 2: this CTA's previous inclusive
-    A incl_own = Op::identity();            // inclusive prefix through this CTA's previous tile
-    auto chain_issue = [&](long long g, long long g_prev, bool have_prev) {
-        const int64_t seg = seg_of_tile(g, p), seg_start = seg * p.tiles_per_seg;
-        if (g == seg_start) { pf_base = 0; pf_lo = 0; pf_hi = -1; }
-        else if (have_prev && g_prev >= seg_start) { pf_base = 2; pf_lo = g_prev + 1; pf_hi = g - 1; }
-        else { pf_base = 1; pf_lo = seg_start; pf_hi = g - 1; }
-#pragma unroll
-        for (int r = 0; r < LOOK; ++r) {
-            const int64_t idx = pf_hi - (r * 32 + lane);
-            pf_flag[r] = SC_INVALID;
-            pf_val[r] = Op::identity();
-            if (idx >= pf_lo) pf_flag[r] = peek_slot<A>(p.status + idx * NW, pf_val[r]);
-        }
-    };
-    // true when every prefetched status word is valid and the gap fits the prefetch (warp-uniform)
-    auto chain_ready = [&]() -> bool {
-        bool ok = pf_hi - pf_lo < (int64_t)LOOK * 32;
-#pragma unroll
-        for (int r = 0; r < LOOK; ++r) {
-            const int64_t idx = pf_hi - (r * 32 + lane);
-            ok = ok && (idx < pf_lo || pf_flag[r] != SC_INVALID);
-        }
-        return __all_sync(0xffffffffu, ok);
-    };
-    auto chain_consume = [&]() -> A {
-        A val = Op::identity();
-#pragma unroll
-        for (int r = 0; r < LOOK; ++r) {
-            const int64_t idx = pf_hi - (r * 32 + lane);
-            if (idx >= pf_lo) {
-                while (pf_flag[r] == SC_INVALID) pf_flag[r] = peek_slot<A>(p.status + idx * NW, pf_val[r]);
-                val = Op::apply(pf_val[r], val);
-            }
-        }
-        for (int64_t idx = pf_hi - (LOOK * 32 + lane); idx >= pf_lo; idx -= 32) {   // gap wider than the prefetch
-            A v;
-            while (peek_slot<A>(p.status + idx * NW, v) == SC_INVALID) {}
-            val = Op::apply(v, val);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) val = Op::apply(val, shfl_xor_any(val, o));
-        const A base = pf_base == 0 ? (p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity())
-                     : pf_base == 1 ? Op::identity() : incl_own;
-        return Op::apply(base, val);
-    };
-    __shared__ int s_chain_ready;
-
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int st = 0; st < S; ++st) { mbar_init(&s_full[st], 1); s_use[st] = 0; }
         fence_proxy_async_smem();
 #pragma unroll
-        for (int st = 0; st < (TSTORE ? S - 1 : S); ++st) fill(st, (long long)atomicAdd(p.ticket, 1ull));
-        if constexpr (TSTORE) s_tile[S - 1] = total;       // filled at the end of iteration 0
+        for (int st = 0; st < S; ++st) fill(st, (long long)atomicAdd(p.ticket, 1ull));
     }
     __syncthreads();
     if (s_tile[0] >= total) return;
@@ -766,10 +699,7 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
     A agg_cur = Op::identity(), agg_nxt = Op::identity();   // meaningful in warp 0
     pass1(0, cpre_cur);
     __syncthreads();
-    if (warp == 0) {
-        agg_cur = finish_pass1(0, 0);
-        if constexpr (CHAIN) chain_issue(s_tile[0], 0, false);
-    }
+    if (warp == 0) agg_cur = finish_pass1(0, 0);
 
     for (int64_t it = 0;; ++it) {
         const int stage = (int)(it % S);
@@ -787,40 +717,16 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
         // look-back re-creates the serial chain: measured 1.7 TB/s instead of 4.4-5.2 TB/s)
         if (have_next) pass1(nxt, cpre_nxt);
         SC_STAT_T(t_p1);
-        if constexpr (CHAIN) {
-            if (warp == 0) {   // status words requested an iteration ago: normally all landed and valid
-                const bool ready = chain_ready();
-                SC_STAT_ADD(7, ready ? 0 : 1);
-                if (ready) {
-                    const A prefix = chain_consume();
-                    incl_own = Op::apply(prefix, agg_cur);
-                    if (lane == 0) s_tile_prefix = prefix;
-                }
-                if (lane == 0) s_chain_ready = ready ? 1 : 0;
-            }
-        }
         SC_STAT_T(t_rdy);
         __syncthreads();                                   // (A) warp totals of the next tile visible
         SC_STAT_T(t_a);
         const int64_t seg = seg_of_tile(g, p), t = g - seg * p.tiles_per_seg;
-        bool need_b = !CHAIN;
-        if constexpr (CHAIN) need_b = s_chain_ready == 0;  // CTA-uniform
         if (warp == 0) {
-            // the next tile's aggregate is published BEFORE anything that may wait: a publication gated
-            // behind a wait lets one late tile delay every successor's aggregate (measured: 50x slower)
             if (have_next) agg_nxt = finish_pass1(nxt, par ^ 1);
-            if constexpr (CHAIN) {
-                if (need_b) {      // some aggregate had not been published when it was prefetched: poll for it now
-                    const A prefix = chain_consume();
-                    incl_own = Op::apply(prefix, agg_cur);
-                    if (lane == 0) s_tile_prefix = prefix;
-                }
-            } else {
-                const A prefix = tile_lookback<Op, LOOK>(p, seg, t, lane, agg_cur, /*publish_partial=*/false);
-                if (lane == 0) s_tile_prefix = prefix;
-            }
+            const A prefix = tile_lookback<Op, LOOK>(p, seg, t, lane, agg_cur, /*publish_partial=*/false);
+            if (lane == 0) s_tile_prefix = prefix;
         }
-        if (need_b) __syncthreads();                       // (B) prefix of the current tile visible
+        __syncthreads();                                   // (B) prefix of the current tile visible
         SC_STAT_T(t_b);
         const A base = Op::apply(s_tile_prefix, s_wexcl[par][warp]);
 
@@ -831,9 +737,6 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
         const Tin *s_in = reinterpret_cast<const Tin *>(s_dyn + stage * STAGE_BYTES);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            if constexpr (CHAIN) {
-                if (k == p.chain_at && warp == 0 && have_next) chain_issue(s_tile[nxt], g, true);
-            }
             Tin e[EPC];
             lds_chunk<Tin, EPC>(s_in + wbase + (k * 32 + lane) * EPC, e);
             A run2 = Op::apply(base, cpre_cur[k]);
@@ -844,21 +747,8 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
                 o[q] = p.exclusive ? run2 : nxtv;
                 run2 = nxtv;
             }
-            if (TSTORE && valid == TILE) {                 // results replace the inputs in the stage (CTA-uniform branch)
-                if constexpr (TSTORE) {
-                    Tout eo[EPC];
-#pragma unroll
-                    for (int q = 0; q < EPC; ++q) eo[q] = cvt<Tout>(o[q]);
-                    sts_chunk<Tout, EPC>(reinterpret_cast<Tout *>(s_dyn + stage * STAGE_BYTES) + wbase + (k * 32 + lane) * EPC, eo);
-                }
-            } else {
-                store_chunk<Tout, A, EPC>(tout, wbase + (k * 32 + lane) * EPC, valid, o);
-            }
+            store_chunk<Tout, A, EPC>(tout, wbase + (k * 32 + lane) * EPC, valid, o);
         }
-        if constexpr (CHAIN) {
-            if (p.chain_at >= K && warp == 0 && have_next) chain_issue(s_tile[nxt], g, true);
-        }
-        if constexpr (TSTORE) fence_proxy_async_smem();    // this thread's shared-memory writes -> visible to the TMA unit
         SC_STAT_T(t_p2);
         __syncthreads();                                   // (C) stage consumed; s_wtot / s_tile_prefix free
         SC_STAT_T(t_c);
@@ -869,26 +759,8 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
         SC_STAT_ADD(5, t_b - t_a);         // publish + look-back / fallback + barrier (B)
         SC_STAT_ADD(6, t_p2 - t_b);        // pass 2
         SC_STAT_ADD(8, t_c - t_p2);        // barrier (C)
-        if constexpr (TSTORE) {
-            if (threadIdx.x == 0) {
-                // one bulk group per iteration (empty for a ragged tile), so "at most one group still reading"
-                // means the stage stored an iteration ago is free for the next load
-                if (valid == TILE) {
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 :: "l"(tout), "r"(smem_u32(s_dyn + stage * STAGE_BYTES)), "r"((uint32_t)STAGE_BYTES) : "memory");
-                }
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                fill((int)((it + S - 1) % S), next_ticket);
-            }
-            if (!have_next) {
-                if (threadIdx.x == 0) tma_store_wait_read();   // shared memory must outlive the last bulk read
-                break;
-            }
-        } else {
-            if (threadIdx.x == 0) fill(stage, next_ticket);
-            if (!have_next) break;
-        }
+        if (threadIdx.x == 0) fill(stage, next_ticket);
+        if (!have_next) break;
 #pragma unroll
         for (int k = 0; k < K; ++k) cpre_cur[k] = cpre_nxt[k];
         agg_cur = agg_nxt;
@@ -1799,9 +1671,11 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
     B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, clear, stream));
     if (vec) {
         // Persistent CTAs over a ring of TMA-loaded stages.  Measured on B200 (cumsum 2^30):
-        //   look-back, STG stores:  Float32 5.3 TB/s (one 512-thread CTA per SM, 96-wide window),
-        //                           Int64 4.8 TB/s (two 256-thread CTAs per SM)
-        //   see DESIGN.md section 4 for the self-chained (CHAIN) and bulk-store (TSTORE) variants
+        //   scan_chain2_kernel (default):  Float32 6.58 TB/s, Int64 5.65 TB/s   (480 + 32 threads, 4 stages of 52.5 KB)
+        //   scan_pipe_kernel (look-back):  Float32 5.28 TB/s (one 512-thread CTA per SM, 96-wide window),
+        //                                  Int64 4.82 TB/s (two 256-thread CTAs per SM)
+        // The single-ahead chain and the bulk-store ring measured on the way were removed
+        // again; they live in the history (commit 4518692).
         constexpr bool kWide = sizeof(A) > 4;
 #ifndef B200_SCAN_NT_NARROW
 #define B200_SCAN_NT_NARROW 512
@@ -1815,137 +1689,83 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
 #ifndef B200_SCAN_LOOK_NARROW
 #define B200_SCAN_LOOK_NARROW 3
 #endif
-#ifndef B200_SCAN_CHAIN_AT
-#define B200_SCAN_CHAIN_AT 4
-#endif
-#ifndef B200_SCAN_CHAIN_CTAS
-#define B200_SCAN_CHAIN_CTAS 2
-#endif
 #ifndef B200_SCAN_CHAIN2_K
 #define B200_SCAN_CHAIN2_K 7
 #endif
-        // Variant selection.  Default: scan_chain2_kernel (measured on B200, cumsum 2^30: Float32 6.58 TB/s vs 5.28 with
-        // the look-back kernel, Int64 5.65 vs 4.82).  B200_SCAN_CHAIN=0 selects the look-back kernel.  The other experiments (single-ahead
-        // chain, bulk-store ring, look-back in its own warp) are only compiled with -DB200_SCAN_EXPERIMENTS
-        // (B200_SCAN_CHAIN=1, B200_SCAN_TSTORE=1, B200_SCAN_WS=1); measurements in DESIGN.md section 4.
+        // B200_SCAN_CHAIN=0 / 2 forces the look-back kernel / chain2 for every shape; B200_SCAN_WS=1 (with the look-back
+        // kernel) gives the look-back its own warp (measured slower).
         static const char *chain_env = getenv("B200_SCAN_CHAIN");
-#ifdef B200_SCAN_EXPERIMENTS
         static const bool use_ws = getenv("B200_SCAN_WS") != nullptr;
-        static const bool use_chain = chain_env && chain_env[0] == '1';
-        constexpr bool kSameSize = sizeof(Tin) == sizeof(Tout);
-        static const bool use_tstore = kSameSize && !use_ws && getenv("B200_SCAN_TSTORE") && getenv("B200_SCAN_TSTORE")[0] == '1';
-#else
-        constexpr bool use_ws = false, use_chain = false, kSameSize = false, use_tstore = false;
-#endif
         // scan_chain2_kernel: status prefetch issued 0 = before barrier (A), 1 = after the publication
         static const int chain_at = getenv("B200_SCAN_CHAIN_AT") ? atoi(getenv("B200_SCAN_CHAIN_AT")) : 1;
         p.chain_at = chain_at < 0 ? 0 : chain_at;
         int dev = 0;
         B200_CUDA_TRY(cudaGetDevice(&dev));
-        // one launch shape = (threads, chunk rows K, stages, CTAs per SM cap); the kernel variant is picked inside
-        auto launch = [&](auto nt_c, auto k_c, auto st_c, auto tstore_c) -> int32_t {
-            constexpr int kThreads = decltype(nt_c)::value, kK = decltype(k_c)::value, kStages = decltype(st_c)::value;
-            constexpr bool kTstore = decltype(tstore_c)::value;
-            constexpr int kLook = kWide ? 4 : B200_SCAN_LOOK_NARROW;
-            constexpr int64_t kTile = (int64_t)kThreads * S::EPC * kK;
-            constexpr size_t smem = (size_t)kTile * sizeof(Tin) * kStages;
-            constexpr int kFit = (200 * 1024) / (int)smem > 0 ? (200 * 1024) / (int)smem : 1;   // CTAs per SM by shared memory
-            constexpr int kChainCtas = kFit < B200_SCAN_CHAIN_CTAS ? kFit : B200_SCAN_CHAIN_CTAS;
-            constexpr int kRows = (148 * kChainCtas * 5 / 4 + 31) / 32;     // 6 or 12 rows of 32 status words (gap + 25 %)
-            void (*kern)(ScanParams);
-#ifdef B200_SCAN_EXPERIMENTS
-            if constexpr (kTstore)
-                kern = use_chain ? scan_pipe_kernel<Tin, Tout, Op, S::EPC, kK, kStages, kThreads, kRows, true, true>
-                                 : scan_pipe_kernel<Tin, Tout, Op, S::EPC, kK, kStages, kThreads, kLook, false, true>;
-            else
-                kern = use_ws ? scan_pipe_ws_kernel<Tin, Tout, Op, S::EPC, kK, kStages, (kThreads > 992 ? 992 : kThreads), kLook>
-                     : use_chain ? scan_pipe_kernel<Tin, Tout, Op, S::EPC, kK, kStages, kThreads, kRows, true>
-                                 : scan_pipe_kernel<Tin, Tout, Op, S::EPC, kK, kStages, kThreads, kLook>;
-#else
-            (void)kRows;
-            kern = scan_pipe_kernel<Tin, Tout, Op, S::EPC, kK, kStages, kThreads, kLook>;
-#endif
-            static thread_local int attr_dev_mask[64][4];  // cudaFuncSetAttribute once per (thread, device, variant)
-            const int variant = (use_ws ? 2 : 0) + (use_chain ? 1 : 0);
-            if (dev >= 0 && dev < 64 && !attr_dev_mask[dev][variant]) {
-                B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_dev_mask[dev][variant] = 1;
-            }
-            p.tiles_per_seg = cdiv(n, kTile);
-            const int64_t ptiles = p.tiles_per_seg * post;
-            int64_t pgrid = (int64_t)devinfo().sm_count * (use_chain && !use_ws ? kChainCtas : kFit);
-            if (pgrid > ptiles) pgrid = ptiles;
-#ifdef B200_SCAN_STATS
-            unsigned long long zero[16] = {};
-            cudaMemcpyToSymbol(g_scan_stats, zero, sizeof(zero));
-#endif
-            kern<<<(unsigned int)pgrid, use_ws && !kTstore ? kThreads + 32 : kThreads, smem, stream>>>(p);
-#ifdef B200_SCAN_STATS
-            cudaStreamSynchronize(stream);
-            unsigned long long h[16];
-            cudaMemcpyFromSymbol(h, g_scan_stats, sizeof(h));
-            if (h[0]) fprintf(stderr, "[scan stats] chain=%d tstore=%d grid=%lld tiles=%lld iters=%llu | cycles/iter: mbar-wait %.0f  ticket+pass1 %.0f  ready %.0f  barA %.0f  "
-                    "publish+lookback+barB %.0f  pass2 %.0f  barC %.0f | fallbacks %.1f%%\n", (int)use_chain, (int)kTstore, (long long)pgrid, (long long)ptiles, h[0],
-                    (double)h[1] / h[0], (double)h[2] / h[0], (double)h[3] / h[0], (double)h[4] / h[0], (double)h[5] / h[0],
-                    (double)h[6] / h[0], (double)h[8] / h[0], 100.0 * h[7] / h[0]);
-#endif
-            return B200_OK;
-        };
-        using std::integral_constant;
-        int32_t rc;
         // Several segments: a segment's last tile is usually ragged and ragged tiles take the slow (LDG) path of pass 1, so
         // pick the tiling that wastes less of its last tile (16384 x 16384 Float32 along dims=1: the look-back kernel's
         // 16384-element tile fits exactly, chain2's 13440 would leave every second tile ragged).
+        constexpr int kLookThreads = kWide ? B200_SCAN_NT_WIDE : B200_SCAN_NT_NARROW;
+        constexpr int kLookK = kWide ? S::K : B200_SCAN_K_NARROW;
         constexpr int64_t kTileChain2 = (int64_t)480 * S::EPC * B200_SCAN_CHAIN2_K;
-        constexpr int64_t kTileLook = (int64_t)(kWide ? B200_SCAN_NT_WIDE : B200_SCAN_NT_NARROW) * S::EPC * (kWide ? S::K : B200_SCAN_K_NARROW);
+        constexpr int64_t kTileLook = (int64_t)kLookThreads * S::EPC * kLookK;
         const int64_t pad2 = cdiv(n, kTileChain2) * kTileChain2 - n, pad1 = cdiv(n, kTileLook) * kTileLook - n;
         const bool chain2_fits = post == 1 || pad2 <= pad1 || pad2 * 8 <= n;      // at most 12.5 % of a segment in a ragged tile
         static const int chain_force = chain_env ? (chain_env[0] == '2' ? 2 : 0) : -1;
-        const bool use_chain2 = chain_force >= 0 ? chain_force == 2 : chain2_fits;
+        const bool use_chain2 = !use_ws && (chain_force >= 0 ? chain_force == 2 : chain2_fits);
+        int64_t pgrid = 0, ptiles = 0;
+#ifdef B200_SCAN_STATS
+        unsigned long long zero[16] = {};
+        cudaMemcpyToSymbol(g_scan_stats, zero, sizeof(zero));
+#endif
         if (use_chain2) {
             constexpr int kThreads = 480, kK = B200_SCAN_CHAIN2_K;   // 15 compute warps + 1 control warp = 512 threads (128 registers each)
-            constexpr int64_t kTile = (int64_t)kThreads * S::EPC * kK;
-            constexpr size_t smem = (size_t)kTile * sizeof(Tin) * 4;
+            constexpr size_t smem = (size_t)kTileChain2 * sizeof(Tin) * 4;
             // one CTA per SM for every type pair: the tile is sized by the OUTPUT bytes a CTA stores per iteration, and a
             // second CTA would double the status words the control warp holds in registers (12 rows: spills)
-            constexpr int kCtas = 1;
-            constexpr int kRows = (148 * kCtas * 5 / 4 + 31) / 32;
+            constexpr int kRows = (148 * 5 / 4 + 31) / 32;           // status rows prefetched: the gap between two tickets + 25 %
             auto kern = scan_chain2_kernel<Tin, Tout, Op, S::EPC, kK, kThreads, kRows>;
             static thread_local int attr2_dev_mask[64];
             if (dev >= 0 && dev < 64 && !attr2_dev_mask[dev]) {
                 B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 attr2_dev_mask[dev] = 1;
             }
-            p.tiles_per_seg = cdiv(n, kTile);
-            const int64_t ptiles = p.tiles_per_seg * post;
-            int64_t pgrid = (int64_t)devinfo().sm_count * kCtas;
+            p.tiles_per_seg = cdiv(n, kTileChain2);
+            ptiles = p.tiles_per_seg * post;
+            pgrid = (int64_t)devinfo().sm_count;
             if (pgrid > ptiles) pgrid = ptiles;
-#ifdef B200_SCAN_STATS
-            unsigned long long zero[16] = {};
-            cudaMemcpyToSymbol(g_scan_stats, zero, sizeof(zero));
-#endif
             kern<<<(unsigned int)pgrid, kThreads + 32, smem, stream>>>(p);
+        } else {
+            constexpr int kStages = 3;
+            constexpr int kLook = kWide ? 4 : B200_SCAN_LOOK_NARROW;
+            constexpr size_t smem = (size_t)kTileLook * sizeof(Tin) * kStages;
+            constexpr int kFit = (200 * 1024) / (int)smem > 0 ? (200 * 1024) / (int)smem : 1;   // CTAs per SM by shared memory
+            auto kern = use_ws ? scan_pipe_ws_kernel<Tin, Tout, Op, S::EPC, kLookK, kStages, (kLookThreads > 992 ? 992 : kLookThreads), kLook>
+                               : scan_pipe_kernel<Tin, Tout, Op, S::EPC, kLookK, kStages, kLookThreads, kLook>;
+            static thread_local int attr_dev_mask[64][2];  // cudaFuncSetAttribute once per (thread, device, variant)
+            if (dev >= 0 && dev < 64 && !attr_dev_mask[dev][use_ws ? 1 : 0]) {
+                B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_dev_mask[dev][use_ws ? 1 : 0] = 1;
+            }
+            p.tiles_per_seg = cdiv(n, kTileLook);
+            ptiles = p.tiles_per_seg * post;
+            pgrid = (int64_t)devinfo().sm_count * kFit;
+            if (pgrid > ptiles) pgrid = ptiles;
+            kern<<<(unsigned int)pgrid, use_ws ? kLookThreads + 32 : kLookThreads, smem, stream>>>(p);
+        }
 #ifdef B200_SCAN_STATS
-            cudaStreamSynchronize(stream);
-            unsigned long long h[16];
-            cudaMemcpyFromSymbol(h, g_scan_stats, sizeof(h));
-            if (h[0]) fprintf(stderr, "[scan stats] chain2 grid=%lld tiles=%lld iters=%llu | compute cycles/iter: mbar-wait %.0f  pass1 %.0f  wait(A) %.0f  pass2 %.0f  wait(C) %.0f"
+        cudaStreamSynchronize(stream);
+        unsigned long long h[16];
+        cudaMemcpyFromSymbol(h, g_scan_stats, sizeof(h));
+        if (h[0] && use_chain2)
+            fprintf(stderr, "[scan stats] chain2 grid=%lld tiles=%lld iters=%llu | compute cycles/iter: mbar-wait %.0f  pass1 %.0f  wait(A) %.0f  pass2 %.0f  wait(C) %.0f"
                     " | control: ready+consume %.0f  wait(A) %.0f  publish+fallback+issue %.0f  wait(C) %.0f | fallbacks %.1f%%\n", (long long)pgrid, (long long)ptiles, h[0],
                     (double)h[1] / h[0], (double)h[2] / h[0], (double)h[9] / h[0], (double)h[6] / h[0], (double)h[10] / h[0],
                     (double)h[3] / h[0], (double)h[4] / h[0], (double)h[5] / h[0], (double)h[8] / h[0], 100.0 * h[7] / h[0]);
+        else if (h[0])
+            fprintf(stderr, "[scan stats] look-back grid=%lld tiles=%lld iters=%llu | cycles/iter: mbar-wait %.0f  ticket+pass1 %.0f  barA %.0f  "
+                    "publish+lookback+barB %.0f  pass2 %.0f  barC %.0f\n", (long long)pgrid, (long long)ptiles, h[0],
+                    (double)h[1] / h[0], (double)h[2] / h[0], (double)h[4] / h[0], (double)h[5] / h[0], (double)h[6] / h[0], (double)h[8] / h[0]);
 #endif
-            rc = B200_OK;
-        } else
-        if constexpr (kSameSize) {
-            // bulk-store ring: 4 stages of 512 x EPC x 7 elements (57344 bytes for 4- and 8-byte types), one CTA per SM
-            if (use_tstore) rc = launch(integral_constant<int, 512>{}, integral_constant<int, 7>{}, integral_constant<int, 4>{}, std::true_type{});
-            else rc = launch(integral_constant<int, (kWide ? B200_SCAN_NT_WIDE : B200_SCAN_NT_NARROW)>{},
-                             integral_constant<int, (kWide ? S::K : B200_SCAN_K_NARROW)>{}, integral_constant<int, 3>{}, std::false_type{});
-        } else {
-            rc = launch(integral_constant<int, (kWide ? B200_SCAN_NT_WIDE : B200_SCAN_NT_NARROW)>{},
-                        integral_constant<int, (kWide ? S::K : B200_SCAN_K_NARROW)>{}, integral_constant<int, 3>{}, std::false_type{});
-        }
-        if (rc != B200_OK) return rc;
     }
     else scan_contig_kernel<Tin, Tout, Op, 1, S::K1><<<(unsigned int)grid, SC_THREADS, 0, stream>>>(p);
     B200_CHECK_LAUNCH();
