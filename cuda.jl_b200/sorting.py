@@ -98,7 +98,7 @@ def partialsort_(c, k, alg=BitonicSort, lt=isless, by=identity, rev=False):
 
 
 def partialsort(c, k, alg=BitonicSort, lt=isless, by=identity, rev=False):
-    """Base.partialsort(c, k; kw...) = partialsort!(copy(c), k; kw...).  For a scalar k nothing needs to be
+    """Base.partialsort(c::AnyCuArray, k; kw...) = partialsort!(copy(c), k; kw...) (sorting.jl:1046-1048).  For a scalar k nothing needs to be
     sorted or copied: b200_select_kth (MSD radix select, sizeof(T) streaming reads of c) finds the element a
     stable sort would put at position k.  Ranges go through the full sort like the reference."""
     if not isinstance(k, (int, np.integer)):

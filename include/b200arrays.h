@@ -240,7 +240,7 @@ int32_t b200_partition_scatter(void *workspace, size_t workspace_bytes, const vo
                                void *const *dst_keys, void *const *dst_payload, const int64_t *dst_base,
                                b200_stream_t stream);
 
-/* ---- radix select: partialsort(c, k) for a scalar k (sorting.jl:1015-1022) - */
+/* ---- radix select: partialsort(c, k) for a scalar k (sorting.jl:1015-1020,1046-1048) - */
 /* The reference's bitonic partialsort is "full sort, then c[k]".  b200_select_kth writes the
  * element that a stable sort (isless order, `descending` as in b200_sort_keys) would put at
  * 0-based position k to out_value[0] (device, element type of the keys) WITHOUT sorting or

@@ -51,12 +51,14 @@ end
 # partialsort!(c, k, ::BitonicSortAlg) = sort! + copy(c[k]) (sorting.jl:1015-1020) reaches the
 # sort! method above unchanged (it must leave `c` sorted); nothing to override.
 #
-# Base.partialsort(c, k; kw...) = partialsort!(copy(c), k; kw...): for a scalar k neither the copy nor the
-# sort is needed — b200_select_kth (MSD radix select: sizeof(T) streaming reads of c, c untouched) returns the
-# element a stable sort would put at position k.  Ranges and custom lt/by keep the reference path.
-function Base.partialsort(c::CuVector{T}, k::Integer; lt=isless, by=identity, rev::Bool=false) where {T<:SortTypes}
-    if !enabled() || lt !== isless || by !== identity
-        return invoke(partialsort, Tuple{AbstractVector,Union{Integer,OrdinalRange}}, c, k; lt, by, rev)
+# Base.partialsort(c::AnyCuArray, k; kw...) = partialsort!(copy(c), k; kw...) (sorting.jl:1046-1048): for a scalar k
+# neither the copy nor the sort is needed — b200_select_kth (MSD radix select: sizeof(T) streaming reads of c, c
+# untouched) returns the element a stable sort would put at position k.  Ranges, custom lt/by and alg=QuickSort keep the
+# reference path.
+function Base.partialsort(c::CuVector{T}, k::Integer; alg::CUDACore.SortingAlgorithm=CUDACore.BitonicSort,
+                          lt=isless, by=identity, rev::Bool=false) where {T<:SortTypes}
+    if !enabled() || !graftable(lt, by, alg)
+        return invoke(partialsort, Tuple{CUDACore.AnyCuArray,Union{Integer,OrdinalRange}}, c, k; alg, lt, by, rev)
     end
     checkbounds(c, k)
     out = CuVector{T}(undef, 1)
