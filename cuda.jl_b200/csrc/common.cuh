@@ -6,6 +6,9 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <type_traits>
+#ifdef B200_TUNING
+#include <cstdlib>
+#endif
 #include "../../include/b200arrays.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -35,6 +38,14 @@ int32_t fail_cuda(cudaError_t e);    // records e, returns B200_LAUNCH_FAILURE
         cudaError_t _e = cudaGetLastError();                  \
         if (_e != cudaSuccess) return ::b200::fail_cuda(_e);  \
     } while (0)
+
+// A/B measurement knobs: read from the environment only in -DB200_TUNING builds (tools/build_variant.sh);
+// the product library has no environment dependence and always takes the default.
+#ifdef B200_TUNING
+static inline int tune_int(const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; }
+#else
+static inline int tune_int(const char *, int dflt) { return dflt; }
+#endif
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -19,9 +19,6 @@ namespace b200 {
 constexpr int RX_THREADS = 256;
 constexpr int RX_WARPS = RX_THREADS / 32;
 constexpr int RX_RADIX = 256;
-#ifndef B200_RX_ATOMOR_MASK
-#define B200_RX_ATOMOR_MASK 0
-#endif
 #ifndef B200_RX_MATCH_MASK
 #define B200_RX_MATCH_MASK 0x8888   // items 3, 7, 11, 15 of every 16
 #endif
@@ -76,6 +73,13 @@ template <class K> __device__ __forceinline__ K key_decode(K key, const SortXfor
     return key ^ ((K)x.base_dec ^ (sar & (K)x.fmn));
 }
 
+// Device-side gate word (MsdCtl::mode, written by an earlier kernel of the same call): L2-coherent load.
+__device__ __forceinline__ unsigned int ld_gate(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // ------------------------------------------------------------------ histogram of every digit
 // One read of the keys builds all sizeof(K) digit histograms (shared-memory atomics,
 // then one global atomic per (pass, bin) per CTA).
@@ -83,8 +87,10 @@ constexpr int RX_HIST_REPL = 8;   // histogram replicas (by lane & 7): spreads r
 
 template <class K>
 __global__ void __launch_bounds__(512) radix_hist_kernel(const K *__restrict__ keys, int64_t n, SortXform xf,
-                                                         unsigned long long *__restrict__ ghist) {
+                                                         unsigned long long *__restrict__ ghist,
+                                                         const unsigned int *__restrict__ gate) {
     constexpr int P = (int)sizeof(K);
+    if (gate && ld_gate(gate) != 0) return;   // the hybrid MSD path (sort_msd.cuh) has taken this call
     constexpr int VN = 16 / (int)sizeof(K);
     extern __shared__ unsigned int sh[];   // [P][256][RX_HIST_REPL]
     for (int i = threadIdx.x; i < P * RX_RADIX * RX_HIST_REPL; i += blockDim.x) sh[i] = 0;
@@ -118,8 +124,10 @@ __global__ void __launch_bounds__(512) radix_hist_kernel(const K *__restrict__ k
 
 // Exclusive scan of each pass's 256-bin histogram: bins[p][d] = first output index of digit d.
 static __global__ void __launch_bounds__(RX_RADIX) radix_bins_kernel(const unsigned long long *__restrict__ ghist,
-                                                              unsigned long long *__restrict__ bins) {
+                                                              unsigned long long *__restrict__ bins,
+                                                              const unsigned int *__restrict__ gate) {
     __shared__ unsigned long long s[RX_RADIX];
+    if (gate && ld_gate(gate) != 0) return;
     const int d = threadIdx.x;
     const unsigned long long c = ghist[blockIdx.x * RX_RADIX + d];
     s[d] = c;
@@ -152,6 +160,16 @@ __global__ void radix_lower_bound_kernel(const K *__restrict__ sorted, int64_t n
     out[j] = lo;
 }
 
+// Device-side control block of one sort call (first 256 bytes of the workspace, zeroed by the call's one memset).
+struct SortCtl {
+    unsigned int mode;          // hybrid MSD path (sort_msd.cuh): 0 = declined (the LSD passes run); 1 / 2 = leaf A / B
+    unsigned int nne;           // non-empty 16-bit segments
+    unsigned int tiles2;        // level-2 tiles
+    unsigned int max_seg;       // longest 16-bit segment (diagnostic)
+    unsigned int ticket1, ticket2, ticket_leaf, pad;
+    unsigned long long lsd_ticket[8];   // one tile ticket per LSD pass (persistent CTAs, no per-pass memset)
+};
+
 // ------------------------------------------------------------------ onesweep pass
 struct OnesweepParams {
     const void *keys_in;
@@ -172,6 +190,12 @@ struct OnesweepParams {
     int64_t index_base;               // 1 for per-segment 1-based indices (+ segment offset when linear)
     int32_t unstable_ok;              // keys-only FIRST pass: equal keys are indistinguishable and no earlier pass has
                                       // established an order, so ranks inside a digit may come from shared-memory atomics
+    int64_t tiles;                    // tiles of this pass; CTAs are persistent and take tiles by ticket
+    const unsigned int *gate;         // non-null: run only while *gate == 0 (hybrid MSD path declined the call)
+    // Look-back flag codes of THIS pass (already shifted into the top two bits).  The status array is zeroed once per
+    // sort call; pass p uses inclusive = 1 + p % 3, partial = 1 + (p + 1) % 3, and what the previous pass left behind
+    // (every tile ends "inclusive", code 1 + (p - 1) % 3) reads as "not yet published" — no memset between passes.
+    unsigned long long flag_incl, flag_part;
 };
 
 template <class LookT> struct LookBits;
@@ -212,7 +236,7 @@ template <> struct PayTraits<NoPayload> { static constexpr bool HAS = false; usi
 // NT = threads per CTA (256, or 512 as an experiment: the per-digit bookkeeping and the look-back are done by 256
 // threads per TILE, so a 512-thread tile halves their cost per key; B200_SORT_NT=512, keys-only, not yet measured).
 template <class K, class V, class LookT, int ITEMS, bool ARANK = false, int NT = RX_THREADS>
-__global__ void __launch_bounds__(NT, (ARANK ? B200_RX_ARANK_CTAS : 0)) radix_onesweep_kernel(OnesweepParams p) {
+__global__ void __launch_bounds__(NT, (sizeof(K) + (PayTraits<V>::HAS ? sizeof(V) : 0) <= 8 ? 1024 / NT : 768 / NT)) radix_onesweep_kernel(OnesweepParams p) {
     using LB = LookBits<LookT>;
     constexpr bool HAS_V = PayTraits<V>::HAS;
     using VT = typename PayTraits<V>::type;
@@ -233,25 +257,24 @@ __global__ void __launch_bounds__(NT, (ARANK ? B200_RX_ARANK_CTAS : 0)) radix_on
     BaseT *s_gbase = reinterpret_cast<BaseT *>(s_gbase_raw);
     K *s_keys = reinterpret_cast<K *>(s_gbase_raw + RX_RADIX);
     VT *s_vals = reinterpret_cast<VT *>(reinterpret_cast<unsigned char *>(s_keys) + ((TILE * sizeof(K) + 15) / 16) * 16);
-    __shared__ unsigned long long s_ticket;
+    __shared__ unsigned long long s_ticket[2];
     __shared__ unsigned int s_wsum[DWARPS];
-#if B200_RX_ATOMOR_MASK
-    __shared__ unsigned int s_match[RX_WARPS][RX_RADIX];   // per-warp peer-mask table for the atomic-or matched items
-#endif
 
+    if (p.gate && ld_gate(p.gate) != 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool dthread = NT == RX_RADIX || tid < RX_RADIX;   // this thread owns digit `tid`
-    if (tid == 0) s_ticket = atomicAdd(p.ticket, 1ull);
-    // zero this warp's digit counters while the ticket is in flight
+    const LookT flag_incl = (LookT)p.flag_incl, flag_part = (LookT)p.flag_part;
     unsigned int *whist = s_whist + warp * RX_RADIX;
+    // Persistent CTA: tiles are taken by ticket (two ticket slots: the next iteration's write cannot overtake a
+    // slow reader of this one, because a barrier separates them).
+  for (unsigned int iter = 0;; ++iter) {
+    if (tid == 0) s_ticket[iter & 1] = atomicAdd(p.ticket, 1ull);
+    // zero this warp's digit counters while the ticket is in flight
 #pragma unroll
     for (int k = 0; k < RX_RADIX / 32; ++k) whist[k * 32 + lane] = 0;
-#if B200_RX_ATOMOR_MASK
-#pragma unroll
-    for (int k = 0; k < RX_RADIX / 32; ++k) s_match[warp][k * 32 + lane] = 0;
-#endif
     __syncthreads();
-    const int64_t t = (int64_t)s_ticket;
+    const int64_t t = (int64_t)s_ticket[iter & 1];
+    if (t >= p.tiles) return;
     const int64_t tile_base = t * TILE;
     const int64_t remain = p.n - tile_base;
     const int valid = remain > TILE ? TILE : (int)remain;
@@ -296,7 +319,7 @@ __global__ void __launch_bounds__(NT, (ARANK ? B200_RX_ARANK_CTAS : 0)) radix_on
         if (dthread) {
             unsigned int c = s_bhist[tid];
             if (tid == RX_RADIX - 1) c -= (unsigned int)(TILE - valid);
-            st_relaxed<LookT>(status + t * RX_RADIX + tid, (LookT)((t > 0 ? LB::PARTIAL : LB::INCLUSIVE) | (LookT)c));
+            st_relaxed<LookT>(status + t * RX_RADIX + tid, (LookT)((t > 0 ? flag_part : flag_incl) | (LookT)c));
         }
     }
 
@@ -334,16 +357,6 @@ __global__ void __launch_bounds__(NT, (ARANK ? B200_RX_ARANK_CTAS : 0)) radix_on
         if ((B200_RX_MATCH_MASK >> (i & 15)) & 1) {
             // a quarter of the items go through MATCH.ANY so that the ADU pipe shares the load with the ALU
             peers = __match_any_sync(0xffffffffu, digit);
-#if B200_RX_ATOMOR_MASK
-        } else if ((B200_RX_ATOMOR_MASK >> (i & 15)) & 1) {
-            // ... and some through a shared-memory atomic-or table, which runs on the LSU pipe
-            volatile unsigned int *mt = &s_match[warp][digit];
-            atomicOr(const_cast<unsigned int *>(mt), 1u << lane);
-            __syncwarp();
-            peers = *mt;
-            __syncwarp();
-            if ((peers & lt_mask) == 0u) *mt = 0u;
-#endif
         } else {
             unsigned int differ = 0;   // lanes whose digit differs from mine in some bit
 #pragma unroll
@@ -388,7 +401,7 @@ __global__ void __launch_bounds__(NT, (ARANK ? B200_RX_ARANK_CTAS : 0)) radix_on
     const unsigned int real_count = (d == RX_RADIX - 1) ? tile_count - pad : tile_count;
     if constexpr (!EARLY_COUNTS) {  // keys-only: publish here; tile 0 knows its inclusive prefix already
         if (dthread)
-            st_relaxed<LookT>(status + t * RX_RADIX + d, (LookT)((t > 0 ? LB::PARTIAL : LB::INCLUSIVE) | (LookT)real_count));
+            st_relaxed<LookT>(status + t * RX_RADIX + d, (LookT)((t > 0 ? flag_part : flag_incl) | (LookT)real_count));
     }
 
     // exclusive scan of tile_count over the 256 digits -> start of each digit run in shared memory
@@ -442,21 +455,22 @@ __global__ void __launch_bounds__(NT, (ARANK ? B200_RX_ARANK_CTAS : 0)) radix_on
                 all_valid = true;
 #pragma unroll
                 for (int k = 0; k < RX_LOOK; ++k) {
-                    w[k] = LB::INCLUSIVE;   // virtual tiles before the first one: inclusive, zero
+                    w[k] = flag_incl;   // virtual tiles before the first one: inclusive, zero
                     if (u - k >= 0) w[k] = ld_relaxed<LookT>(status + (u - k) * RX_RADIX + d);
-                    all_valid = all_valid && ((w[k] & LB::FLAGS) != 0);
+                    const LookT f = w[k] & LB::FLAGS;
+                    all_valid = all_valid && (f == flag_incl || f == flag_part);
                 }
             } while (!all_valid);
 #pragma unroll
             for (int k = 0; k < RX_LOOK; ++k) {
                 if (!done) {
                     excl += (unsigned long long)(w[k] & LB::MASK);
-                    done = (w[k] & LB::FLAGS) == LB::INCLUSIVE;
+                    done = (w[k] & LB::FLAGS) == flag_incl;
                 }
             }
             u -= RX_LOOK;
         }
-        st_relaxed<LookT>(status + t * RX_RADIX + d, (LookT)(LB::INCLUSIVE | (LookT)(excl + real_count)));
+        st_relaxed<LookT>(status + t * RX_RADIX + d, (LookT)(flag_incl | (LookT)(excl + real_count)));
     }
     if (dthread) s_gbase[d] = (BaseT)((long long)(p.bins[d] + excl) - (long long)doff);
     __syncthreads();
@@ -496,6 +510,7 @@ __global__ void __launch_bounds__(NT, (ARANK ? B200_RX_ARANK_CTAS : 0)) radix_on
     };
     if (full) emit_mode(std::true_type{});
     else emit_mode(std::false_type{});
+  }   // persistent tile loop
 }
 
 }  // namespace b200

@@ -1,11 +1,12 @@
 // sort_inst.cu — one translation unit per key width (-DB200_KEY_BYTES=1|2|4|8).
-// Host orchestration of the onesweep passes for keys / sortperm / pairs.
-#include "sort_pipe.cuh"
-#include "sort_ctr.cuh"
+// Host orchestration: LSD onesweep passes for keys / sortperm / pairs, and (32-bit keys-only) the hybrid MSD
+// path of sort_msd.cuh with the LSD passes as its device-gated fallback.
 #include "select_kth.cuh"
 #include "sort_block.cuh"
 #include "sort_host.h"
-#include <cstdlib>
+#if B200_KEY_BYTES == 4
+#include "sort_msd.cuh"
+#endif
 
 namespace b200 {
 
@@ -29,146 +30,171 @@ template <class V> static size_t onesweep_smem() {
     return s;
 }
 
-template <class V> static size_t pipe_smem() {
-    using VT = typename PayTraits<V>::type;
-    constexpr int TILE = tile_for<V>();
-    size_t s = (size_t)(RXP_STAGES + 2) * TILE * sizeof(K) + (size_t)RX_WARPS * RX_RADIX * 4 + 2 * RX_RADIX * 8;
-    if (PayTraits<V>::HAS) s += 2 * (size_t)TILE * sizeof(VT);
-    return s;
-}
-
-// Persistent pipelined pass: needs 16-byte aligned keys (TMA) and at least one full tile.
-template <class V, class LookT> static int32_t launch_pipe(const OnesweepParams &p, int64_t tiles, cudaStream_t st) {
-    auto kern = radix_onesweep_pipe_kernel<K, V, LookT, ItemsFor<V>::value>;
-    const size_t smem = pipe_smem<V>();
-    static thread_local bool attr_set[64];
+// One-time (per kernel, per device) setup: opt in to the dynamic shared memory and ask how many CTAs fit on an SM —
+// the passes are persistent (tiles by ticket), so the grid is resident CTAs, not tiles.
+struct KernelSetup {
+    bool done[64] = {};
+    int ctas_per_sm[64] = {};
+};
+template <class Kern> static int32_t setup_kernel(KernelSetup &ks, Kern kern, int threads, size_t smem, int *ctas_per_sm) {
     int dev = 0;
     B200_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    if (dev < 0 || dev >= 64) return B200_INVALID_VALUE;
+    if (!ks.done[dev]) {
         B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[dev] = true;
+        int nb = 0;
+        B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem));
+        ks.ctas_per_sm[dev] = nb < 1 ? 1 : nb;
+        ks.done[dev] = true;
     }
-    int64_t per_sm = (int64_t)(220 * 1024 / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 3) per_sm = 3;
+    *ctas_per_sm = ks.ctas_per_sm[dev];
+    return B200_OK;
+}
+
+template <class Kern> static int32_t launch_persistent(KernelSetup &ks, Kern kern, int threads, size_t smem,
+                                                       const OnesweepParams &p, cudaStream_t st) {
+    int per_sm = 1;
+    const int32_t rc = setup_kernel(ks, kern, threads, smem, &per_sm);
+    if (rc != B200_OK) return rc;
     int64_t grid = (int64_t)devinfo().sm_count * per_sm;
-    if (grid > tiles) grid = tiles;
-    kern<<<(unsigned int)grid, RX_THREADS, smem, st>>>(p, (long long)tiles);
+    if (grid > p.tiles) grid = p.tiles;
+    kern<<<(unsigned int)grid, threads, smem, st>>>(p);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }
 
-// 512-thread tiles for keys-only sorts of 32-bit keys (experiment, B200_SORT_NT=512; see radix_onesweep_kernel's NT).
-static bool wide_cta() {
-#if B200_KEY_BYTES == 4
-    static const bool on = [] { const char *e = getenv("B200_SORT_NT"); return e && atoi(e) == 512; }();
-    return on;
-#else
-    return false;
-#endif
-}
-constexpr int WIDE_NT = 512;
-constexpr int WIDE_TILE = WIDE_NT * ItemsFor<NoPayload>::value;
-
-// Counter-ranked pass (sort_ctr.cuh) for keys-only sorts of 32-bit keys: 0 = off, 1 = 128 threads x 64 keys,
-// 2 = 64 threads x 128 keys.
-static int ctr_mode() {
-#if B200_KEY_BYTES == 4
-    static const int mode = [] { const char *e = getenv("B200_SORT_CTR"); return e ? atoi(e) : 0; }();
-    return mode;
-#else
-    return 0;
-#endif
-}
-constexpr int CTR_TILE = 8192;
-
-#if B200_KEY_BYTES == 4
-template <class LookT, int NT, int ITEMS> static int32_t launch_ctr(const OnesweepParams &p, int64_t tiles, cudaStream_t st) {
-    auto kern = radix_onesweep_ctr_kernel<LookT, NT, ITEMS>;
-    constexpr size_t smem = ctr_smem_bytes<NT, ITEMS>();
-    static thread_local bool attr_set[64];
-    int dev = 0;
-    B200_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[dev] = true;
-    }
-    kern<<<(unsigned int)tiles, NT, smem, st>>>(p);
-    B200_CHECK_LAUNCH();
-    return B200_OK;
-}
-#endif
-
-template <class V, class LookT> static int32_t launch_pass(const OnesweepParams &p, int64_t tiles, cudaStream_t st) {
-#if B200_KEY_BYTES == 4
-    if constexpr (!PayTraits<V>::HAS) {
-        if (ctr_mode() == 1) return launch_ctr<LookT, 128, 64>(p, tiles, st);
-        if (ctr_mode() == 2) return launch_ctr<LookT, 64, 128>(p, tiles, st);
-    }
-#endif
-    static const bool use_pipe = getenv("B200_SORT_PIPE") != nullptr;   // persistent variant: measured slower (fewer warps per SM)
-    if (use_pipe && tiles >= 2 && (reinterpret_cast<uintptr_t>(p.keys_in) % 16) == 0 && pipe_smem<V>() <= 200 * 1024)
-        return launch_pipe<V, LookT>(p, tiles, st);
+template <class V, class LookT> static int32_t launch_pass(const OnesweepParams &p, cudaStream_t st) {
     const size_t smem = onesweep_smem<V>();
-    int dev = 0;
-    B200_CUDA_TRY(cudaGetDevice(&dev));
-#if B200_KEY_BYTES == 4
-    if constexpr (!PayTraits<V>::HAS) {
-        if (wide_cta()) {
-            constexpr size_t wsmem = (size_t)(WIDE_NT / 32) * RX_RADIX * 4 + RX_RADIX * 4 + RX_RADIX * 8 + (size_t)WIDE_TILE * sizeof(K);
-            auto k0 = radix_onesweep_kernel<K, V, LookT, ItemsFor<V>::value, false, WIDE_NT>;
-            auto k1 = radix_onesweep_kernel<K, V, LookT, ItemsFor<V>::value, true, WIDE_NT>;
-            static thread_local bool wattr_set[64];
-            if (dev >= 0 && dev < 64 && !wattr_set[dev]) {
-                B200_CUDA_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-                B200_CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-                wattr_set[dev] = true;
-            }
-            if (p.unstable_ok) k1<<<(unsigned int)tiles, WIDE_NT, wsmem, st>>>(p);
-            else k0<<<(unsigned int)tiles, WIDE_NT, wsmem, st>>>(p);
-            B200_CHECK_LAUNCH();
-            return B200_OK;
-        }
-    }
-#endif
     if constexpr (!PayTraits<V>::HAS) {
         if (p.unstable_ok) {
-            auto akern = radix_onesweep_kernel<K, V, LookT, ItemsFor<V>::value, true>;
-            static thread_local bool aattr_set[64];
-            if (dev >= 0 && dev < 64 && !aattr_set[dev]) {
-                B200_CUDA_TRY(cudaFuncSetAttribute(akern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                aattr_set[dev] = true;
-            }
-            akern<<<(unsigned int)tiles, RX_THREADS, smem, st>>>(p);
-            B200_CHECK_LAUNCH();
-            return B200_OK;
+            static thread_local KernelSetup ks;
+            return launch_persistent(ks, radix_onesweep_kernel<K, V, LookT, ItemsFor<V>::value, true>, RX_THREADS, smem, p, st);
         }
     }
-    auto kern = radix_onesweep_kernel<K, V, LookT, ItemsFor<V>::value>;
-    static thread_local bool attr_set[64];
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[dev] = true;
-    }
-    kern<<<(unsigned int)tiles, RX_THREADS, smem, st>>>(p);
-    B200_CHECK_LAUNCH();
-    return B200_OK;
+    static thread_local KernelSetup ks;
+    return launch_persistent(ks, radix_onesweep_kernel<K, V, LookT, ItemsFor<V>::value>, RX_THREADS, smem, p, st);
 }
 
-template <class LookT> static int32_t dispatch_pass(const OnesweepParams &p, int pay_bytes, int64_t tiles, cudaStream_t st) {
-    if (pay_bytes == 0) return launch_pass<NoPayload, LookT>(p, tiles, st);
-    if (pay_bytes == 4) return launch_pass<uint32_t, LookT>(p, tiles, st);
-    return launch_pass<uint64_t, LookT>(p, tiles, st);
+template <class LookT> static int32_t dispatch_pass(const OnesweepParams &p, int pay_bytes, cudaStream_t st) {
+    if (pay_bytes == 0) return launch_pass<NoPayload, LookT>(p, st);
+    if (pay_bytes == 4) return launch_pass<uint32_t, LookT>(p, st);
+    return launch_pass<uint64_t, LookT>(p, st);
 }
 
 #define B200_CAT2(a, b) a##b
 #define B200_CAT(a, b) B200_CAT2(a, b)
 
+#if B200_KEY_BYTES == 4
+// ---- hybrid MSD path (sort_msd.cuh): dense 32-bit keys-only sorts -------------------------------------------
+constexpr int MSD_NT = 512, MSD_ITEMS = 20, MSD_TILE = MSD_NT * MSD_ITEMS;      // P1 / P2 tile
+constexpr int LEAF_A_NT = 512, LEAF_A_ITEMS = 36;                              // 18432 keys, 2 CTAs per SM
+constexpr int LEAF_B_NT = 1024, LEAF_B_ITEMS = 36;                             // 36864 keys, 1 CTA per SM
+constexpr unsigned int MSD_MIN_AVG = 6144;   // counting leaf: 65536 / (keys per segment) counters scanned per key
+constexpr int64_t MSD_MIN_N = 1LL << 27;     // below this even a full key range cannot reach MSD_MIN_AVG ... per
+                                             // non-empty segment unless the keys sit in a narrow range; not worth the histogram
+constexpr int64_t MSD_MAX_N = 1LL << 30;     // 32-bit look-back words carry 30-bit counts
+
+static bool xform_is_identity(const SortXform &x) { return x.base_enc == 0 && x.fmn == 0 && x.mag_mask == 0 && x.desc == 0; }
+
+struct MsdBuffers {
+    MsdCtl *ctl;
+    unsigned int *hist16, *status1, *status2, *seg_start, *seg_list, *l1_tile_start;
+};
+
+template <bool IDENT>
+static int32_t msd_launch(const SortCall &c, const MsdBuffers &b, uint32_t *alt, cudaStream_t st) {
+    const int64_t n = c.n;
+    const DevInfo &dev = devinfo();
+    {   // H: histogram of the top 16 bits
+        static thread_local KernelSetup ks;
+        int per_sm = 1;
+        const size_t smem = (size_t)MSD_H16_WORDS * 4;
+        int32_t rc = setup_kernel(ks, msd_hist16_kernel<IDENT>, MSD_H16_THREADS, smem, &per_sm);
+        if (rc != B200_OK) return rc;
+        int64_t grid = dev.sm_count;
+        const int64_t need = cdiv(n, (int64_t)MSD_H16_THREADS * MSD_H16_VPT * 4);
+        if (grid > need) grid = need;
+        msd_hist16_kernel<IDENT><<<(unsigned int)grid, MSD_H16_THREADS, smem, st>>>(static_cast<const uint32_t *>(c.keys), n, c.xf, b.hist16);
+        B200_CHECK_LAUNCH();
+    }
+    {   // PL
+        MsdPlanParams pp{};
+        pp.hist16 = b.hist16; pp.seg_start = b.seg_start; pp.seg_list = b.seg_list; pp.l1_tile_start = b.l1_tile_start;
+        pp.ctl = b.ctl; pp.n = (unsigned int)n; pp.tile2 = MSD_TILE;
+        pp.cap_a = LEAF_A_NT * LEAF_A_ITEMS; pp.cap_b = LEAF_B_NT * LEAF_B_ITEMS;
+        static const unsigned int min_avg = (unsigned int)tune_int("B200_MSD_MIN_AVG", (int)MSD_MIN_AVG);
+        pp.min_avg = min_avg;
+        msd_plan_kernel<<<1, 1024, 0, st>>>(pp);
+        B200_CHECK_LAUNCH();
+    }
+    MsdScatterParams sp{};
+    sp.n = (unsigned int)n; sp.seg_start = b.seg_start; sp.l1_tile_start = b.l1_tile_start; sp.ctl = b.ctl; sp.xf = c.xf;
+    const size_t ssmem = (size_t)MSD_TILE * 4;
+    {   // P1: keys -> alt by byte 3
+        static thread_local KernelSetup ks;
+        int per_sm = 1;
+        auto kern = msd_scatter_kernel<1, MSD_NT, MSD_ITEMS, IDENT>;
+        int32_t rc = setup_kernel(ks, kern, MSD_NT, ssmem, &per_sm);
+        if (rc != B200_OK) return rc;
+        sp.keys_in = static_cast<const uint32_t *>(c.keys); sp.keys_out = alt; sp.status = b.status1;
+        int64_t grid = (int64_t)dev.sm_count * per_sm;
+        const int64_t tiles = cdiv(n, MSD_TILE);
+        if (grid > tiles) grid = tiles;
+        kern<<<(unsigned int)grid, MSD_NT, ssmem, st>>>(sp);
+        B200_CHECK_LAUNCH();
+    }
+    {   // P2: alt -> keys by byte 2 inside every level-1 bucket
+        static thread_local KernelSetup ks;
+        int per_sm = 1;
+        auto kern = msd_scatter_kernel<2, MSD_NT, MSD_ITEMS, IDENT>;
+        int32_t rc = setup_kernel(ks, kern, MSD_NT, ssmem, &per_sm);
+        if (rc != B200_OK) return rc;
+        sp.keys_in = alt; sp.keys_out = static_cast<uint32_t *>(c.keys); sp.status = b.status2;
+        int64_t grid = (int64_t)dev.sm_count * per_sm;
+        const int64_t tiles = cdiv(n, MSD_TILE) + 256;
+        if (grid > tiles) grid = tiles;
+        kern<<<(unsigned int)grid, MSD_NT, ssmem, st>>>(sp);
+        B200_CHECK_LAUNCH();
+    }
+    MsdLeafParams lp{};
+    lp.keys = static_cast<uint32_t *>(c.keys); lp.seg_start = b.seg_start; lp.seg_list = b.seg_list; lp.ctl = b.ctl; lp.xf = c.xf;
+    {   // leaf A (segments up to 18432 keys)
+        static thread_local KernelSetup ks;
+        int per_sm = 1;
+        auto kern = msd_leaf_kernel<LEAF_A_NT, LEAF_A_ITEMS, IDENT>;
+        const size_t smem = (size_t)LEAF_A_NT * LEAF_A_ITEMS * 4 + (size_t)(LEAF_A_NT / 32) * 1024;
+        int32_t rc = setup_kernel(ks, kern, LEAF_A_NT, smem, &per_sm);
+        if (rc != B200_OK) return rc;
+        lp.want_mode = 1;
+        kern<<<(unsigned int)(dev.sm_count * per_sm), LEAF_A_NT, smem, st>>>(lp);
+        B200_CHECK_LAUNCH();
+    }
+    {   // leaf B (segments up to 36864 keys)
+        static thread_local KernelSetup ks;
+        int per_sm = 1;
+        auto kern = msd_leaf_kernel<LEAF_B_NT, LEAF_B_ITEMS, IDENT>;
+        const size_t smem = (size_t)LEAF_B_NT * LEAF_B_ITEMS * 4 + (size_t)(LEAF_B_NT / 32) * 1024;
+        int32_t rc = setup_kernel(ks, kern, LEAF_B_NT, smem, &per_sm);
+        if (rc != B200_OK) return rc;
+        lp.want_mode = 2;
+        kern<<<(unsigned int)(dev.sm_count * per_sm), LEAF_B_NT, smem, st>>>(lp);
+        B200_CHECK_LAUNCH();
+    }
+    return B200_OK;
+}
+
+static bool msd_eligible(const SortCall &c) {
+    static const int on = tune_int("B200_SORT_HYBRID", 1);
+    static const int min_log2 = tune_int("B200_MSD_MIN_LOG2N", 27);
+    return on && c.mode == SORT_KEYS && c.n >= (1LL << min_log2) && c.n <= MSD_MAX_N;
+}
+#else
+static bool msd_eligible(const SortCall &) { return false; }
+#endif
+
 int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
     const int64_t n = c.n;
-    const int64_t max_tiles = cdiv(n, c.mode == SORT_KEYS ? tile_for<NoPayload>() : tile_for<uint32_t>());
-    const int64_t tiles = (c.mode == SORT_KEYS && ctr_mode() && !c.query) ? cdiv(n, CTR_TILE)
-                        : (c.mode == SORT_KEYS && wide_cta() && !c.query) ? cdiv(n, WIDE_TILE) : max_tiles;
+    const int64_t tiles = cdiv(n, c.mode == SORT_KEYS ? tile_for<NoPayload>() : tile_for<uint32_t>());
     // 32-bit status words carry 30-bit counts.  Every prefix that is ever READ belongs to a tile before the last
     // one and is therefore < n, so n == 2^30 still fits (only the last tile's own inclusive value can reach 2^30,
     // and nobody looks back at the last tile).
@@ -178,12 +204,32 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
     int pay = 0;
     if (c.mode == SORT_PERM) pay = n > 0xFFFFFFFFLL ? 8 : 4;
     else if (c.mode == SORT_PAIRS) pay = c.payload_bytes;
+    const bool hybrid = msd_eligible(c);
 
+    // workspace: [ctl | ghist | status | (hybrid: hist16 | status2)] is zeroed by ONE memset per call
     Carver w(c.ws);
+    char *ctl_raw = w.take<char>(256);
     unsigned long long *ghist = w.take<unsigned long long>(P * RX_RADIX);
+    char *status = w.take<char>((size_t)tiles * RX_RADIX * look_bytes);
+#if B200_KEY_BYTES == 4
+    MsdBuffers mb{};
+    mb.ctl = reinterpret_cast<MsdCtl *>(ctl_raw);
+    static_assert(sizeof(MsdCtl) <= 256, "control block");
+    if (hybrid) {
+        mb.hist16 = w.take<unsigned int>(MSD_BINS);
+        mb.status1 = reinterpret_cast<unsigned int *>(status);     // P1 has fewer tiles than an LSD pass
+        mb.status2 = w.take<unsigned int>((size_t)(cdiv(n, MSD_TILE) + 256) * RX_RADIX);
+    }
+#endif
+    const size_t clear_bytes = w.bytes();
+#if B200_KEY_BYTES == 4
+    if (hybrid) {
+        mb.seg_start = w.take<unsigned int>(MSD_BINS + 1);
+        mb.seg_list = w.take<unsigned int>(MSD_BINS);
+        mb.l1_tile_start = w.take<unsigned int>(257);
+    }
+#endif
     unsigned long long *bins = w.take<unsigned long long>(P * RX_RADIX);
-    unsigned long long *ticket = w.take<unsigned long long>(1);
-    char *status = w.take<char>((size_t)max_tiles * RX_RADIX * look_bytes);
     char *kbuf0 = w.take<char>((size_t)n * sizeof(K));
     char *kbuf1 = c.mode == SORT_PERM ? w.take<char>((size_t)n * sizeof(K)) : nullptr;
     char *vbuf0 = pay ? w.take<char>((size_t)n * pay) : nullptr;
@@ -193,9 +239,21 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
     if (c.ws == nullptr) return B200_INVALID_VALUE;
     if (tiles > 2147483647LL) return B200_INVALID_VALUE;
     cudaStream_t st = c.stream;
+    SortCtl *ctl = reinterpret_cast<SortCtl *>(ctl_raw);
+    static_assert(P <= 8 && sizeof(SortCtl) <= 256, "one LSD ticket per pass; control block is the first 256 bytes");
+
+    B200_CUDA_TRY(cudaMemsetAsync(c.ws, 0, clear_bytes, st));
+    const unsigned int *gate = nullptr;
+#if B200_KEY_BYTES == 4
+    if (hybrid) {
+        const int32_t rc = xform_is_identity(c.xf) ? msd_launch<true>(c, mb, reinterpret_cast<uint32_t *>(kbuf0), st)
+                                                    : msd_launch<false>(c, mb, reinterpret_cast<uint32_t *>(kbuf0), st);
+        if (rc != B200_OK) return rc;
+        gate = &ctl->mode;      // the LSD kernels below return at once when the hybrid path took the call
+    }
+#endif
 
     // ---- digit histograms of all passes in one read, then their exclusive scans
-    B200_CUDA_TRY(cudaMemsetAsync(ghist, 0, (size_t)P * RX_RADIX * sizeof(unsigned long long), st));
     {
         const DevInfo &dev = devinfo();
         int64_t grid = (int64_t)dev.sm_count * 4;
@@ -210,24 +268,28 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
             B200_CUDA_TRY(cudaFuncSetAttribute(radix_hist_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
             hist_attr[hdev] = true;
         }
-        radix_hist_kernel<K><<<(unsigned int)grid, 512, hist_smem, st>>>(static_cast<const K *>(c.keys), n, c.xf, ghist);
+        radix_hist_kernel<K><<<(unsigned int)grid, 512, hist_smem, st>>>(static_cast<const K *>(c.keys), n, c.xf, ghist, gate);
         B200_CHECK_LAUNCH();
-        radix_bins_kernel<<<P, RX_RADIX, 0, st>>>(ghist, bins);
+        radix_bins_kernel<<<P, RX_RADIX, 0, st>>>(ghist, bins, gate);
         B200_CHECK_LAUNCH();
     }
 
-    const size_t clear = (size_t)((status + (size_t)tiles * RX_RADIX * look_bytes) - reinterpret_cast<char *>(ticket));
+    const int flag_shift = wide ? 62 : 30;
     for (int pass = 0; pass < P; ++pass) {
         OnesweepParams p{};
         p.n = n;
         p.shift = 8 * pass;
         p.bins = bins + pass * RX_RADIX;
         p.status = status;
-        p.ticket = ticket;
+        p.ticket = &ctl->lsd_ticket[pass];
+        p.tiles = tiles;
+        p.gate = gate;
+        p.flag_incl = (unsigned long long)(1 + pass % 3) << flag_shift;
+        p.flag_part = (unsigned long long)(1 + (pass + 1) % 3) << flag_shift;
         p.xf = c.xf;
         p.encode_in = pass == 0;
-        static const bool no_atomic_rank = getenv("B200_SORT_STABLE_FIRST") != nullptr;   // A/B switch
-        p.unstable_ok = pass == 0 && c.mode == SORT_KEYS && !no_atomic_rank;
+        static const int stable_first = tune_int("B200_SORT_STABLE_FIRST", 0);   // A/B switch
+        p.unstable_ok = pass == 0 && c.mode == SORT_KEYS && !stable_first;
         p.decode_out = (pass == P - 1) && c.mode != SORT_PERM;
         p.store_keys = !(pass == P - 1 && c.mode == SORT_PERM);
         p.gen_payload = (pass == 0 && c.mode == SORT_PERM);
@@ -250,8 +312,7 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
                 p.vals_out = from_user ? vbuf0 : c.payload;
             }
         }
-        B200_CUDA_TRY(cudaMemsetAsync(ticket, 0, clear, st));
-        int32_t rc = wide ? dispatch_pass<uint64_t>(p, pay, tiles, st) : dispatch_pass<uint32_t>(p, pay, tiles, st);
+        int32_t rc = wide ? dispatch_pass<uint64_t>(p, pay, st) : dispatch_pass<uint32_t>(p, pay, st);
         if (rc != B200_OK) return rc;
     }
     if (c.mode != SORT_PERM && (P & 1)) {
