@@ -235,8 +235,13 @@ template <> struct PayTraits<NoPayload> { static constexpr bool HAS = false; usi
 #endif
 // NT = threads per CTA (256, or 512 as an experiment: the per-digit bookkeeping and the look-back are done by 256
 // threads per TILE, so a 512-thread tile halves their cost per key; B200_SORT_NT=512, keys-only, not yet measured).
-template <class K, class V, class LookT, int ITEMS, bool ARANK = false, int NT = RX_THREADS>
-__global__ void __launch_bounds__(NT, (sizeof(K) + (PayTraits<V>::HAS ? sizeof(V) : 0) <= 8 ? 1024 / NT : 768 / NT)) radix_onesweep_kernel(OnesweepParams p) {
+// PERSIST (only instantiated for the gated fallback of the hybrid MSD path, where a grid of `tiles` CTAs that all
+// return at once would cost more than the sort): persistent CTAs, registers capped so that 4 CTAs stay resident.
+// Measured on B200, sort! 2^30 UInt32: one CTA per tile 15.7 ms, persistent 17.8 ms — so everything else keeps the
+// one-tile-per-CTA form, whose SASS is the round-1 kernel plus the flag-code compares.
+template <class K, class V, class LookT, int ITEMS, bool ARANK = false, int NT = RX_THREADS, bool PERSIST = false>
+__global__ void __launch_bounds__(NT, ((PERSIST || sizeof(K) + (PayTraits<V>::HAS ? sizeof(V) : 0) <= 8) ? 1024 / NT : 0))
+radix_onesweep_kernel(OnesweepParams p) {
     using LB = LookBits<LookT>;
     constexpr bool HAS_V = PayTraits<V>::HAS;
     using VT = typename PayTraits<V>::type;
@@ -265,8 +270,8 @@ __global__ void __launch_bounds__(NT, (sizeof(K) + (PayTraits<V>::HAS ? sizeof(V
     const bool dthread = NT == RX_RADIX || tid < RX_RADIX;   // this thread owns digit `tid`
     const LookT flag_incl = (LookT)p.flag_incl, flag_part = (LookT)p.flag_part;
     unsigned int *whist = s_whist + warp * RX_RADIX;
-    // Persistent CTA: tiles are taken by ticket (two ticket slots: the next iteration's write cannot overtake a
-    // slow reader of this one, because a barrier separates them).
+    // PERSIST: the CTA loops, taking tiles by ticket (two ticket slots: the next iteration's write cannot overtake
+    // a slow reader of this one, because a barrier separates them).  !PERSIST: one tile per CTA, grid == tiles.
   for (unsigned int iter = 0;; ++iter) {
     if (tid == 0) s_ticket[iter & 1] = atomicAdd(p.ticket, 1ull);
     // zero this warp's digit counters while the ticket is in flight
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(NT, (sizeof(K) + (PayTraits<V>::HAS ? sizeof(V
     for (int k = 0; k < RX_RADIX / 32; ++k) whist[k * 32 + lane] = 0;
     __syncthreads();
     const int64_t t = (int64_t)s_ticket[iter & 1];
-    if (t >= p.tiles) return;
+    if (PERSIST && t >= p.tiles) return;
     const int64_t tile_base = t * TILE;
     const int64_t remain = p.n - tile_base;
     const int valid = remain > TILE ? TILE : (int)remain;
@@ -510,6 +515,7 @@ __global__ void __launch_bounds__(NT, (sizeof(K) + (PayTraits<V>::HAS ? sizeof(V
     };
     if (full) emit_mode(std::true_type{});
     else emit_mode(std::false_type{});
+    if constexpr (!PERSIST) return;
   }   // persistent tile loop
 }
 

@@ -51,13 +51,13 @@ template <class Kern> static int32_t setup_kernel(KernelSetup &ks, Kern kern, in
     return B200_OK;
 }
 
-template <class Kern> static int32_t launch_persistent(KernelSetup &ks, Kern kern, int threads, size_t smem,
-                                                       const OnesweepParams &p, cudaStream_t st) {
+template <class Kern> static int32_t launch_pass_kernel(KernelSetup &ks, Kern kern, int threads, size_t smem, bool persistent,
+                                                        const OnesweepParams &p, cudaStream_t st) {
     int per_sm = 1;
     const int32_t rc = setup_kernel(ks, kern, threads, smem, &per_sm);
     if (rc != B200_OK) return rc;
-    int64_t grid = (int64_t)devinfo().sm_count * per_sm;
-    if (grid > p.tiles) grid = p.tiles;
+    int64_t grid = p.tiles;
+    if (persistent && grid > (int64_t)devinfo().sm_count * per_sm) grid = (int64_t)devinfo().sm_count * per_sm;
     kern<<<(unsigned int)grid, threads, smem, st>>>(p);
     B200_CHECK_LAUNCH();
     return B200_OK;
@@ -65,14 +65,25 @@ template <class Kern> static int32_t launch_persistent(KernelSetup &ks, Kern ker
 
 template <class V, class LookT> static int32_t launch_pass(const OnesweepParams &p, cudaStream_t st) {
     const size_t smem = onesweep_smem<V>();
+    constexpr int IT = ItemsFor<V>::value;
+#if B200_KEY_BYTES == 4
+    if constexpr (!PayTraits<V>::HAS && sizeof(LookT) == 4) {
+        if (p.gate) {       // fallback of the hybrid MSD path: persistent CTAs (an all-returning grid must be small)
+            static thread_local KernelSetup ks0, ks1;
+            if (p.unstable_ok)
+                return launch_pass_kernel(ks1, radix_onesweep_kernel<K, V, LookT, IT, true, RX_THREADS, true>, RX_THREADS, smem, true, p, st);
+            return launch_pass_kernel(ks0, radix_onesweep_kernel<K, V, LookT, IT, false, RX_THREADS, true>, RX_THREADS, smem, true, p, st);
+        }
+    }
+#endif
     if constexpr (!PayTraits<V>::HAS) {
         if (p.unstable_ok) {
             static thread_local KernelSetup ks;
-            return launch_persistent(ks, radix_onesweep_kernel<K, V, LookT, ItemsFor<V>::value, true>, RX_THREADS, smem, p, st);
+            return launch_pass_kernel(ks, radix_onesweep_kernel<K, V, LookT, IT, true>, RX_THREADS, smem, false, p, st);
         }
     }
     static thread_local KernelSetup ks;
-    return launch_persistent(ks, radix_onesweep_kernel<K, V, LookT, ItemsFor<V>::value>, RX_THREADS, smem, p, st);
+    return launch_pass_kernel(ks, radix_onesweep_kernel<K, V, LookT, IT>, RX_THREADS, smem, false, p, st);
 }
 
 template <class LookT> static int32_t dispatch_pass(const OnesweepParams &p, int pay_bytes, cudaStream_t st) {

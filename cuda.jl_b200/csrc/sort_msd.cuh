@@ -45,6 +45,14 @@ template <int N> struct PackedRanks {
     __device__ __forceinline__ unsigned int get(int j) const { return (j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xFFFFu); }
 };
 
+// Phase A of the leaf reads keys that phase B reads again a few microseconds later: plain L2-cached load (the
+// L1::no_allocate streaming form, SASS LDG.E.NA, was measured to send 85 % of the re-reads to DRAM).
+__device__ __forceinline__ uint32_t ld_keep_l2(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ unsigned int ld_cg_u32(const unsigned int *p) {
     unsigned int v;
     asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -231,6 +239,16 @@ struct MsdScatterParams {
 
 // LEVEL 1: digit = key byte 3 of the encoded key, one chain over all tiles, input = raw keys (encoded here).
 // LEVEL 2: digit = key byte 2, tile t lies inside level-1 bucket `seg`, chain restarts at the bucket's first tile.
+//
+// Persistent CTAs, software-pipelined over tiles: once a tile's keys sit in the shared staging buffer their
+// registers are dead, so the NEXT tile's global loads are issued right there — before the look-back and the
+// write-out of the current tile — and the DRAM round trip hides behind them (measured before this change: 32 %
+// issue utilisation, barrier + scoreboard stalls on top, profiles/r2_sort_msd_v1.md).
+struct MsdTile {
+    unsigned int t, first, seg, base;   // ticket, chain's first ticket, level-1 bucket, index of the tile's first key
+    int valid;                          // keys in the tile
+};
+
 template <int LEVEL, int NT, int ITEMS, bool IDENT>
 __global__ void __launch_bounds__(NT, 1024 / NT) msd_scatter_kernel(MsdScatterParams p) {
     using LB = LookBits<uint32_t>;
@@ -244,7 +262,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msd_scatter_kernel(MsdScatterPa
     __shared__ unsigned int s_gbase[256];
     __shared__ unsigned int s_wsum[8];
     __shared__ unsigned int s_tk[2];
-    __shared__ unsigned int s_seg[4];
+    __shared__ unsigned int s_seg[2][4];                     // {bucket, first tile, first key, end key} of a ticket
+    __shared__ unsigned int s_l1ts[LEVEL == 2 ? 257 : 1];    // first tile of every level-1 bucket (loaded once)
+    __shared__ unsigned int s_l1lo[LEVEL == 2 ? 257 : 1];    // first key of every level-1 bucket
 
     if (ld_cg_u32(&p.ctl->mode) == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -252,48 +272,72 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msd_scatter_kernel(MsdScatterPa
     const unsigned int tiles = LEVEL == 1 ? (p.n + TILE - 1) / TILE : ld_cg_u32(&p.ctl->tiles2);
     unsigned int *ticket = LEVEL == 1 ? &p.ctl->ticket1 : &p.ctl->ticket2;
 
-    for (unsigned int it = 0;; ++it) {
-        if (tid == 0) s_tk[it & 1] = atomicAdd(ticket, 1u);
-        if (dthread) s_hist[tid] = 0;
-        __syncthreads();
-        const unsigned int t = s_tk[it & 1];
-        if (t >= tiles) break;
-        unsigned int seg = 0, first = 0, lo = 0, hi = p.n;
+    // which bucket does ticket t fall into?  (LEVEL 2; the one digit thread whose range holds t answers)
+    auto locate = [&](unsigned int t, int slot) {
         if constexpr (LEVEL == 2) {
-            if (dthread) {
-                const unsigned int a = p.l1_tile_start[tid], b = p.l1_tile_start[tid + 1];
+            if (dthread && t < tiles) {
+                const unsigned int a = s_l1ts[tid], b = s_l1ts[tid + 1];
                 if (a <= t && t < b) {
-                    s_seg[0] = tid; s_seg[1] = a;
-                    s_seg[2] = p.seg_start[tid * 256]; s_seg[3] = p.seg_start[tid * 256 + 256];
+                    s_seg[slot][0] = tid; s_seg[slot][1] = a;
+                    s_seg[slot][2] = s_l1lo[tid]; s_seg[slot][3] = s_l1lo[tid + 1];
                 }
             }
-            __syncthreads();
-            seg = s_seg[0]; first = s_seg[1]; lo = s_seg[2]; hi = s_seg[3];
         }
-        const unsigned int tile_base = lo + (t - first) * TILE;
-        const unsigned int remain = hi - tile_base;
-        const int valid = remain > (unsigned int)TILE ? TILE : (int)remain;
-        const bool full = valid == TILE;
-        const bool chain_head = t == first;
-        // first output index of this bucket's digit `tid` (loaded early, used after the look-back)
-        unsigned int bin = 0;
-        if (dthread) bin = LEVEL == 1 ? p.seg_start[tid * 256] : p.seg_start[seg * 256 + tid];
-
-        // ---- load (coalesced, thread-strided: no order to preserve) and rank with one shared atomic per key
-        const uint32_t *kin = p.keys_in + tile_base + tid;
-        uint32_t keys[ITEMS];
-        PackedRanks<ITEMS> ranks;
-        if (full) {
+    };
+    auto describe = [&](unsigned int t, int slot) {
+        MsdTile d;
+        d.t = t;
+        unsigned int lo = 0, hi = p.n;
+        d.seg = 0; d.first = 0;
+        if constexpr (LEVEL == 2) { d.seg = s_seg[slot][0]; d.first = s_seg[slot][1]; lo = s_seg[slot][2]; hi = s_seg[slot][3]; }
+        d.base = lo + (t - d.first) * TILE;
+        const unsigned int remain = hi - d.base;
+        d.valid = remain > (unsigned int)TILE ? TILE : (int)remain;
+        return d;
+    };
+    uint32_t keys[ITEMS];
+    auto load_tile = [&](const MsdTile &d) {
+        const uint32_t *kin = p.keys_in + d.base + tid;
+        if (d.valid == TILE) {
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) keys[i] = ldg_stream(kin + i * NT);
         } else {
 #pragma unroll
-            for (int i = 0; i < ITEMS; ++i) keys[i] = (i * NT + tid < valid) ? ldg_stream(kin + i * NT) : 0u;
+            for (int i = 0; i < ITEMS; ++i) keys[i] = (i * NT + tid < d.valid) ? ldg_stream(kin + i * NT) : 0u;
         }
+    };
+
+    // ---- prologue: tables, first ticket, first tile's loads
+    unsigned int next_t = 0;                       // thread 0: ticket after the current one, requested a tile early
+    if (tid == 0) s_tk[0] = atomicAdd(ticket, 1u);
+    if constexpr (LEVEL == 2) {
+        for (int i = tid; i < 257; i += NT) {
+            s_l1ts[i] = p.l1_tile_start[i];
+            s_l1lo[i] = p.seg_start[i * 256];
+        }
+    }
+    if (dthread) s_hist[tid] = 0;
+    __syncthreads();
+    if (s_tk[0] >= tiles) return;
+    if (tid == 0) next_t = atomicAdd(ticket, 1u);
+    locate(s_tk[0], 0);
+    if constexpr (LEVEL == 2) __syncthreads();
+    MsdTile cur = describe(s_tk[0], 0);
+    load_tile(cur);
+
+    for (unsigned int it = 0;; ++it) {
+        const bool full = cur.valid == TILE;
+        const bool chain_head = cur.t == cur.first;
+        // first output index of this bucket's digit `tid` (loaded early, used after the look-back)
+        unsigned int bin = 0;
+        if (dthread) bin = LEVEL == 1 ? p.seg_start[tid * 256] : p.seg_start[cur.seg * 256 + tid];
+
+        // ---- rank with one shared atomic per key (s_hist is zero: prologue / zeroed below by its digit thread)
         if constexpr (LEVEL == 1 && !IDENT) {
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) keys[i] = key_encode<uint32_t>(keys[i], p.xf);
         }
+        PackedRanks<ITEMS> ranks;
         if (full) {
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) ranks.set(i, atomicAdd(&s_hist[(keys[i] >> SHIFT) & 0xFFu], 1u));
@@ -301,18 +345,20 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msd_scatter_kernel(MsdScatterPa
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) {
                 unsigned int r = 0;
-                if (i * NT + tid < valid) r = atomicAdd(&s_hist[(keys[i] >> SHIFT) & 0xFFu], 1u);
+                if (i * NT + tid < cur.valid) r = atomicAdd(&s_hist[(keys[i] >> SHIFT) & 0xFFu], 1u);
                 ranks.set(i, r);
             }
         }
-        __syncthreads();
+        __syncthreads();                                                                     // (A)
 
         // ---- per digit: publish the tile's count, exclusive scan over the digits
         unsigned int cnt = 0;
         if (dthread) {
             cnt = s_hist[tid];
-            st_relaxed<uint32_t>(p.status + (size_t)t * 256 + tid, (chain_head ? LB::INCLUSIVE : LB::PARTIAL) | cnt);
+            s_hist[tid] = 0;                       // ready for the next tile's ranking (two barriers away)
+            st_relaxed<uint32_t>(p.status + (size_t)cur.t * 256 + tid, (chain_head ? LB::INCLUSIVE : LB::PARTIAL) | cnt);
         }
+        if (tid == 0) s_tk[(it + 1) & 1] = next_t;  // the ticket requested during the previous tile has long arrived
         unsigned int incl = cnt;
         if (warp < 8) {
 #pragma unroll
@@ -322,7 +368,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msd_scatter_kernel(MsdScatterPa
             }
             if (lane == 31) s_wsum[warp] = incl;
         }
-        __syncthreads();
+        __syncthreads();                                                                     // (B)
         unsigned int doff = 0;
         if (dthread) {
             unsigned int wbase = 0;
@@ -331,7 +377,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msd_scatter_kernel(MsdScatterPa
             doff = wbase + incl - cnt;
             s_doff[tid] = doff;
         }
-        __syncthreads();
+        const unsigned int tn = s_tk[(it + 1) & 1];
+        const bool have_next = tn < tiles;
+        locate(tn, (it + 1) & 1);
+        __syncthreads();                                                                     // (C)
 
         // ---- scatter into shared memory, grouped by digit
         if (full) {
@@ -340,15 +389,23 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msd_scatter_kernel(MsdScatterPa
         } else {
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i)
-                if (i * NT + tid < valid) s_keys[s_doff[(keys[i] >> SHIFT) & 0xFFu] + ranks.get(i)] = keys[i];
+                if (i * NT + tid < cur.valid) s_keys[s_doff[(keys[i] >> SHIFT) & 0xFFu] + ranks.get(i)] = keys[i];
+        }
+
+        // ---- the key registers are dead: start the next tile's loads now
+        MsdTile nxt = cur;
+        if (have_next) {
+            if (tid == 0) next_t = atomicAdd(ticket, 1u);
+            nxt = describe(tn, (it + 1) & 1);
+            load_tile(nxt);
         }
 
         // ---- decoupled look-back over this chain's earlier tiles
         if (dthread) {
             unsigned int excl = 0;
             if (!chain_head) {
-                int u = (int)t - 1;
-                const int floor_t = (int)first;
+                int u = (int)cur.t - 1;
+                const int floor_t = (int)cur.first;
                 bool done = false;
                 while (!done) {
                     uint32_t w[RX_LOOK];
@@ -371,11 +428,11 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msd_scatter_kernel(MsdScatterPa
                     }
                     u -= RX_LOOK;
                 }
-                st_relaxed<uint32_t>(p.status + (size_t)t * 256 + tid, LB::INCLUSIVE | (excl + cnt));
+                st_relaxed<uint32_t>(p.status + (size_t)cur.t * 256 + tid, LB::INCLUSIVE | (excl + cnt));
             }
             s_gbase[tid] = bin + excl - doff;
         }
-        __syncthreads();
+        __syncthreads();                                                                     // (D)
 
         // ---- write out: consecutive threads -> consecutive addresses inside each digit run
         uint32_t *kout = p.keys_out;
@@ -390,12 +447,17 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msd_scatter_kernel(MsdScatterPa
 #pragma unroll
             for (int k = 0; k < ITEMS; ++k) {
                 const int i = tid + k * NT;
-                if (i < valid) {
+                if (i < cur.valid) {
                     const uint32_t key = s_keys[i];
                     kout[s_gbase[(key >> SHIFT) & 0xFFu] + (unsigned int)i] = key;
                 }
             }
         }
+        if (!have_next) break;
+        cur = nxt;
+        // Hazards into the next iteration: s_hist was re-zeroed by its owner before (B); the next scatter into s_keys
+        // and the next s_gbase / s_doff / s_seg / s_tk writes all sit behind barrier (A) of the next iteration, which no
+        // thread passes before every thread has finished the write-out above.
     }
 }
 
@@ -409,11 +471,39 @@ struct MsdLeafParams {
     unsigned int want_mode;
 };
 
+constexpr int MSD_LEAF_CHUNK = 6;      // global loads in flight per thread in phases A / B
+constexpr int MSD_LEAF_BIG = 512;      // byte-1 groups longer than this are finished by the whole CTA, not one warp
+
+// Exclusive scan of one value per thread over the first 256 threads (8 warps); all threads must call it.
+// Returns the exclusive prefix for tid < 256; `s_wsum` is an 8-word scratch.  Ends with the barrier that makes the
+// caller's subsequent shared-memory writes of the result safe to read.
+__device__ __forceinline__ unsigned int msd_scan256(unsigned int cnt, int tid, unsigned int *s_wsum) {
+    const int lane = tid & 31, warp = tid >> 5;
+    unsigned int incl = cnt;
+    if (warp < 8) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+    }
+    __syncthreads();
+    unsigned int wbase = 0;
+    if (warp < 8) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) wbase += (w < warp) ? s_wsum[w] : 0u;
+    }
+    return wbase + incl - cnt;
+}
+
 template <int NT, int ITEMS, bool IDENT>
 __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) msd_leaf_kernel(MsdLeafParams p) {
     constexpr int CAP = NT * ITEMS;
     constexpr int NW = NT / 32;
+    constexpr int CH = MSD_LEAF_CHUNK;
     static_assert(CAP < 65536, "16-bit ranks");
+    static_assert(ITEMS % CH == 0, "whole chunks");
     extern __shared__ __align__(16) unsigned char s_raw[];
     uint32_t *S = reinterpret_cast<uint32_t *>(s_raw);                 // [CAP] keys grouped by byte 1
     unsigned int *s_wc = reinterpret_cast<unsigned int *>(S + CAP);    // [NW][256] per-warp byte-0 counters
@@ -421,73 +511,111 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) msd_leaf_kernel(MsdLe
     __shared__ unsigned int s_gstart[256];
     __shared__ unsigned int s_gcnt[256];
     __shared__ unsigned int s_wsum[8];
-    __shared__ unsigned int s_tk[2];
+    __shared__ unsigned int s_wsum2[8];
+    __shared__ unsigned int s_nbig;
+    __shared__ unsigned short s_big[CAP / MSD_LEAF_BIG + 1];
 
     if (ld_cg_u32(&p.ctl->mode) != p.want_mode) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int nne = ld_cg_u32(&p.ctl->nne);
     unsigned int *wc = s_wc + warp * 256;
+    // Segments are dealt round-robin to the persistent CTAs (every segment is independent: no ticket needed); the
+    // bounds of the next segment and the id of the one after are loaded one iteration early (every thread loads the
+    // same words: one broadcast request per warp, no shared-memory hand-off).
+    const unsigned int G = gridDim.x;
+    unsigned int k = blockIdx.x;
+    if (k >= nne) return;
+    unsigned int lo, hi, seg_n1 = 0;
+    {
+        const unsigned int seg0 = __ldg(p.seg_list + k);
+        lo = __ldg(p.seg_start + seg0);
+        hi = __ldg(p.seg_start + seg0 + 1);
+        if (k + G < nne) seg_n1 = __ldg(p.seg_list + k + G);
+    }
 
-    for (unsigned int it = 0;; ++it) {
-        if (tid == 0) s_tk[it & 1] = atomicAdd(&p.ctl->ticket_leaf, 1u);
+    for (; k < nne; k += G) {
+        unsigned int nlo = 0, nhi = 0, seg_n2 = 0;
+        if (k + G < nne) { nlo = __ldg(p.seg_start + seg_n1); nhi = __ldg(p.seg_start + seg_n1 + 1); }
+        if (k + 2 * G < nne) seg_n2 = __ldg(p.seg_list + k + 2 * G);
+        if (tid == 0) s_nbig = 0;
         if (tid < 256) s_hist[tid] = 0;
         __syncthreads();
-        const unsigned int k = s_tk[it & 1];
-        if (k >= nne) break;
-        const unsigned int seg = p.seg_list[k];
-        const unsigned int lo = p.seg_start[seg];
-        const int m = (int)(p.seg_start[seg + 1] - lo);      // 1 <= m <= CAP (plan kernel)
+        const int m = (int)(hi - lo);                        // 1 <= m <= CAP (plan kernel)
         uint32_t *base = p.keys + lo;
 
-        // ---- A: rank by byte 1 (one shared atomic per key); the keys are re-read from L2 in B
+        // ---- A: rank by byte 1 (one shared atomic per key); the keys are re-read from L2 in B.
+        // Loads go out CH at a time: a load -> atomic -> load chain would expose one L2 round trip per key.
+        // Chunks that lie entirely inside the segment (all but the last) run without per-key predicates.
         PackedRanks<ITEMS> ranks;
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            if (j * NT >= m) break;
-            const int i = j * NT + tid;
-            unsigned int r = 0;
-            if (i < m) r = atomicAdd(&s_hist[(ld_coh(base + i) >> 8) & 0xFFu], 1u);
-            ranks.set(j, r);
-        }
-        __syncthreads();
-        unsigned int cnt = 0, incl = 0;
-        if (tid < 256) cnt = s_hist[tid];
-        incl = cnt;
-        if (warp < 8) {
+        for (int j0 = 0; j0 < ITEMS; j0 += CH) {
+            if (j0 * NT >= m) break;
+            uint32_t kk[CH];
+            if ((j0 + CH) * NT <= m) {
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += up;
+                for (int c = 0; c < CH; ++c) kk[c] = ld_keep_l2(base + (j0 + c) * NT + tid);
+#pragma unroll
+                for (int c = 0; c < CH; ++c) ranks.set(j0 + c, atomicAdd(&s_hist[(kk[c] >> 8) & 0xFFu], 1u));
+            } else {
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const int i = (j0 + c) * NT + tid;
+                    kk[c] = i < m ? ld_keep_l2(base + i) : 0u;
+                }
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const int i = (j0 + c) * NT + tid;
+                    unsigned int r = 0;
+                    if (i < m) r = atomicAdd(&s_hist[(kk[c] >> 8) & 0xFFu], 1u);
+                    ranks.set(j0 + c, r);
+                }
             }
-            if (lane == 31) s_wsum[warp] = incl;
         }
         __syncthreads();
-        if (tid < 256) {
-            unsigned int wbase = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) wbase += (w < warp) ? s_wsum[w] : 0u;
-            s_gstart[tid] = wbase + incl - cnt;
-            s_gcnt[tid] = cnt;
+        {
+            const unsigned int cnt = tid < 256 ? s_hist[tid] : 0u;
+            const unsigned int ex = msd_scan256(cnt, tid, s_wsum);
+            if (tid < 256) {
+                s_gstart[tid] = ex;
+                s_gcnt[tid] = cnt;
+                if (cnt > MSD_LEAF_BIG) s_big[atomicAdd(&s_nbig, 1u)] = (unsigned short)tid;
+            }
         }
         __syncthreads();
+        const int nbig = (int)s_nbig;
 
         // ---- B: scatter into shared memory, grouped by byte 1
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            if (j * NT >= m) break;
-            const int i = j * NT + tid;
-            if (i < m) {
-                const uint32_t key = ld_coh(base + i);
-                S[s_gstart[(key >> 8) & 0xFFu] + ranks.get(j)] = key;
+        for (int j0 = 0; j0 < ITEMS; j0 += CH) {
+            if (j0 * NT >= m) break;
+            uint32_t kk[CH];
+            if ((j0 + CH) * NT <= m) {
+#pragma unroll
+                for (int c = 0; c < CH; ++c) kk[c] = ld_coh(base + (j0 + c) * NT + tid);
+#pragma unroll
+                for (int c = 0; c < CH; ++c) S[s_gstart[(kk[c] >> 8) & 0xFFu] + ranks.get(j0 + c)] = kk[c];
+            } else {
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const int i = (j0 + c) * NT + tid;
+                    kk[c] = i < m ? ld_coh(base + i) : 0u;
+                }
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const int i = (j0 + c) * NT + tid;
+                    if (i < m) S[s_gstart[(kk[c] >> 8) & 0xFFu] + ranks.get(j0 + c)] = kk[c];
+                }
             }
         }
         __syncthreads();
 
         // ---- C: every warp finishes whole byte-1 groups: counting sort on byte 0 into the final place.
         // All keys of a group share their top 24 bits, so keys with equal byte 0 are identical: any order.
+        // Groups of up to 96 keys (the common case: 64 on average for 2^30 uniform keys) keep their keys in three
+        // registers per lane between the count and the place step; longer ones loop over shared memory.
         for (int g = warp; g < 256; g += NW) {
             const int gc = (int)s_gcnt[g];
-            if (gc == 0) continue;
+            if (gc == 0 || gc > MSD_LEAF_BIG) continue;
             const unsigned int gs = s_gstart[g];
             if (gc == 1) {
                 if (lane == 0) {
@@ -498,8 +626,23 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) msd_leaf_kernel(MsdLe
             }
             reinterpret_cast<uint4 *>(wc)[lane] = make_uint4(0, 0, 0, 0);
             reinterpret_cast<uint4 *>(wc)[lane + 32] = make_uint4(0, 0, 0, 0);
+            const bool small = gc <= 96;
+            const bool v0 = lane < gc, v1 = lane + 32 < gc, v2 = lane + 64 < gc;
+            uint32_t k0 = 0, k1 = 0, k2 = 0;
+            if (small) {
+                if (v0) k0 = S[gs + lane];
+                if (v1) k1 = S[gs + 32 + lane];
+                if (v2) k2 = S[gs + 64 + lane];
+            }
             __syncwarp();
-            for (int r = lane; r < gc; r += 32) atomicAdd(&wc[S[gs + r] & 0xFFu], 1u);
+            if (small) {
+                if (v0) atomicAdd(&wc[k0 & 0xFFu], 1u);
+                if (v1) atomicAdd(&wc[k1 & 0xFFu], 1u);
+                if (v2) atomicAdd(&wc[k2 & 0xFFu], 1u);
+            } else {
+#pragma unroll 1
+                for (int r = lane; r < gc; r += 32) atomicAdd(&wc[S[gs + r] & 0xFFu], 1u);
+            }
             __syncwarp();
             // lane owns counters 8 lane .. 8 lane + 7
             uint4 a = reinterpret_cast<uint4 *>(wc)[2 * lane], b = reinterpret_cast<uint4 *>(wc)[2 * lane + 1];
@@ -517,13 +660,43 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) msd_leaf_kernel(MsdLe
             reinterpret_cast<uint4 *>(wc)[2 * lane] = oa;
             reinterpret_cast<uint4 *>(wc)[2 * lane + 1] = ob;
             __syncwarp();
-            for (int r = lane; r < gc; r += 32) {
-                const uint32_t key = S[gs + r];
-                const unsigned int pos = atomicAdd(&wc[key & 0xFFu], 1u);
-                base[gs + pos] = IDENT ? key : key_decode<uint32_t>(key, p.xf);
+            uint32_t *gout = base + gs;
+            if (small) {
+                if (v0) gout[atomicAdd(&wc[k0 & 0xFFu], 1u)] = IDENT ? k0 : key_decode<uint32_t>(k0, p.xf);
+                if (v1) gout[atomicAdd(&wc[k1 & 0xFFu], 1u)] = IDENT ? k1 : key_decode<uint32_t>(k1, p.xf);
+                if (v2) gout[atomicAdd(&wc[k2 & 0xFFu], 1u)] = IDENT ? k2 : key_decode<uint32_t>(k2, p.xf);
+            } else {
+#pragma unroll 1
+                for (int r = lane; r < gc; r += 32) {
+                    const uint32_t key = S[gs + r];
+                    gout[atomicAdd(&wc[key & 0xFFu], 1u)] = IDENT ? key : key_decode<uint32_t>(key, p.xf);
+                }
             }
             __syncwarp();
         }
+
+        // ---- C': long groups (skewed byte 1) are finished by the whole CTA, one after the other
+        for (int b = 0; b < nbig; ++b) {
+            const int g = s_big[b];
+            const int gc = (int)s_gcnt[g];
+            const unsigned int gs = s_gstart[g];
+            __syncthreads();                       // previous user of s_hist is done
+            if (tid < 256) s_hist[tid] = 0;
+            __syncthreads();
+            for (int r = tid; r < gc; r += NT) atomicAdd(&s_hist[S[gs + r] & 0xFFu], 1u);
+            __syncthreads();
+            const unsigned int cnt = tid < 256 ? s_hist[tid] : 0u;
+            const unsigned int ex = msd_scan256(cnt, tid, s_wsum2);
+            if (tid < 256) s_hist[tid] = ex;
+            __syncthreads();
+            for (int r = tid; r < gc; r += NT) {
+                const uint32_t key = S[gs + r];
+                const unsigned int pos = atomicAdd(&s_hist[key & 0xFFu], 1u);
+                base[gs + pos] = IDENT ? key : key_decode<uint32_t>(key, p.xf);
+            }
+        }
+        if (nbig) __syncthreads();                 // s_hist is zeroed at the top of the next iteration
+        lo = nlo; hi = nhi; seg_n1 = seg_n2;
     }
 }
 

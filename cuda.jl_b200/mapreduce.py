@@ -44,15 +44,14 @@ INIT_NEUTRAL, INIT_FROM_OUT = 0, 1
 
 
 def neutral_element(op, eltype):
-    """GPUArrays.neutral_element(op, T) for the grafted ops (SURVEY §8 a1')."""
+    """GPUArrays.neutral_element(op, T) for the grafted ops (SURVEY §8 a1').  NB: for `&` this is one(T), which is
+    the true neutral element only for Bool — see `true_neutral`."""
     npdt = dt.np_dtype(eltype)
     isf = eltype in dt.FLOATS
     if op in (add, add_sum, or_):
         return npdt.type(0)
-    if op in (mul, mul_prod):
+    if op in (mul, mul_prod, and_):
         return npdt.type(1)
-    if op is and_:
-        return npdt.type(1) if eltype == dt.BOOL else npdt.type(~np.uint64(0)) if eltype in dt.UNSIGNED else npdt.type(-1)
     if op is max_:
         return npdt.type(-np.inf) if isf else (npdt.type(False) if eltype == dt.BOOL else np.iinfo(npdt).min)
     if op is min_:
@@ -60,9 +59,22 @@ def neutral_element(op, eltype):
     raise NotGraftedError(f"no neutral element for {op}")
 
 
+def true_neutral(op, eltype):
+    """The element e with op(e, x) == x for every x (lib/B200Arrays/src/mapreduce.jl `true_neutral`).  Differs from
+    GPUArrays.neutral_element for integer `&` (all-ones, not one(T)): the reference seeds every thread with the
+    value it is given (mapreduce.jl:114,148), so `reduce(&, ints)` with GPUArrays' one(T) is not a plain AND and stays
+    on the reference path."""
+    if op is and_ and eltype != dt.BOOL:
+        if eltype in dt.FLOATS:
+            raise NotGraftedError("bitwise ops on floats")
+        npdt = dt.np_dtype(eltype)
+        return npdt.type(~np.uint64(0)) if eltype in dt.UNSIGNED else npdt.type(-1)
+    return neutral_element(op, eltype)
+
+
 def _is_neutral(op, eltype, init):
     try:
-        ne = neutral_element(op, eltype)
+        ne = true_neutral(op, eltype)
     except NotGraftedError:
         return False
     a = np.asarray(init).astype(dt.np_dtype(eltype))

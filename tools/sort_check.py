@@ -95,8 +95,10 @@ def run(n, e, dist, rev, reps=3):
 def main():
     logs = [int(a) for a in sys.argv[1:]] or [27, 28, 30]
     all_ok = True
-    if os.environ.get("SORT_CHECK_ONE"):            # one case only (for ncu launch lists)
-        ok = run(1 << logs[0], dt.U32, os.environ["SORT_CHECK_ONE"], False, reps=2)
+    if os.environ.get("SORT_CHECK_ONE"):            # listed distributions only, UInt32 (ncu launch lists, A/B timing)
+        ok = True
+        for dist in os.environ["SORT_CHECK_ONE"].split(","):
+            ok &= run(1 << logs[0], dt.U32, dist, False, reps=int(os.environ.get("SORT_CHECK_REPS", "2")))
         sys.exit(0 if ok else 1)
     for lg in logs:
         n = 1 << lg
