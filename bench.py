@@ -383,6 +383,12 @@ def run_comparators(b, dt, torch, dev):
         R = None
         out["reference_algorithms"] = f"unavailable: {e}"
     stream = torch.cuda.current_stream(dev).cuda_stream
+    try:
+        import cub_baseline as C
+        C.lib()
+    except Exception as e:
+        C = None
+        out["cub"] = f"unavailable: {e}"
 
     def tmed(fn, reps, pre=None):
         ts = []
@@ -414,12 +420,16 @@ def run_comparators(b, dt, torch, dev):
     r1 = torch.empty(1, device=dev, dtype=torch.float32)
     d = {}
     fn = lambda: torch.sum(V); fn(); d["torch_ms"] = tmed(fn, 5)
+    if C is not None:
+        fn = C.call("cub_sum_f32", torch, dev, V.data_ptr(), r1.data_ptr(), n=n, stream=stream); fn(); d["cub_ms"] = tmed(fn, 5)
     if R is not None:
         fn = lambda: R.sum_f32(V.data_ptr(), r1.data_ptr(), part.data_ptr(), 1, n, 1, stream); fn(); d["reference_algorithm_ms"] = tmed(fn, 5)
     out["sum 2^30 Float32"] = d
     O = torch.empty_like(V)
     d = {}
     fn = lambda: torch.cumsum(V, 0, out=O); fn(); d["torch_ms"] = tmed(fn, 3)
+    if C is not None:
+        fn = C.call("cub_inclusive_sum_f32", torch, dev, V.data_ptr(), O.data_ptr(), n=n, stream=stream); fn(); d["cub_ms"] = tmed(fn, 3)
     if R is not None:
         scratch = torch.empty(n // 512 + 4096, device=dev, dtype=torch.float32)
         fn = lambda: R.cumsum(V.data_ptr(), O.data_ptr(), scratch.data_ptr(), n, stream); fn(); d["reference_algorithm_ms"] = tmed(fn, 3)
@@ -428,9 +438,24 @@ def run_comparators(b, dt, torch, dev):
     del O
     d = {}
     fn = lambda: torch.sort(V); fn(); d["torch_ms"] = tmed(fn, 2)
+    d["torch_note"] = "torch.sort returns values AND Int64 indices (a pairs sort)"
+    if C is not None:
+        O = torch.empty_like(V)
+        fn = C.call("cub_sort_keys_f32", torch, dev, V.data_ptr(), O.data_ptr(), n=n, stream=stream); fn(); d["cub_sort_keys_ms"] = tmed(fn, 3)
+        vi = torch.arange(n, device=dev, dtype=torch.int32); vo = torch.empty_like(vi)
+        fn = C.call("cub_sort_pairs_f32_u32", torch, dev, V.data_ptr(), O.data_ptr(), vi.data_ptr(), vo.data_ptr(), n=n, stream=stream)
+        fn(); d["cub_sort_pairs_u32_payload_ms"] = tmed(fn, 3)
+        del O, vi, vo
     out["sort 2^30 Float32"] = d
     del V, part
     torch.cuda.empty_cache()
+    if C is not None:
+        U = torch.randint(-2**31, 2**31 - 1, (n,), device=dev, generator=g, dtype=torch.int32)
+        O = torch.empty_like(U)
+        fn = C.call("cub_sort_keys_u32", torch, dev, U.data_ptr(), O.data_ptr(), n=n, stream=stream); fn()
+        out["sort! 2^30 UInt32 (CUB DeviceRadixSort::SortKeys)"] = {"cub_ms": tmed(fn, 3), "Gkeys/s": n / tmed(fn, 3) / 1e6}
+        del U, O
+        torch.cuda.empty_cache()
     if R is not None:
         U = torch.randint(-2**31, 2**31 - 1, (n,), device=dev, generator=g, dtype=torch.int32)
         K = U.clone()
@@ -442,7 +467,9 @@ def run_comparators(b, dt, torch, dev):
         del U, K
     torch.cuda.empty_cache()
     out["_labels"] = {"reference_algorithm": "restatement of CUDA.jl's algorithm + launch structure in CUDA C++ (nvcc, not Julia-JIT): "
-                                            "bench/baselines/ref_algos.cu", "torch": "torch 2.11 (CUB) library comparator"}
+                                            "bench/baselines/ref_algos.cu", "torch": "torch 2.11 (CUB) library comparator",
+                      "cub": "CUB DeviceReduce / DeviceScan / DeviceRadixSort of the CUDA 12.9 toolkit called directly "
+                             "(bench/baselines/cub_baseline.cu)"}
     return out
 
 
@@ -597,10 +624,57 @@ def run_extras(b, dt, torch, dev, peak):
     del I, cI, O
     torch.cuda.empty_cache()
     try:
+        out["configs[0] 2^24 Float32: Base Julia CPU path (port) beside the graft"] = run_configs0(b, dt, torch, dev)
+    except Exception as e:
+        out["configs[0] 2^24 Float32: Base Julia CPU path (port) beside the graft"] = {"error": repr(e)}
+    try:
         out["comparators"] = run_comparators(b, dt, torch, dev)
     except Exception as e:  # baselines are reported numbers, never the product path
         out["comparators"] = {"error": repr(e)}
     return out
+
+
+def run_configs0(b, dt, torch, dev):
+    """BASELINE.json configs[0]: sum / cumsum / sort! / sortperm on a 2^24-element Float32 Array via Base Julia's CPU
+    path — here its C restatement (oracle/oracle_cpu.c, single thread like Base) — next to the same calls on the GPU
+    through the public API, data resident.  For sort both CPU algorithms SURVEY section 8(d) asks for are timed: LSD radix
+    (what Julia >= 1.9 picks for large Float32 vectors) and a comparison sort."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_cpu as oc
+    n = 1 << 24
+    rng = np.random.default_rng(0xB200)
+    a = rng.random(n).astype(np.float32)
+
+    def cpu(fn, reps=2):
+        best = None
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); t = (time.perf_counter() - t0) * 1e3
+            best = t if best is None else min(best, t)
+        return best
+
+    def gpu(fn, reps=5, pre=None):
+        ts = []
+        for _ in range(reps + 1):
+            if pre is not None:
+                pre()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record(); e.synchronize()
+            ts.append(s.elapsed_time(e))
+        return float(np.median(ts[1:]))
+
+    cA = b.CuArray(a)
+    R = b.CuArray.undef(dt.F32, (1,)); O = b.CuArray.undef(dt.F32, (n,)); K = cA.copy()
+    res = {
+        "sum": {"cpu_ms": cpu(lambda: oc.sum_f32(a)), "gpu_ms": gpu(lambda: b.mapreducedim_(b.identity, b.add_sum, R, cA, init=0))},
+        "cumsum": {"cpu_ms": cpu(lambda: oc.cumsum(a)), "gpu_ms": gpu(lambda: b.accumulate_(b.add, O, cA))},
+        "sort!": {"cpu_radix_ms": cpu(lambda: oc.sort(a)), "cpu_comparison_sort_ms": cpu(lambda: oc.sort_cmp(a), reps=1),
+                  "gpu_ms": gpu(lambda: b.sort_(K), pre=lambda: K.buf.copy_(cA.buf))},
+        "sortperm": {"cpu_ms": cpu(lambda: oc.sortperm(a), reps=1), "gpu_ms": gpu(lambda: b.sortperm(cA))},
+        "cpu": {"cores": 1, "host_cores": os.cpu_count(), "kind": "port",
+                "note": "Base Julia's sum / cumsum / sort! / sortperm are single-threaded (Threads.nthreads() is irrelevant); "
+                        "oracle/oracle_cpu.c restates their algorithms; the sort timings include one copy of the input"},
+    }
+    return res
 
 
 _REAL_STDOUT = sys.stdout

@@ -28,6 +28,7 @@ SIGNATURES = {
     "b200_findminmax": (_i32, [_vp, _sz, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _i64, _vp]),
     "b200_scan_workspace_bytes": (_i32, [_i32, _i32, _i32, _i64, _i64, _i64, _c.POINTER(_sz)]),
     "b200_scan": (_i32, [_vp, _sz, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _vp, _vp]),
+    "b200_scan_carry": (_i32, [_vp, _sz, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _vp, _vp, _i32, _vp]),
     "b200_sort_workspace_bytes": (_i32, [_i32, _i32, _i64, _i64, _c.POINTER(_sz)]),
     "b200_sort_keys": (_i32, [_vp, _sz, _vp, _i32, _i64, _i64, _i32, _vp]),
     "b200_sortperm": (_i32, [_vp, _sz, _vp, _vp, _i32, _i32, _i64, _i64, _i32, _i32, _vp]),

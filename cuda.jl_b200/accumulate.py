@@ -21,9 +21,11 @@ def _factor(dims_tuple, dims):
     return pre, n, post
 
 
-def scan_(f, output, input, dims, init=None, exclusive=False):
+def scan_(f, output, input, dims, init=None, exclusive=False, carry=None, carry_count=0):
     """CUDACore.scan!(f, output, input; dims, init) (accumulate.jl:135).  `init` is the x of
-    Some(x).  `exclusive=True` is the extra variant BASELINE config 3 names."""
+    Some(x).  `exclusive=True` is the extra variant BASELINE config 3 names.  `carry` (a device CuArray of the
+    accumulator type) with `carry_count` is the sharded scan's device-side carry (b200_scan_carry): its first
+    carry_count values are folded into the seed on the device, no host round trip."""
     if f not in _SCAN_OPS:
         raise NotGraftedError(f"scan!({f}, ...) stays on the reference's generic kernels")
     if not (isinstance(dims, (int, np.integer)) and dims > 0):
@@ -46,6 +48,12 @@ def scan_(f, output, input, dims, init=None, exclusive=False):
     opcode = _SCAN_OPS[f]
     _lib.check(lib.b200_scan_workspace_bytes(input.eltype, output.eltype, opcode, pre, n, post, ctypes.byref(nbytes)))
     ws = Workspace(nbytes.value, input.buf.device)
+    if carry is not None and carry_count > 0:
+        _lib.check(lib.b200_scan_carry(ws.ptr, ws.nbytes, input.pointer, output.pointer, input.eltype, output.eltype,
+                                       opcode, 1 if exclusive else 0, pre, n, post,
+                                       init_buf.ctypes.data if init_buf is not None else None,
+                                       carry.pointer, int(carry_count), current_stream_handle(input.buf.device)))
+        return output
     _lib.check(lib.b200_scan(ws.ptr, ws.nbytes, input.pointer, output.pointer, input.eltype, output.eltype, opcode,
                              1 if exclusive else 0, pre, n, post,
                              init_buf.ctypes.data if init_buf is not None else None,

@@ -55,8 +55,23 @@ struct ScanParams {
     int32_t exclusive;
     int32_t has_init;
     uint64_t init_bits;            // the Some(x) value, bit pattern of the accumulator type
+    const void *carry_dev;         // optional DEVICE array of accumulator-typed values folded (in order) into the seed:
+    int32_t carry_count;           // the totals of the shards before this one in a sharded scan (no host round trip)
     int32_t chain_at;              // scan_chain2_kernel: 0 = status prefetch before barrier (A), 1 = after the publication
 };
+
+template <class A> __device__ __forceinline__ A bits_to_acc(uint64_t bits);
+
+// What every chain of the scan starts from: init (a host value) and / or the device-side carry values, else the
+// operator's identity.  Evaluated where a segment's FIRST tile is seeded only.
+template <class A, class Op> __device__ __forceinline__ A scan_seed(const ScanParams &p) {
+    A s = p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity();
+    if (p.carry_dev != nullptr) {
+        const A *c = static_cast<const A *>(p.carry_dev);
+        for (int i = 0; i < p.carry_count; ++i) s = Op::apply(s, c[i]);
+    }
+    return s;
+}
 
 __device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
@@ -154,7 +169,7 @@ __device__ __forceinline__ typename Op::acc_t tile_lookback(const ScanParams &p,
     uint64_t *slots = p.status + seg * p.tiles_per_seg * NW;
     A prefix;
     if (t == 0) {
-        prefix = p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity();
+        prefix = scan_seed<A, Op>(p);
         if (lane == 0 && p.tiles_per_seg > 1) publish<A>(slots, SC_INCLUSIVE, Op::apply(prefix, tile_agg));
         return prefix;
     }
@@ -675,7 +690,7 @@ __global__ void __launch_bounds__(NT) scan_pipe_kernel(ScanParams p) {
             uint64_t *slots = p.status + seg * p.tiles_per_seg * NW;
             if (t == 0) {
                 if (p.tiles_per_seg > 1) {
-                    const A seed = p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity();
+                    const A seed = scan_seed<A, Op>(p);
                     publish<A>(slots, SC_INCLUSIVE, Op::apply(seed, tile_agg));
                 }
             } else {
@@ -898,7 +913,7 @@ __global__ void __launch_bounds__(NT + 32) scan_chain2_kernel(ScanParams p) {
             uint64_t *slots = p.status + seg * p.tiles_per_seg * NW;
             if (t == 0) {
                 if (p.tiles_per_seg > 1) {
-                    const A seed = p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity();
+                    const A seed = scan_seed<A, Op>(p);
                     publish<A>(slots, SC_INCLUSIVE, Op::apply(seed, tile_agg));
                 }
             } else {
@@ -984,7 +999,7 @@ __global__ void __launch_bounds__(NT + 32) scan_chain2_kernel(ScanParams p) {
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) val = Op::apply(val, shfl_xor_any(val, o));
-        const A base = pf_base == 0 ? (p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity())
+        const A base = pf_base == 0 ? scan_seed<A, Op>(p)
                      : pf_base == 1 ? Op::identity() : incl_own;
         return Op::apply(base, val);
     };
@@ -1266,7 +1281,7 @@ __global__ void __launch_bounds__(NT + 32) scan_pipe_ws_kernel(ScanParams p) {
             uint64_t *slots = p.status + seg * p.tiles_per_seg * NW;
             if (t == 0) {
                 if (p.tiles_per_seg > 1) {
-                    const A seed = p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity();
+                    const A seed = scan_seed<A, Op>(p);
                     publish<A>(slots, SC_INCLUSIVE, Op::apply(seed, tile_agg));
                 }
             } else {
@@ -1348,7 +1363,7 @@ __global__ void __launch_bounds__(256) scan_strided_kernel(ScanParams p) {
     const int64_t j = o / p.pre, i = o - j * p.pre;
     const Tin *in = static_cast<const Tin *>(p.in) + i + p.pre * p.n * j;
     Tout *out = static_cast<Tout *>(p.out) + i + p.pre * p.n * j;
-    A acc = p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity();
+    A acc = scan_seed<A, Op>(p);
     constexpr int U = 8;
     int64_t r = 0;
     for (; r + U <= p.n; r += U) {
@@ -1404,7 +1419,7 @@ __global__ void __launch_bounds__(256) scan_strided_lb_kernel(ScanParams p, int6
     const int64_t rstride = cols * NW;
     A prefix;
     if (rt == 0) {
-        prefix = p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity();
+        prefix = scan_seed<A, Op>(p);
         if (nrt > 1) publish<A>(slots, SC_INCLUSIVE, Op::apply(prefix, agg));
     } else {
         publish<A>(slots + rt * rstride, SC_PARTIAL, agg);
@@ -1477,7 +1492,7 @@ __global__ void __launch_bounds__(256) scan_fewcols_kernel(ScanParams p, int col
         const int64_t gstride = (int64_t)cols * NW;
         A prefix;
         if (g == 0) {
-            prefix = p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity();
+            prefix = scan_seed<A, Op>(p);
             if (nctas > 1) publish<A>(slots, SC_INCLUSIVE, Op::apply(prefix, total));
         } else {
             publish<A>(slots + g * gstride, SC_PARTIAL, total);
@@ -1522,7 +1537,7 @@ __global__ void __launch_bounds__(256) scan_warpseg_kernel(ScanParams p) {
     const Tin *tin = static_cast<const Tin *>(p.in) + seg * p.n;
     Tout *tout = static_cast<Tout *>(p.out) + seg * p.n;
     constexpr int STEP = 32 * EPC;
-    A carry = p.has_init ? bits_to_acc<A>(p.init_bits) : Op::identity();
+    A carry = scan_seed<A, Op>(p);
     A nxt[EPC];
     load_chunk<Tin, A, Op, EPC>(tin, (int64_t)lane * EPC, p.n, nxt);
     for (int64_t base = 0; base < p.n; base += STEP) {
@@ -1567,12 +1582,15 @@ template <class Tin, class Tout> struct ScanShape {
 
 template <class Tin, class Tout, class Op>
 int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_t pre, int64_t n, int64_t post,
-                    int exclusive, const void *init_host, cudaStream_t stream, size_t *query_bytes) {
+                    int exclusive, const void *init_host, const void *carry_dev, int carry_count, cudaStream_t stream,
+                    size_t *query_bytes) {
     using A = typename Op::acc_t;
     using S = ScanShape<Tin, Tout>;
     constexpr int NW = StatusWords<A>::NW;
     ScanParams p{};
     p.in = in; p.out = out; p.pre = pre; p.n = n; p.post = post; p.exclusive = exclusive;
+    p.carry_dev = carry_count > 0 ? carry_dev : nullptr;
+    p.carry_count = carry_count;
     p.has_init = init_host != nullptr;
     if (init_host) {
         // init arrives as a value of the OUTPUT element type; convert to the accumulator

@@ -98,9 +98,10 @@ template <class LookT> static int32_t dispatch_pass(const OnesweepParams &p, int
 #if B200_KEY_BYTES == 4
 // ---- hybrid MSD path (sort_msd.cuh): dense 32-bit keys-only sorts -------------------------------------------
 constexpr int MSD_NT = 512, MSD_ITEMS = 20, MSD_TILE = MSD_NT * MSD_ITEMS;      // P1 / P2 tile
-constexpr int LEAF_A_NT = 512, LEAF_A_ITEMS = 36;                              // 18432 keys, 2 CTAs per SM
-constexpr int LEAF_B_NT = 1024, LEAF_B_ITEMS = 36;                             // 36864 keys, 1 CTA per SM
-constexpr unsigned int MSD_MIN_AVG = 6144;   // counting leaf: 65536 / (keys per segment) counters scanned per key
+constexpr int LEAF_NT = 512;
+constexpr unsigned int LEAF8_CAP = 32768;    // segments up to this many keys go to the 8-bit-bin leaf first
+constexpr unsigned int LEAF_MAX_SEG = 65535; // 16-bit bins cannot overflow up to here; longer segments: LSD fallback
+constexpr unsigned int MSD_MIN_AVG = 3072;   // counting leaf: 65536 bins are walked per segment whatever its length
 constexpr int64_t MSD_MIN_N = 1LL << 27;     // below this even a full key range cannot reach MSD_MIN_AVG ... per
                                              // non-empty segment unless the keys sit in a narrow range; not worth the histogram
 constexpr int64_t MSD_MAX_N = 1LL << 30;     // 32-bit look-back words carry 30-bit counts
@@ -109,7 +110,7 @@ static bool xform_is_identity(const SortXform &x) { return x.base_enc == 0 && x.
 
 struct MsdBuffers {
     MsdCtl *ctl;
-    unsigned int *hist16, *status1, *status2, *seg_start, *seg_list, *l1_tile_start;
+    unsigned int *hist16, *status1, *status2, *redo, *seg_start, *seg_list, *l1_tile_start;
 };
 
 template <bool IDENT>
@@ -132,7 +133,7 @@ static int32_t msd_launch(const SortCall &c, const MsdBuffers &b, uint32_t *alt,
         MsdPlanParams pp{};
         pp.hist16 = b.hist16; pp.seg_start = b.seg_start; pp.seg_list = b.seg_list; pp.l1_tile_start = b.l1_tile_start;
         pp.ctl = b.ctl; pp.n = (unsigned int)n; pp.tile2 = MSD_TILE;
-        pp.cap_a = LEAF_A_NT * LEAF_A_ITEMS; pp.cap_b = LEAF_B_NT * LEAF_B_ITEMS;
+        pp.cap_a = LEAF_MAX_SEG; pp.cap_b = 0;
         static const unsigned int min_avg = (unsigned int)tune_int("B200_MSD_MIN_AVG", (int)MSD_MIN_AVG);
         pp.min_avg = min_avg;
         msd_plan_kernel<<<1, 1024, 0, st>>>(pp);
@@ -169,26 +170,25 @@ static int32_t msd_launch(const SortCall &c, const MsdBuffers &b, uint32_t *alt,
     }
     MsdLeafParams lp{};
     lp.keys = static_cast<uint32_t *>(c.keys); lp.seg_start = b.seg_start; lp.seg_list = b.seg_list; lp.ctl = b.ctl; lp.xf = c.xf;
-    {   // leaf A (segments up to 18432 keys)
+    lp.redo = b.redo; lp.cap8 = LEAF8_CAP;
+    {   // 8-bit bins: segments up to LEAF8_CAP keys without heavy duplicates
         static thread_local KernelSetup ks;
         int per_sm = 1;
-        auto kern = msd_leaf_kernel<LEAF_A_NT, LEAF_A_ITEMS, IDENT>;
-        const size_t smem = (size_t)LEAF_A_NT * LEAF_A_ITEMS * 4 + (size_t)(LEAF_A_NT / 32) * 1024;
-        int32_t rc = setup_kernel(ks, kern, LEAF_A_NT, smem, &per_sm);
+        auto kern = msd_leaf_kernel<8, LEAF_NT, IDENT>;
+        const size_t smem = (size_t)MSD_BINS;
+        int32_t rc = setup_kernel(ks, kern, LEAF_NT, smem, &per_sm);
         if (rc != B200_OK) return rc;
-        lp.want_mode = 1;
-        kern<<<(unsigned int)(dev.sm_count * per_sm), LEAF_A_NT, smem, st>>>(lp);
+        kern<<<(unsigned int)(dev.sm_count * per_sm), LEAF_NT, smem, st>>>(lp);
         B200_CHECK_LAUNCH();
     }
-    {   // leaf B (segments up to 36864 keys)
+    {   // 16-bit bins: what the 8-bit kernel skipped or gave up on
         static thread_local KernelSetup ks;
         int per_sm = 1;
-        auto kern = msd_leaf_kernel<LEAF_B_NT, LEAF_B_ITEMS, IDENT>;
-        const size_t smem = (size_t)LEAF_B_NT * LEAF_B_ITEMS * 4 + (size_t)(LEAF_B_NT / 32) * 1024;
-        int32_t rc = setup_kernel(ks, kern, LEAF_B_NT, smem, &per_sm);
+        auto kern = msd_leaf_kernel<16, LEAF_NT, IDENT>;
+        const size_t smem = (size_t)MSD_BINS * 2;
+        int32_t rc = setup_kernel(ks, kern, LEAF_NT, smem, &per_sm);
         if (rc != B200_OK) return rc;
-        lp.want_mode = 2;
-        kern<<<(unsigned int)(dev.sm_count * per_sm), LEAF_B_NT, smem, st>>>(lp);
+        kern<<<(unsigned int)(dev.sm_count * per_sm), LEAF_NT, smem, st>>>(lp);
         B200_CHECK_LAUNCH();
     }
     return B200_OK;
@@ -230,6 +230,7 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
         mb.hist16 = w.take<unsigned int>(MSD_BINS);
         mb.status1 = reinterpret_cast<unsigned int *>(status);     // P1 has fewer tiles than an LSD pass
         mb.status2 = w.take<unsigned int>((size_t)(cdiv(n, MSD_TILE) + 256) * RX_RADIX);
+        mb.redo = w.take<unsigned int>(MSD_BINS);
     }
 #endif
     const size_t clear_bytes = w.bytes();

@@ -16,11 +16,12 @@
 //                           the tiles, digit runs written from shared memory) : keys -> alt
 //   P2  msd_scatter_kernel<2>  the same inside each level-1 bucket by key byte 2 (tiles never straddle a bucket,
 //                           the look-back chain restarts at a bucket's first tile)       : alt -> keys
-//   L   msd_leaf_kernel     persistent CTAs take one 16-bit segment (<= CAP keys) at a time: partition it by byte 1
-//                           into shared memory (atomic rank), then every warp finishes whole byte-1 groups with a
-//                           256-counter counting sort on byte 0 straight into the segment's final place (in place)
+//   L   msd_leaf_kernel     persistent CTAs take one 16-bit segment at a time: histogram of its low 16 bits in a packed
+//                           shared-memory table (one atomic per key), then the table is walked in value order and
+//                           every value written `count` times, in place (a keys-only sort of a 16-bit residue IS
+//                           its histogram)
 //
-// ~145 instructions per key in total instead of ~290, three passes over HBM plus the histogram read.
+// ~125 instructions per key in total instead of ~290, three passes over HBM plus the histogram read.
 // Replaces (for this input class) CUDACore/src/sorting.jl:909-974 `bitonic_sort!`; keys keep Julia's `isless`
 // order through key_encode / key_decode exactly as in the LSD path.
 #pragma once
@@ -71,13 +72,14 @@ msd_hist16_kernel(const uint32_t *__restrict__ keys, int64_t n, SortXform xf, un
     if (tid == 0) s_flush = 0;
     __syncthreads();
     // A field is flushed before it can reach 2^16: an iteration adds at most 1024 * 32 = 2^15 to one field, and an
-    // iteration that started with a field above 2^14 is followed by a flush (some add saw bit 14 or 15 set).
-    auto count = [&](uint32_t raw) {
-        const uint32_t key = IDENT ? raw : key_encode<uint32_t>(raw, xf);
+    // iteration in which some add saw a field at or above 2^14 is followed by a flush — so every iteration starts with
+    // all fields <= 2^14 and ends with all fields <= 2^14 + 2^15 < 2^16.
+    auto count_enc = [&](uint32_t key) {
         const uint32_t inc = (key & 0x10000u) ? 0x10000u : 1u;
         const uint32_t old = atomicAdd(&sh16[key >> 17], inc);
         if (old & 0xC000C000u) s_flush = 1;
     };
+    auto count = [&](uint32_t raw) { count_enc(IDENT ? raw : key_encode<uint32_t>(raw, xf)); };
     auto flush = [&]() {
         for (int w = tid; w < MSD_H16_WORDS; w += MSD_H16_THREADS) {
             const uint32_t v = sh16[w];
@@ -102,17 +104,49 @@ msd_hist16_kernel(const uint32_t *__restrict__ keys, int64_t n, SortXform xf, un
     for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
         const int64_t v0 = c * CHUNK_V + tid;
         Vec16 r[MSD_H16_VPT];
+        const bool whole = (c + 1) * CHUNK_V <= nvec;        // uniform: every thread has all its vectors
 #pragma unroll
         for (int k = 0; k < MSD_H16_VPT; ++k) {
             const int64_t v = v0 + (int64_t)k * MSD_H16_THREADS;
-            if (v < nvec) r[k] = ldg_stream16(body + v * 4);
+            if (whole || v < nvec) r[k] = ldg_stream16(body + v * 4);
         }
+        bool uniform = false;
+        if (whole) {
+            // Sorted / clustered input: all 1024 keys of the warp fall into one bin, and 32 lanes adding to one word
+            // serialise.  One extra LOP3 per key finds out; lane 0 then adds the warp's whole count in one atomic.
+            if constexpr (!IDENT) {
 #pragma unroll
-        for (int k = 0; k < MSD_H16_VPT; ++k) {
-            const int64_t v = v0 + (int64_t)k * MSD_H16_THREADS;
-            if (v < nvec) {
+                for (int k = 0; k < MSD_H16_VPT; ++k)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) count(r[k].w[j]);
+                    for (int j = 0; j < 4; ++j) r[k].w[j] = key_encode<uint32_t>(r[k].w[j], xf);
+            }
+            const uint32_t ref = __shfl_sync(0xffffffffu, r[0].w[0], 0);
+            uint32_t diff = 0;
+#pragma unroll
+            for (int k = 0; k < MSD_H16_VPT; ++k)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) diff |= r[k].w[j] ^ ref;
+            uniform = __all_sync(0xffffffffu, (diff >> 16) == 0);
+            if (uniform) {
+                if ((threadIdx.x & 31) == 0) {
+                    const uint32_t inc = ((ref & 0x10000u) ? 0x10000u : 1u) * (32u * MSD_H16_VPT * 4u);
+                    const uint32_t old = atomicAdd(&sh16[ref >> 17], inc);
+                    if (old & 0xC000C000u) s_flush = 1;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < MSD_H16_VPT; ++k)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) count_enc(r[k].w[j]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < MSD_H16_VPT; ++k) {
+                const int64_t v = v0 + (int64_t)k * MSD_H16_THREADS;
+                if (v < nvec) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) count(r[k].w[j]);
+                }
             }
         }
         __syncthreads();
@@ -338,7 +372,28 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msd_scatter_kernel(MsdScatterPa
             for (int i = 0; i < ITEMS; ++i) keys[i] = key_encode<uint32_t>(keys[i], p.xf);
         }
         PackedRanks<ITEMS> ranks;
+        // Sorted / clustered input: every warp row (32 consecutive keys) carries ONE digit, and 10240 atomics on one
+        // shared counter would serialise.  If all of this warp's rows are digit-uniform, lane 0 reserves 32 ranks per
+        // row with a single atomic (~2 extra instructions per row to find out; random data takes the plain path).
+        bool rows_uniform = false;
         if (full) {
+            bool same = true;
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const unsigned int d = (keys[i] >> SHIFT) & 0xFFu;
+                const unsigned int d0 = __shfl_sync(0xffffffffu, d, 0);     // every lane executes every shuffle:
+                same = same & (d == d0);                                     // no short-circuit around a .sync op
+            }
+            rows_uniform = __all_sync(0xffffffffu, same);
+        }
+        if (rows_uniform) {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                unsigned int b = 0;
+                if (lane == 0) b = atomicAdd(&s_hist[(keys[i] >> SHIFT) & 0xFFu], 32u);
+                ranks.set(i, __shfl_sync(0xffffffffu, b, 0) + lane);
+            }
+        } else if (full) {
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) ranks.set(i, atomicAdd(&s_hist[(keys[i] >> SHIFT) & 0xFFu], 1u));
         } else {
@@ -462,241 +517,158 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msd_scatter_kernel(MsdScatterPa
 }
 
 // ------------------------------------------------------------------ L: leaf, one 16-bit segment per CTA iteration
+// All keys of a segment share their top 16 bits, and equal keys are indistinguishable: the sorted segment is fully
+// described by the HISTOGRAM of the low 16 bits.  With dense keys (2^30 keys over a 32-bit range: 4 bins per key) the
+// cheapest sort is therefore: count (one shared atomic per key into a packed 65536-bin table), then walk the table in
+// order and emit every value `count` times.  Per 32 keys: ~60 instructions and ~7 shared-memory wavefronts, against
+// ~106 / 44 for the group-wise counting sort this replaces (profiles/r2_sort_msd_v2.md).
+//
+//   BITS = 8 : four bins per word, 64 KB table, 3 CTAs per SM; a bin that reaches 128 marks the segment in `redo`
+//              (heavy duplicates) and the 16-bit kernel takes it.  Segments longer than CAP8 are skipped (also 16-bit).
+//   BITS = 16: two bins per word, 128 KB table, 1 CTA per SM; cannot overflow (the plan kernel admits the hybrid path
+//              only when every segment has at most 65535 keys).  Takes the segments the 8-bit kernel left.
 struct MsdLeafParams {
     uint32_t *keys;                   // encoded keys grouped by their top 16 bits; sorted + decoded in place
     const unsigned int *seg_start;    // [65537]
     const unsigned int *seg_list;     // non-empty segment ids
+    unsigned int *redo;               // [65536] per list slot: 1 = the 8-bit kernel gave up on it (zeroed by the memset)
     MsdCtl *ctl;
     SortXform xf;
-    unsigned int want_mode;
+    unsigned int cap8;                // longest segment the 8-bit kernel takes
 };
 
-constexpr int MSD_LEAF_CHUNK = 6;      // global loads in flight per thread in phases A / B
-constexpr int MSD_LEAF_BIG = 512;      // byte-1 groups longer than this are finished by the whole CTA, not one warp
+constexpr int MSD_LEAF_CHUNK = 8;      // global loads in flight per thread in the count phase
 
-// Exclusive scan of one value per thread over the first 256 threads (8 warps); all threads must call it.
-// Returns the exclusive prefix for tid < 256; `s_wsum` is an 8-word scratch.  Ends with the barrier that makes the
-// caller's subsequent shared-memory writes of the result safe to read.
-__device__ __forceinline__ unsigned int msd_scan256(unsigned int cnt, int tid, unsigned int *s_wsum) {
-    const int lane = tid & 31, warp = tid >> 5;
-    unsigned int incl = cnt;
-    if (warp < 8) {
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += up;
-        }
-        if (lane == 31) s_wsum[warp] = incl;
-    }
-    __syncthreads();
-    unsigned int wbase = 0;
-    if (warp < 8) {
-#pragma unroll
-        for (int w = 0; w < 8; ++w) wbase += (w < warp) ? s_wsum[w] : 0u;
-    }
-    return wbase + incl - cnt;
-}
-
-template <int NT, int ITEMS, bool IDENT>
-__global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) msd_leaf_kernel(MsdLeafParams p) {
-    constexpr int CAP = NT * ITEMS;
+template <int BITS, int NT, bool IDENT>
+__global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLeafParams p) {
+    constexpr int PER_WORD = 32 / BITS;               // bins per 32-bit word
+    constexpr int WORDS = MSD_BINS / PER_WORD;        // 16384 (8-bit) / 32768 (16-bit)
     constexpr int NW = NT / 32;
+    constexpr int WORDS_PER_WARP = WORDS / NW;        // contiguous slice of the table walked by one warp
     constexpr int CH = MSD_LEAF_CHUNK;
-    static_assert(CAP < 65536, "16-bit ranks");
-    static_assert(ITEMS % CH == 0, "whole chunks");
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    uint32_t *S = reinterpret_cast<uint32_t *>(s_raw);                 // [CAP] keys grouped by byte 1
-    unsigned int *s_wc = reinterpret_cast<unsigned int *>(S + CAP);    // [NW][256] per-warp byte-0 counters
-    __shared__ unsigned int s_hist[256];
-    __shared__ unsigned int s_gstart[256];
-    __shared__ unsigned int s_gcnt[256];
-    __shared__ unsigned int s_wsum[8];
-    __shared__ unsigned int s_wsum2[8];
-    __shared__ unsigned int s_nbig;
-    __shared__ unsigned short s_big[CAP / MSD_LEAF_BIG + 1];
+    constexpr unsigned int FIELD = (1u << BITS) - 1u;
+    extern __shared__ __align__(16) unsigned int s_bins[];   // [WORDS] packed counters, all zero between segments
+    __shared__ unsigned int s_wtot[NW];
+    __shared__ int s_over;
 
-    if (ld_cg_u32(&p.ctl->mode) != p.want_mode) return;
+    if (ld_cg_u32(&p.ctl->mode) == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int nne = ld_cg_u32(&p.ctl->nne);
-    unsigned int *wc = s_wc + warp * 256;
-    // Segments are dealt round-robin to the persistent CTAs (every segment is independent: no ticket needed); the
-    // bounds of the next segment and the id of the one after are loaded one iteration early (every thread loads the
-    // same words: one broadcast request per warp, no shared-memory hand-off).
+    for (int i = tid; i < WORDS / 4; i += NT) reinterpret_cast<uint4 *>(s_bins)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) s_over = 0;
+
+    // Segments are dealt round-robin to the persistent CTAs (independent work: no ticket).  Bounds of the next segment
+    // and the id of the one after are loaded an iteration early; every thread loads the same words (broadcast).
     const unsigned int G = gridDim.x;
     unsigned int k = blockIdx.x;
     if (k >= nne) return;
-    unsigned int lo, hi, seg_n1 = 0;
-    {
-        const unsigned int seg0 = __ldg(p.seg_list + k);
-        lo = __ldg(p.seg_start + seg0);
-        hi = __ldg(p.seg_start + seg0 + 1);
-        if (k + G < nne) seg_n1 = __ldg(p.seg_list + k + G);
-    }
+    unsigned int seg, lo, hi, seg_n1 = 0;
+    seg = __ldg(p.seg_list + k);
+    lo = __ldg(p.seg_start + seg);
+    hi = __ldg(p.seg_start + seg + 1);
+    if (k + G < nne) seg_n1 = __ldg(p.seg_list + k + G);
+    __syncthreads();
 
     for (; k < nne; k += G) {
         unsigned int nlo = 0, nhi = 0, seg_n2 = 0;
         if (k + G < nne) { nlo = __ldg(p.seg_start + seg_n1); nhi = __ldg(p.seg_start + seg_n1 + 1); }
         if (k + 2 * G < nne) seg_n2 = __ldg(p.seg_list + k + 2 * G);
-        if (tid == 0) s_nbig = 0;
-        if (tid < 256) s_hist[tid] = 0;
-        __syncthreads();
-        const int m = (int)(hi - lo);                        // 1 <= m <= CAP (plan kernel)
-        uint32_t *base = p.keys + lo;
-
-        // ---- A: rank by byte 1 (one shared atomic per key); the keys are re-read from L2 in B.
-        // Loads go out CH at a time: a load -> atomic -> load chain would expose one L2 round trip per key.
-        // Chunks that lie entirely inside the segment (all but the last) run without per-key predicates.
-        PackedRanks<ITEMS> ranks;
+        const int m = (int)(hi - lo);
+        bool mine;
+        if constexpr (BITS == 8) mine = m <= (int)p.cap8;
+        else mine = m > (int)p.cap8 || ld_cg_u32(p.redo + k) != 0;
+        if (mine) {                                          // uniform over the CTA
+            uint32_t *base = p.keys + lo;
+            // ---- count: one shared atomic per key.  Loads go out CH at a time (a load -> atomic -> load chain would
+            // expose one memory round trip per key).
+            for (int i0 = 0; i0 < m; i0 += CH * NT) {
+                uint32_t kk[CH];
+                if (i0 + CH * NT <= m) {
 #pragma unroll
-        for (int j0 = 0; j0 < ITEMS; j0 += CH) {
-            if (j0 * NT >= m) break;
-            uint32_t kk[CH];
-            if ((j0 + CH) * NT <= m) {
+                    for (int c = 0; c < CH; ++c) kk[c] = ld_coh(base + i0 + c * NT + tid);
 #pragma unroll
-                for (int c = 0; c < CH; ++c) kk[c] = ld_keep_l2(base + (j0 + c) * NT + tid);
+                    for (int c = 0; c < CH; ++c) {
+                        const unsigned int v = kk[c] & 0xFFFFu;
+                        const unsigned int sh = (v % PER_WORD) * BITS;
+                        const unsigned int old = atomicAdd(&s_bins[v / PER_WORD], 1u << sh);
+                        if (BITS == 8 && (old & (0x80u << sh))) s_over = 1;
+                    }
+                } else {
 #pragma unroll
-                for (int c = 0; c < CH; ++c) ranks.set(j0 + c, atomicAdd(&s_hist[(kk[c] >> 8) & 0xFFu], 1u));
-            } else {
+                    for (int c = 0; c < CH; ++c) {
+                        const int i = i0 + c * NT + tid;
+                        kk[c] = i < m ? ld_coh(base + i) : 0u;
+                    }
 #pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    const int i = (j0 + c) * NT + tid;
-                    kk[c] = i < m ? ld_keep_l2(base + i) : 0u;
-                }
-#pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    const int i = (j0 + c) * NT + tid;
-                    unsigned int r = 0;
-                    if (i < m) r = atomicAdd(&s_hist[(kk[c] >> 8) & 0xFFu], 1u);
-                    ranks.set(j0 + c, r);
-                }
-            }
-        }
-        __syncthreads();
-        {
-            const unsigned int cnt = tid < 256 ? s_hist[tid] : 0u;
-            const unsigned int ex = msd_scan256(cnt, tid, s_wsum);
-            if (tid < 256) {
-                s_gstart[tid] = ex;
-                s_gcnt[tid] = cnt;
-                if (cnt > MSD_LEAF_BIG) s_big[atomicAdd(&s_nbig, 1u)] = (unsigned short)tid;
-            }
-        }
-        __syncthreads();
-        const int nbig = (int)s_nbig;
-
-        // ---- B: scatter into shared memory, grouped by byte 1
-#pragma unroll
-        for (int j0 = 0; j0 < ITEMS; j0 += CH) {
-            if (j0 * NT >= m) break;
-            uint32_t kk[CH];
-            if ((j0 + CH) * NT <= m) {
-#pragma unroll
-                for (int c = 0; c < CH; ++c) kk[c] = ld_coh(base + (j0 + c) * NT + tid);
-#pragma unroll
-                for (int c = 0; c < CH; ++c) S[s_gstart[(kk[c] >> 8) & 0xFFu] + ranks.get(j0 + c)] = kk[c];
-            } else {
-#pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    const int i = (j0 + c) * NT + tid;
-                    kk[c] = i < m ? ld_coh(base + i) : 0u;
-                }
-#pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    const int i = (j0 + c) * NT + tid;
-                    if (i < m) S[s_gstart[(kk[c] >> 8) & 0xFFu] + ranks.get(j0 + c)] = kk[c];
+                    for (int c = 0; c < CH; ++c) {
+                        const int i = i0 + c * NT + tid;
+                        if (i < m) {
+                            const unsigned int v = kk[c] & 0xFFFFu;
+                            const unsigned int sh = (v % PER_WORD) * BITS;
+                            const unsigned int old = atomicAdd(&s_bins[v / PER_WORD], 1u << sh);
+                            if (BITS == 8 && (old & (0x80u << sh))) s_over = 1;
+                        }
+                    }
                 }
             }
-        }
-        __syncthreads();
-
-        // ---- C: every warp finishes whole byte-1 groups: counting sort on byte 0 into the final place.
-        // All keys of a group share their top 24 bits, so keys with equal byte 0 are identical: any order.
-        // Groups of up to 96 keys (the common case: 64 on average for 2^30 uniform keys) keep their keys in three
-        // registers per lane between the count and the place step; longer ones loop over shared memory.
-        for (int g = warp; g < 256; g += NW) {
-            const int gc = (int)s_gcnt[g];
-            if (gc == 0 || gc > MSD_LEAF_BIG) continue;
-            const unsigned int gs = s_gstart[g];
-            if (gc == 1) {
-                if (lane == 0) {
-                    const uint32_t key = S[gs];
-                    base[gs] = IDENT ? key : key_decode<uint32_t>(key, p.xf);
-                }
-                continue;
-            }
-            reinterpret_cast<uint4 *>(wc)[lane] = make_uint4(0, 0, 0, 0);
-            reinterpret_cast<uint4 *>(wc)[lane + 32] = make_uint4(0, 0, 0, 0);
-            const bool small = gc <= 96;
-            const bool v0 = lane < gc, v1 = lane + 32 < gc, v2 = lane + 64 < gc;
-            uint32_t k0 = 0, k1 = 0, k2 = 0;
-            if (small) {
-                if (v0) k0 = S[gs + lane];
-                if (v1) k1 = S[gs + 32 + lane];
-                if (v2) k2 = S[gs + 64 + lane];
-            }
-            __syncwarp();
-            if (small) {
-                if (v0) atomicAdd(&wc[k0 & 0xFFu], 1u);
-                if (v1) atomicAdd(&wc[k1 & 0xFFu], 1u);
-                if (v2) atomicAdd(&wc[k2 & 0xFFu], 1u);
-            } else {
-#pragma unroll 1
-                for (int r = lane; r < gc; r += 32) atomicAdd(&wc[S[gs + r] & 0xFFu], 1u);
-            }
-            __syncwarp();
-            // lane owns counters 8 lane .. 8 lane + 7
-            uint4 a = reinterpret_cast<uint4 *>(wc)[2 * lane], b = reinterpret_cast<uint4 *>(wc)[2 * lane + 1];
-            const unsigned int tot = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
-            unsigned int inc = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned int up = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += up;
-            }
-            unsigned int run = inc - tot;
-            uint4 oa, ob;
-            oa.x = run; run += a.x; oa.y = run; run += a.y; oa.z = run; run += a.z; oa.w = run; run += a.w;
-            ob.x = run; run += b.x; ob.y = run; run += b.y; ob.z = run; run += b.z; ob.w = run;
-            reinterpret_cast<uint4 *>(wc)[2 * lane] = oa;
-            reinterpret_cast<uint4 *>(wc)[2 * lane + 1] = ob;
-            __syncwarp();
-            uint32_t *gout = base + gs;
-            if (small) {
-                if (v0) gout[atomicAdd(&wc[k0 & 0xFFu], 1u)] = IDENT ? k0 : key_decode<uint32_t>(k0, p.xf);
-                if (v1) gout[atomicAdd(&wc[k1 & 0xFFu], 1u)] = IDENT ? k1 : key_decode<uint32_t>(k1, p.xf);
-                if (v2) gout[atomicAdd(&wc[k2 & 0xFFu], 1u)] = IDENT ? k2 : key_decode<uint32_t>(k2, p.xf);
-            } else {
-#pragma unroll 1
-                for (int r = lane; r < gc; r += 32) {
-                    const uint32_t key = S[gs + r];
-                    gout[atomicAdd(&wc[key & 0xFFu], 1u)] = IDENT ? key : key_decode<uint32_t>(key, p.xf);
-                }
-            }
-            __syncwarp();
-        }
-
-        // ---- C': long groups (skewed byte 1) are finished by the whole CTA, one after the other
-        for (int b = 0; b < nbig; ++b) {
-            const int g = s_big[b];
-            const int gc = (int)s_gcnt[g];
-            const unsigned int gs = s_gstart[g];
-            __syncthreads();                       // previous user of s_hist is done
-            if (tid < 256) s_hist[tid] = 0;
             __syncthreads();
-            for (int r = tid; r < gc; r += NT) atomicAdd(&s_hist[S[gs + r] & 0xFFu], 1u);
-            __syncthreads();
-            const unsigned int cnt = tid < 256 ? s_hist[tid] : 0u;
-            const unsigned int ex = msd_scan256(cnt, tid, s_wsum2);
-            if (tid < 256) s_hist[tid] = ex;
-            __syncthreads();
-            for (int r = tid; r < gc; r += NT) {
-                const uint32_t key = S[gs + r];
-                const unsigned int pos = atomicAdd(&s_hist[key & 0xFFu], 1u);
-                base[gs + pos] = IDENT ? key : key_decode<uint32_t>(key, p.xf);
+            const bool over = BITS == 8 && s_over != 0;      // uniform
+            // ---- warp totals: warp w owns table words [w * WORDS_PER_WARP, (w + 1) * WORDS_PER_WARP)
+            const unsigned int *wb = s_bins + warp * WORDS_PER_WARP;
+            if (!over) {
+                unsigned int acc = 0;
+#pragma unroll 8
+                for (int j = lane; j < WORDS_PER_WARP; j += 32) {
+                    const unsigned int w = wb[j];
+                    acc += BITS == 8 ? __dp4a(w, 0x01010101u, 0u) : (w & 0xFFFFu) + (w >> 16);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) s_wtot[warp] = acc;
             }
+            __syncthreads();
+            if (over) {
+                // a value occurs 128 times or more: hand the segment to the 16-bit kernel and clear the table
+                for (int i = tid; i < WORDS / 4; i += NT) reinterpret_cast<uint4 *>(s_bins)[i] = make_uint4(0, 0, 0, 0);
+                if (tid == 0) { p.redo[k] = 1u; s_over = 0; }
+            } else {
+                // ---- expand: walk the table in value order; 32 words (32 * PER_WORD values) per step and warp.
+                // A lane emits its word's values `count` times each at consecutive positions, lanes back to back.
+                unsigned int run = 0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) run += (w < warp) ? s_wtot[w] : 0u;
+                const uint32_t hi16 = ld_coh(base) & 0xFFFF0000u;        // any key of the segment (read before any write: barrier above)
+                unsigned int *wbw = s_bins + warp * WORDS_PER_WARP;
+                __syncthreads();                                          // every warp has read base[0]
+#pragma unroll 2
+                for (int j = lane; j < WORDS_PER_WARP; j += 32) {
+                    const unsigned int w = wbw[j];
+                    wbw[j] = 0;                                           // table is clean again for the next segment
+                    const unsigned int cnt = BITS == 8 ? __dp4a(w, 0x01010101u, 0u) : (w & 0xFFFFu) + (w >> 16);
+                    unsigned int incl = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += up;
+                    }
+                    const unsigned int tot = __shfl_sync(0xffffffffu, incl, 31);
+                    if (w) {
+                        unsigned int pos = run + incl - cnt;
+                        const uint32_t v0 = hi16 | (uint32_t)((warp * WORDS_PER_WARP + j) * PER_WORD);
+#pragma unroll
+                        for (int f = 0; f < PER_WORD; ++f) {
+                            unsigned int c = (w >> (f * BITS)) & FIELD;
+                            const uint32_t key = v0 + f;
+                            const uint32_t outv = IDENT ? key : key_decode<uint32_t>(key, p.xf);
+                            while (c--) base[pos++] = outv;
+                        }
+                    }
+                    run += tot;
+                }
+            }
+            __syncthreads();        // table clean / redo written before the next segment's atomics
         }
-        if (nbig) __syncthreads();                 // s_hist is zeroed at the top of the next iteration
-        lo = nlo; hi = nhi; seg_n1 = seg_n2;
+        lo = nlo; hi = nhi; seg = seg_n1; seg_n1 = seg_n2;
     }
 }
 

@@ -37,9 +37,9 @@ class DeviceOps:
         mapreducedim_(f, op, R, shard, init=init)
         return R
 
-    def scan(self, op, out, shard, init, exclusive):
+    def scan(self, op, out, shard, init, exclusive, carry=None, carry_count=0):
         from .accumulate import scan_
-        return scan_(op, out, shard, 1, init=init, exclusive=exclusive)
+        return scan_(op, out, shard, 1, init=init, exclusive=exclusive, carry=carry, carry_count=carry_count)
 
     def sort_keys(self, c, rev):
         from .sorting import sort_
@@ -157,13 +157,27 @@ def dist_mapreduce(f, op, shard, group=None, ops=None):
     if red is None:
         raise NotGraftedError(f"no collective for {op}")
     t = partial.typed()
-    if t.dtype in (torch.uint32, torch.uint64):          # NCCL/gloo have no unsigned reductions: wrap-around add is bit-identical
-        if red not in (dist.ReduceOp.SUM, dist.ReduceOp.PRODUCT, dist.ReduceOp.BAND, dist.ReduceOp.BOR):
-            raise NotGraftedError("unsigned max/min across ranks")
-        t = t.view(torch.int32 if t.dtype == torch.uint32 else torch.int64)
-    if t.dtype == torch.bool:
-        t8 = t.view(torch.uint8)
-        dist.all_reduce(t8, op=dist.ReduceOp.MAX if red == dist.ReduceOp.BOR else dist.ReduceOp.MIN, group=group)
+    if t.dtype in (torch.uint32, torch.uint64):
+        # NCCL/gloo have no unsigned reductions.  Wrap-around add / mul and the bitwise ops are bit-identical on the
+        # signed view; max / min compare correctly once the sign bit is flipped (order-preserving map to signed).
+        st = t.view(torch.int32 if t.dtype == torch.uint32 else torch.int64)
+        if red in (dist.ReduceOp.MAX, dist.ReduceOp.MIN):
+            sign = torch.iinfo(st.dtype).min
+            st.bitwise_xor_(sign)
+            dist.all_reduce(st, op=red, group=group)
+            st.bitwise_xor_(sign)
+        else:
+            dist.all_reduce(st, op=red, group=group)
+    elif t.dtype == torch.bool:
+        # Bool partials travel as bytes: `|` and max are a byte MAX, `&`, min and `*` a byte MIN; `+` on Bool would
+        # need a widened output (Base: reduce(+, bools) isa Int) and is not a sharded reduction we graft.
+        if red in (dist.ReduceOp.BOR, dist.ReduceOp.MAX):
+            bop = dist.ReduceOp.MAX
+        elif red in (dist.ReduceOp.BAND, dist.ReduceOp.MIN, dist.ReduceOp.PRODUCT):
+            bop = dist.ReduceOp.MIN
+        else:
+            raise NotGraftedError("reduce(+, ::Bool shards): use count / add_sum (Bool -> Int64)")
+        dist.all_reduce(t.view(torch.uint8), op=bop, group=group)
     else:
         dist.all_reduce(t, op=red, group=group)
     host = partial.to_host().reshape(-1)[0]
@@ -178,9 +192,9 @@ def dist_extrema(shard, group=None, ops=None):
 # ----------------------------------------------------------------------------- scan
 def dist_accumulate(op, shard, exclusive=False, group=None, ops=None, out_eltype=None):
     """accumulate(op, A) over the concatenation of all shards.  Each rank reduces its shard
-    (N reads), the G shard totals are all-gathered, every rank folds the totals of the ranks
-    before it into its carry, and scans its shard once with that carry as `init`
-    (N reads + N writes): 3N traffic instead of the 4N of scan-then-fix-up."""
+    (N reads), the G shard totals are all-gathered, and every rank scans its shard once with the
+    totals of the ranks before it folded into the seed on the device (N reads + N writes):
+    3N traffic instead of the 4N of scan-then-fix-up, and no host synchronisation anywhere."""
     from .mapreduce import identity, neutral_element
     ops = ops or DeviceOps()
     G, r = _world(group)
@@ -191,12 +205,9 @@ def dist_accumulate(op, shard, exclusive=False, group=None, ops=None, out_eltype
     dist.all_gather_into_tensor(_typed(gathered), _typed(total), group=group) if hasattr(dist, "all_gather_into_tensor") \
         and shard.buf.is_cuda else _all_gather_fallback(_typed(gathered), _typed(total), group)
     out = shard.similar(out_et)
-    init = None
-    if r > 0:
-        before = CuArray(gathered.buf[:r * dt.SIZES[part_et]], (r,), part_et)
-        carry = ops.reduce(identity, op, before, part_et).to_host().reshape(-1)[0]
-        init = carry.astype(dt.np_dtype(out_et))
-    ops.scan(op, out, shard, init, exclusive)
+    # the carry of rank r = op over the totals of ranks 0 .. r-1: folded into the scan's seed ON THE DEVICE
+    # (b200_scan_carry reads gathered[0:r]) — no host read-back, no extra reduce launch, graph-capturable
+    ops.scan(op, out, shard, None, exclusive, carry=gathered, carry_count=r)
     return out
 
 

@@ -31,11 +31,18 @@ QuickSort = _Token("CUDA.QuickSort")          # not exercised on cc >= 9.0 (test
 SORTPERM_INDEX = 100
 
 
-def _guard(lt, by, alg):
-    if lt is not isless or by is not identity:
+_SORT_KW = ("lt", "by", "rev", "dims")
+
+
+def _graftable(kwargs):
+    """lib/B200Arrays/src/sorting.jl `graftable_sort`: only known keywords, default lt / by, Bool rev."""
+    for k in kwargs:
+        if k not in _SORT_KW:
+            raise NotGraftedError(f"keyword {k!r}: the reference method decides (MethodError for unknown keywords)")
+    if kwargs.get("lt", isless) is not isless or kwargs.get("by", identity) is not identity:
         raise NotGraftedError("sort with a custom lt/by stays on the reference's bitonic kernels")
-    if alg is not BitonicSort:
-        raise NotGraftedError("alg=QuickSort stays on the reference path")
+    if not isinstance(kwargs.get("rev", False), bool):
+        raise NotGraftedError("rev must be a Bool")
 
 
 def _factor(c, dims):
@@ -54,10 +61,15 @@ def _factor(c, dims):
     return pre, n, post
 
 
-def sort_(c, alg=BitonicSort, lt=isless, by=identity, rev=False, dims=None):
-    """Base.sort!(c::AnyCuArray; alg=BitonicSort, lt, by, rev, dims) (sorting.jl:1003-1009)."""
-    _guard(lt, by, alg)
-    pre, n, post = _factor(c, dims)
+def sort_alg_(c, alg, **kwargs):
+    """Base.sort!(c::CuArray{T}, alg::BitonicSortAlg; kwargs...) — THE grafted method (lib/B200Arrays/src/sorting.jl):
+    the reference's `sort!(c; alg, kw...)` (sorting.jl:1007-1009) and `partialsort!(c, k, alg; ...)` (sorting.jl:1015-1020)
+    both pass `alg` positionally and land here; QuickSort dispatches to the reference's own method (sorting.jl:993)."""
+    if alg is not BitonicSort:
+        raise NotGraftedError("alg=QuickSort stays on the reference path (sorting.jl:993-1001)")
+    _graftable(kwargs)
+    pre, n, post = _factor(c, kwargs.get("dims"))
+    rev = kwargs.get("rev", False)
     if n <= 1 or pre * post == 0:
         return c
     lib = _lib.load()
@@ -67,6 +79,11 @@ def sort_(c, alg=BitonicSort, lt=isless, by=identity, rev=False, dims=None):
     _lib.check(lib.b200_sort_keys_dims(ws.ptr, ws.nbytes, c.pointer, c.eltype, pre, n, post, 1 if rev else 0,
                                        current_stream_handle(c.buf.device)))
     return c
+
+
+def sort_(c, alg=BitonicSort, **kwargs):
+    """Base.sort!(c::AnyCuArray; alg=BitonicSort, kwargs...) = sort!(c, alg; kwargs...) (sorting.jl:1007-1009)."""
+    return sort_alg_(c, alg, **kwargs)
 
 
 def sort(c, **kw):
@@ -89,23 +106,32 @@ def _index_k(c, k):
     return CuArray(c.buf[lo * sz:(lo + len(k)) * sz].clone(), (len(k),), c.eltype)
 
 
-def partialsort_(c, k, alg=BitonicSort, lt=isless, by=identity, rev=False):
-    """Base.partialsort!(c, k, ::BitonicSortAlg; ...) = sort! then copy(c[k]) (sorting.jl:1015-1020)."""
+def partialsort_alg_(c, k, alg, lt=isless, by=identity, rev=False):
+    """Base.partialsort!(c::AnyCuVector, k, alg::BitonicSortAlg; lt, by, rev) = sort!(c, alg; lt, by, rev); copy(c[k])
+    (sorting.jl:1015-1020) — reference code, reaches the grafted positional sort! method."""
     if c.ndims != 1:
         raise NotGraftedError("partialsort! is defined for vectors")
-    sort_(c, alg=alg, lt=lt, by=by, rev=rev)
+    sort_alg_(c, alg, lt=lt, by=by, rev=rev)
     return _index_k(c, k)
 
 
-def partialsort(c, k, alg=BitonicSort, lt=isless, by=identity, rev=False):
+def partialsort_(c, k, alg=BitonicSort, **kwargs):
+    """Base.partialsort!(c, k; alg=BitonicSort, kwargs...) = partialsort!(c, k, alg; kwargs...) (sorting.jl:1042-1044)."""
+    return partialsort_alg_(c, k, alg, **kwargs)
+
+
+def partialsort(c, k, alg=BitonicSort, **kwargs):
     """Base.partialsort(c::AnyCuArray, k; kw...) = partialsort!(copy(c), k; kw...) (sorting.jl:1046-1048).  For a scalar k nothing needs to be
-    sorted or copied: b200_select_kth (MSD radix select, sizeof(T) streaming reads of c) finds the element a
+    sorted or copied: b200_select_kth (radix select, c untouched) finds the element a
     stable sort would put at position k.  Ranges go through the full sort like the reference."""
     if not isinstance(k, (int, np.integer)):
-        return partialsort_(c.copy(), k, alg=alg, lt=lt, by=by, rev=rev)
+        return partialsort_(c.copy(), k, alg=alg, **kwargs)
     if c.ndims != 1:
         raise NotGraftedError("partialsort is defined for vectors")
-    _guard(lt, by, alg)
+    if alg is not BitonicSort or "dims" in kwargs:
+        raise NotGraftedError("alg=QuickSort / dims stay on the reference path")
+    _graftable(kwargs)
+    rev = kwargs.get("rev", False)
     if not 1 <= k <= c.length:
         raise IndexError(f"BoundsError: attempt to access {c.length}-element CuArray at index [{k}]")
     lib = _lib.load()
@@ -119,8 +145,9 @@ def partialsort(c, k, alg=BitonicSort, lt=isless, by=identity, rev=False):
     return out.to_host()[0]                                                    # @allowscalar, like the reference
 
 
-def sortperm_(ix, A, initialized=False, alg=BitonicSort, lt=isless, by=identity, rev=False, dims=None):
-    """Base.sortperm!(ix::AnyCuArray, A::AnyCuArray; initialized=false, kw...) (sorting.jl:1051-1061)."""
+def sortperm_(ix, A, initialized=False, **kwargs):
+    """Base.sortperm!(ix::AnyCuArray, A::AnyCuArray; initialized=false, kw...) (sorting.jl:1051-1061).  The reference
+    forwards kw to bitonic_sort!(; by, lt, rev, dims), which has no `alg` keyword."""
     if ix.dims != A.dims:
         def axes(d):
             return "(" + ", ".join(f"Base.OneTo({s})" for s in d) + ("," if len(d) == 1 else "") + ")"
@@ -128,7 +155,8 @@ def sortperm_(ix, A, initialized=False, alg=BitonicSort, lt=isless, by=identity,
                             f"{axes(ix.dims)} != {axes(A.dims)}")              # sorting.jl:1052-1054
     if A.length == 0:
         return ix                                                              # sorting.jl:1055
-    _guard(lt, by, alg)
+    _graftable(kwargs)
+    rev, dims = kwargs.get("rev", False), kwargs.get("dims")
     if initialized:
         # a caller-supplied starting permutation breaks ties by index VALUE (sorting.jl:642-643)
         raise NotGraftedError("sortperm!(...; initialized=true) stays on the reference path")

@@ -164,6 +164,18 @@ int32_t b200_scan(void *workspace, size_t workspace_bytes,
                   int32_t dtype_in, int32_t dtype_out, int32_t op, int32_t exclusive,
                   int64_t pre, int64_t n, int64_t post,
                   const void *init_host, b200_stream_t stream);
+/* Same, plus a DEVICE-side carry: `carry_dev` points at `carry_count` values of the ACCUMULATOR type of dtype_out
+ * (Float32 for Float16 / BFloat16, dtype_out otherwise) that are folded, in order, into the seed of every chain
+ * after `init_host`.  This is the sharded scan of SURVEY section 8(e): rank r passes the all-gathered shard totals and
+ * carry_count = r, so the carry never visits the host (no sync, graph-capturable).  No reference counterpart
+ * (the reference has no multi-GPU scan); single-GPU semantics are those of b200_scan with
+ * init = op(init_host, carry[0], ..., carry[carry_count-1]). */
+int32_t b200_scan_carry(void *workspace, size_t workspace_bytes,
+                        const void *in, void *out,
+                        int32_t dtype_in, int32_t dtype_out, int32_t op, int32_t exclusive,
+                        int64_t pre, int64_t n, int64_t post,
+                        const void *init_host, const void *carry_dev, int32_t carry_count,
+                        b200_stream_t stream);
 
 /* ---- sort: Base.sort! / sortperm! hooks (sorting.jl:1003-1070) ---------- */
 /* Order is Julia's `isless`: -Inf < ... < -0.0 < +0.0 < ... < +Inf < NaN (all

@@ -23,7 +23,7 @@
  *   - sort! of UInt32/Float32 vectors: Julia >= 1.9 dispatches large bit-type inputs to an
  *     LSD radix sort after mapping floats to ordered unsigned keys (isless order, NaNs last)
  *   - sortperm: stable merge sort of the index vector under isless (ties by index)
- * Validated against oracle/oracle.py (numpy) in tests/test_oracle_cpu.py.
+ * Validated against oracle/oracle.py (numpy) in tests/test_oracle_golden.py::test_c_restatement_matches_numpy_oracle.
  */
 #include <math.h>
 #include <stdint.h>
@@ -214,3 +214,17 @@ void ref_sortperm_u32(const uint32_t *v, int64_t *perm, int64_t n) {
     msort_perm(v, perm, tmp, 0, n);
     free(tmp);
 }
+
+/* Comparison-sort variant (SURVEY section 8d asks for BOTH a radix and a comparison baseline, because Julia >= 1.9
+ * picks radix sort for large bit-type vectors while older versions used quick/merge sort). */
+static int cmp_u32(const void *a, const void *b) {
+    const uint32_t x = *(const uint32_t *)a, y = *(const uint32_t *)b;
+    return (x > y) - (x < y);
+}
+void ref_sort_f32_cmp(float *a, int64_t n) {
+    uint32_t *k = (uint32_t *)a;
+    for (int64_t i = 0; i < n; ++i) k[i] = f32_key(k[i]);
+    qsort(k, (size_t)n, sizeof(uint32_t), cmp_u32);
+    for (int64_t i = 0; i < n; ++i) { uint32_t e = k[i]; k[i] = (e & 0x80000000u) ? (e ^ 0x80000000u) : ~e; }
+}
+

@@ -31,7 +31,7 @@ def lib():
         for name in ("ref_cumsum_f32", "ref_cumsum_i64", "ref_sortperm_f32", "ref_sortperm_u32"):
             getattr(L, name).restype = None
             getattr(L, name).argtypes = [vp, vp, i64]
-        for name in ("ref_sort_u32", "ref_sort_f32"):
+        for name in ("ref_sort_u32", "ref_sort_f32", "ref_sort_f32_cmp"):
             getattr(L, name).restype = None
             getattr(L, name).argtypes = [vp, i64]
         _lib = L
@@ -82,6 +82,13 @@ def cumsum(v):
 def sort(v):
     v = np.ascontiguousarray(v).copy()
     (lib().ref_sort_f32 if v.dtype == np.float32 else lib().ref_sort_u32)(_p(v), v.size)
+    return v
+
+
+def sort_cmp(v):
+    """Comparison-sort (qsort) variant of sort for Float32 — timing baseline only."""
+    v = np.ascontiguousarray(v, dtype=np.float32).copy()
+    lib().ref_sort_f32_cmp(_p(v), v.size)
     return v
 
 

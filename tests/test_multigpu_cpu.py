@@ -44,9 +44,16 @@ class FakeOps:
             val = np.asarray(self.o.mapreducedim("identity" if f is self.b.identity else "abs2", self._name(op), a, (1,), odt)).astype(odt).reshape(1)
         return _mk(val, self.b)
 
-    def scan(self, op, out, shard, init, exclusive):
+    def scan(self, op, out, shard, init, exclusive, carry=None, carry_count=0):
         a = shard.to_host()
         odt = self.b.dtypes.np_dtype(out.eltype)
+        if carry is not None and carry_count > 0:        # what b200_scan_carry does on the device
+            c = carry.to_host()[:carry_count]
+            acc = c[0]
+            for x in c[1:]:
+                acc = self.o.mapreducedim("identity", self._name(op), np.array([acc, x]), (1,), c.dtype)[0]
+            init = acc if init is None else self.o.mapreducedim("identity", self._name(op), np.array([init, acc]), (1,), c.dtype)[0]
+            init = np.asarray(init).astype(odt)[()]
         r = np.asarray(self.o.accumulate(self._name(op), a, 1, init, odt, exclusive)).astype(odt)
         out.buf.copy_(torch.from_numpy(np.ascontiguousarray(r).view(np.uint8)))
         return out
@@ -113,6 +120,23 @@ def _worker(rank, world, port, case, ret):
             out["scan_i_excl"] = mg.dist_accumulate(b.add, si, exclusive=True, ops=ops).to_host()
             out["scan_f"] = mg.dist_accumulate(b.add, sf, ops=ops).to_host()
             out["scan_max"] = mg.dist_accumulate(b.max_, si, ops=ops).to_host()
+            # Bool and unsigned partials across ranks (max over Bool shards was combined with MIN)
+            fb = np.zeros(999, dtype=np.bool_); fb[700] = True          # only the LAST rank's shard holds a True
+            cb = np.linspace(0, fb.size, world + 1).astype(int)
+            sb = _mk(fb[cb[rank]:cb[rank + 1]], b)
+            for name, op in (("bmax", b.max_), ("bmin", b.min_), ("bor", b.or_), ("band", b.and_)):
+                out[name] = bool(mg.dist_mapreduce(b.identity, op, sb, ops=ops))
+            fu = rng.integers(0, 2**32, size=5000, dtype=np.uint32)
+            fu[4000] = 0xFFFFFFF0; fu[10] = 3                           # extremes on different ranks, above 2^31
+            cu = np.linspace(0, fu.size, world + 1).astype(int)
+            su = _mk(fu[cu[rank]:cu[rank + 1]], b)
+            out["umax"] = int(mg.dist_mapreduce(b.identity, b.max_, su, ops=ops))
+            out["umin"] = int(mg.dist_mapreduce(b.identity, b.min_, su, ops=ops))
+            try:
+                mg.dist_mapreduce(b.identity, b.add, sb, ops=ops)
+                out["bool_add"] = "no error"
+            except b.NotGraftedError:
+                out["bool_add"] = "NotGrafted"
         elif case == "sort":
             full = rng.standard_normal(50_000).astype(np.float32)
             full[::97] = 0.25                       # heavy duplicates
@@ -163,6 +187,9 @@ def test_sharded_reduce_and_scan(world):
         assert r["max_f"] == float(full_f.max())
         assert abs(r["sum_f"] - float(full_f.astype(np.float64).sum())) <= 1e-6 * float(full_f.sum()) * 20
         assert r["ext"] == (int(full_i.min()), int(full_i.max()))
+        assert (r["bmax"], r["bmin"], r["bor"], r["band"]) == (True, False, True, False)
+        assert r["umax"] == 0xFFFFFFF0 and r["umin"] <= 3
+        assert r["bool_add"] == "NotGrafted"
     np.testing.assert_array_equal(np.concatenate([r["scan_i"] for r in res]), np.cumsum(full_i))
     excl = np.concatenate([[0], np.cumsum(full_i)[:-1]])
     np.testing.assert_array_equal(np.concatenate([r["scan_i_excl"] for r in res]), excl)

@@ -40,6 +40,48 @@ def test_reference_literal_pins():
     assert checked == 6
 
 
+def test_reference_deterministic_cases_pin_the_oracle():
+    """Sort / partialsort / sortperm / accumulate on the reference tests' own deterministic inputs (and constructed
+    tie / NaN / signed-zero vectors): expected outputs are closed forms built in tests/golden/cases.py."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import cases as G
+    n_checked = 0
+    for c in G.load():
+        call = c["call"]
+        if call == "sort":
+            a = G.make_input(c["input"])
+            np.testing.assert_array_equal(oracle.sort(a, rev=c["rev"]), G.make_expected(c), err_msg=c["name"])
+        elif call == "partialsort!":
+            a = G.make_input(c["input"])
+            srt = oracle.sort(a)
+            k = c["k"]
+            got = srt[k - 1:k] if isinstance(k, int) else srt[k[0] - 1:k[1]]
+            np.testing.assert_array_equal(got, G.make_expected(c), err_msg=c["name"])
+        elif call == "sortperm":
+            a = G.make_input(c["input"])
+            np.testing.assert_array_equal(oracle.sortperm(a, rev=c["rev"]), G.make_expected(c), err_msg=c["name"])
+        elif call in ("accumulate", "accumulate_init"):
+            for n in c["sizes"]:
+                a = G.make_input(c["input"], n=n)
+                init = a.dtype.type(c["init"]) if "init" in c else None
+                np.testing.assert_array_equal(oracle.accumulate("add", a, 1, init), G.make_expected(c, n=n), err_msg=c["name"])
+        elif call == "accumulate_cols":
+            for n in c["sizes"]:
+                a = G.make_input(c["input"], shape=(n, 2))
+                got = oracle.accumulate("add", a.reshape(-1, order="F"), 1).reshape(a.shape, order="F")   # A[:] branch
+                for col in range(2):
+                    np.testing.assert_array_equal(got[:, col], np.arange(1, n + 1) + col * n, err_msg=c["name"])
+        elif call == "accumulate_dims":
+            shape = tuple(c["shape"])
+            a = G.make_input(c["input"], shape=shape)
+            np.testing.assert_array_equal(oracle.accumulate("add", a, c["dims"]), G.make_expected(c, shape=shape), err_msg=c["name"])
+        else:
+            continue
+        n_checked += 1
+    assert n_checked == 25
+
+
 def test_oracle_regression_vectors():
     g = np.load(os.path.join(HERE, "golden", "oracle_vectors.npz"))
     a, f, i64, u8 = g["i32"], g["f32"], g["i64"], g["u8"]
