@@ -206,6 +206,27 @@ int32_t b200_sort_workspace_bytes(int32_t dtype_key, int32_t dtype_payload, int6
     return run(kb, c);
 }
 
+int32_t b200_sort_keys_from(void *workspace, size_t workspace_bytes, const void *src, void *dst, int32_t dtype_key,
+                            int64_t n, int32_t descending, const void *hist16_dev, b200_stream_t stream) {
+    using namespace b200;
+    if (n < 0) return B200_INVALID_VALUE;
+    SortXform xf; int kb;
+    if (!make_xform(dtype_key, descending, 0, xf, kb)) return B200_UNSUPPORTED;
+    if (n == 0) return B200_OK;
+    if (!src || !dst) return B200_INVALID_VALUE;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (n == 1 || kb != 4 || (kb & 1) || n <= RB_TILE) {
+        // short inputs and the odd-pass (1-byte) layout: copy, then the in-place entry point
+        if (src != dst) B200_CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)n * kb, cudaMemcpyDeviceToDevice, st));
+        return b200_sort_keys(workspace, workspace_bytes, dst, dtype_key, n, 1, descending, stream);
+    }
+    SortCall c{};
+    c.ws = workspace; c.ws_bytes = workspace_bytes;
+    c.keys = dst; c.keys_src = src == dst ? nullptr : src; c.hist16_in = hist16_dev;
+    c.mode = SORT_KEYS; c.n = n; c.xf = xf; c.stream = st;
+    return run(kb, c);
+}
+
 int32_t b200_sort_keys(void *workspace, size_t workspace_bytes, void *keys, int32_t dtype_key, int64_t n, int64_t nseg,
                        int32_t descending, b200_stream_t stream) {
     return b200_sort_keys_dims(workspace, workspace_bytes, keys, dtype_key, 1, n, nseg, descending, stream);

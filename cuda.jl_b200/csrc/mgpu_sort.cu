@@ -1,0 +1,427 @@
+// mgpu_sort.cu — device-driven multi-GPU sample sort for 32-bit keys (keys-only `sort!`), SURVEY §8(e).
+//
+// One process per GPU; the host code (cuda.jl_b200/multigpu.py, or a Julia task per device) only strings these calls
+// together with ONE all-gather — no host-side splitter search, no count matrix on the host, no per-rank `.item()`:
+//
+//   1. b200_mgpu_hist16      histogram of the top 16 bits of the (order-mapped) keys of this rank's shard
+//                            (msd_hist16_kernel, the first kernel of the single-GPU hybrid sort)
+//      -- all-gather of the G histograms (256 KB each) --
+//   2. b200_mgpu_plan        on every rank, from the SAME G x 65536 table: global histogram, G-1 splitters at
+//                            16-bit-bin granularity (bucket b = bins [spl[b], spl[b+1]), sizes within one bin of N/G),
+//                            the exact G x G count matrix, hence where this rank's keys start inside every
+//                            destination's receive buffer, how much this rank receives, and the 16-bit histogram of
+//                            what it will receive (handed to the local sort, which then skips its own histogram pass)
+//   3. b200_mgpu_scatter     ONE pass over the shard: bucket of every key (table lookup on its top byte + the few
+//                            splitters inside that byte), atomic rank inside the tile, decoupled look-back over the
+//                            tiles per destination, keys staged by destination in shared memory and written as full
+//                            lines STRAIGHT INTO THE DESTINATION RANK'S RECEIVE BUFFER (NVLink peer stores): the
+//                            all-to-all is this kernel; nothing is written to local HBM first and the keys are read once
+//   4. b200_sort_keys_from   local hybrid MSD sort of the received keys, src = receive buffer, dst = result
+//
+// Equal keys always land in one bucket (a 16-bit bin is never split), so the concatenation of the ranks' results is the
+// sorted sequence; with heavy duplicates a rank can receive more than N/G keys — `max_recv_total` tells every rank the
+// capacity the receive buffers need before anything is sent.  No reference counterpart (the reference has no multi-GPU
+// sort).  Pairs / sortperm keep the stable partition of partition.cu.
+#include "sort_msd.cuh"
+
+namespace b200 {
+
+constexpr int MG_MAXG = 16;
+constexpr int MG_NT = 512, MG_ITEMS = 20, MG_TILE = MG_NT * MG_ITEMS;
+
+using MgpuPlan = b200_mgpu_plan_t;      // public layout (include/b200arrays.h): the host reads recv_total / max_recv_total
+
+struct MgpuPlanParams {
+    const unsigned int *hist_all;            // [G][65536]
+    MgpuPlan *plan;
+    unsigned int *hist_recv;                 // [65536] histogram of the keys this rank will receive
+    int G, rank;
+};
+
+__global__ void __launch_bounds__(1024, 1) mgpu_plan_kernel(MgpuPlanParams p) {
+    __shared__ unsigned long long s_w[32];
+    __shared__ unsigned int s_spl[MG_MAXG + 1];
+    __shared__ unsigned long long s_cnt[MG_MAXG][MG_MAXG];     // [source][bucket]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = p.G;
+    if (tid <= MG_MAXG) s_spl[tid] = 0;
+    if (tid < MG_MAXG * MG_MAXG) s_cnt[tid / MG_MAXG][tid % MG_MAXG] = 0;
+    // thread t owns bins [64 t, 64 t + 64): global count of its bins
+    unsigned long long mine = 0;
+    for (int s = 0; s < G; ++s) {
+        const uint4 *h4 = reinterpret_cast<const uint4 *>(p.hist_all + (size_t)s * MSD_BINS) + tid * 16;
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) { const uint4 v = h4[k]; mine += (unsigned long long)v.x + v.y + v.z + v.w; }
+    }
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    unsigned long long base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) { if (w < warp) base += s_w[w]; total += s_w[w]; }
+    const unsigned long long excl0 = base + incl - mine;        // keys in the bins before this thread's first bin
+    // spl[b] = number of bins whose exclusive prefix is below the b-th target = first bin with prefix >= b N / G
+    {
+        unsigned long long target[MG_MAXG];
+#pragma unroll
+        for (int b = 0; b < MG_MAXG; ++b) target[b] = b < G ? (total * (unsigned long long)b) / (unsigned long long)G : ~0ull;
+        unsigned long long run = excl0;
+        unsigned int below[MG_MAXG];
+#pragma unroll
+        for (int b = 0; b < MG_MAXG; ++b) below[b] = 0;
+        for (int k4 = 0; k4 < 16; ++k4) {
+            unsigned long long g[4] = {0, 0, 0, 0};
+            for (int s = 0; s < G; ++s) {
+                const uint4 v = (reinterpret_cast<const uint4 *>(p.hist_all + (size_t)s * MSD_BINS) + tid * 16)[k4];
+                g[0] += v.x; g[1] += v.y; g[2] += v.z; g[3] += v.w;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                for (int b = 1; b < MG_MAXG; ++b) below[b] += (b < G && run < target[b]) ? 1u : 0u;
+                run += g[q];
+            }
+        }
+#pragma unroll
+        for (int b = 1; b < MG_MAXG; ++b)
+            if (b < G && below[b]) atomicAdd(&s_spl[b], below[b]);
+    }
+    __syncthreads();
+    if (tid == 0) { s_spl[0] = 0; s_spl[G] = MSD_BINS; }
+    __syncthreads();
+    // exact count matrix and the histogram of what this rank receives
+    {
+        const unsigned int lo_r = s_spl[p.rank], hi_r = s_spl[p.rank + 1];
+        int b = 0;
+        unsigned int bin = (unsigned int)tid * 64;
+        while (b + 1 < G && bin >= s_spl[b + 1]) ++b;
+        unsigned long long acc[MG_MAXG];
+#pragma unroll
+        for (int s = 0; s < MG_MAXG; ++s) acc[s] = 0;
+        for (int k4 = 0; k4 < 16; ++k4) {
+            uint4 v[MG_MAXG];
+#pragma unroll
+            for (int s = 0; s < MG_MAXG; ++s)
+                v[s] = s < G ? (reinterpret_cast<const uint4 *>(p.hist_all + (size_t)s * MSD_BINS) + tid * 16)[k4] : make_uint4(0, 0, 0, 0);
+            uint4 out;
+#pragma unroll
+            for (int q = 0; q < 4; ++q, ++bin) {
+                while (b + 1 < G && bin >= s_spl[b + 1]) {          // bucket boundary inside this thread's range
+#pragma unroll
+                    for (int s = 0; s < MG_MAXG; ++s) {
+                        if (s < G && acc[s]) atomicAdd(&s_cnt[s][b], acc[s]);
+                        acc[s] = 0;
+                    }
+                    ++b;
+                }
+                unsigned int g = 0;
+#pragma unroll
+                for (int s = 0; s < MG_MAXG; ++s) {
+                    const unsigned int c = q == 0 ? v[s].x : q == 1 ? v[s].y : q == 2 ? v[s].z : v[s].w;
+                    acc[s] += c;
+                    g += c;
+                }
+                const unsigned int r = (bin >= lo_r && bin < hi_r) ? g : 0u;
+                if (q == 0) out.x = r; else if (q == 1) out.y = r; else if (q == 2) out.z = r; else out.w = r;
+            }
+            (reinterpret_cast<uint4 *>(p.hist_recv) + tid * 16)[k4] = out;
+        }
+#pragma unroll
+        for (int s = 0; s < MG_MAXG; ++s)
+            if (s < G && acc[s]) atomicAdd(&s_cnt[s][b], acc[s]);
+    }
+    __syncthreads();
+    if (tid < MG_MAXG) {
+        const int b = tid;
+        unsigned long long before = 0, recv_b = 0;
+        for (int s = 0; s < G; ++s) {
+            if (s < p.rank) before += s_cnt[s][b];
+            recv_b += s_cnt[s][b];
+        }
+        p.plan->dst_base[b] = b < G ? before : 0;
+        p.plan->send_count[b] = b < G ? s_cnt[p.rank][b] : 0;
+        p.plan->recv_count[b] = b < G ? s_cnt[b][p.rank] : 0;   // from source b
+        // max over destinations of what they receive
+        unsigned long long mx = b < G ? recv_b : 0;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0x0000ffffu, mx, o);
+            mx = mx > other ? mx : other;
+        }
+        if (tid == 0) {
+            unsigned long long rt = 0;
+            for (int s = 0; s < G; ++s) rt += s_cnt[s][p.rank];
+            p.plan->recv_total = rt;
+            p.plan->max_recv_total = mx;
+            p.plan->total = total;
+            p.plan->ticket = 0;
+        }
+    }
+    if (tid <= MG_MAXG) p.plan->spl[tid] = tid <= G ? s_spl[tid] : MSD_BINS;
+}
+
+// ------------------------------------------------------------------ fused partition + exchange
+struct MgpuScatterParams {
+    const uint32_t *keys;
+    unsigned int n;
+    MgpuPlan *plan;
+    unsigned int *status;          // [tiles][16], zeroed
+    uint32_t *dst[MG_MAXG];        // receive buffers (peer-mapped), one per destination rank
+    SortXform xf;
+    int G;
+};
+
+template <bool IDENT>
+__global__ void __launch_bounds__(MG_NT, 2) mgpu_scatter_kernel(MgpuScatterParams p) {
+    using LB = LookBits<uint32_t>;
+    constexpr int NW = MG_NT / 32;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    uint32_t *s_keys = reinterpret_cast<uint32_t *>(s_raw);                       // [TILE] RAW keys grouped by bucket
+    unsigned char *s_bkt = reinterpret_cast<unsigned char *>(s_keys + MG_TILE);   // [TILE] bucket of every staged key
+    __shared__ unsigned int s_whist[NW][MG_MAXG];      // per-warp bucket counters -> warp offsets inside the bucket
+    __shared__ unsigned int s_boff[MG_MAXG];           // start of every bucket in the staging buffer
+    __shared__ unsigned long long s_gbase[MG_MAXG];    // destination index of staged position 0 of the bucket's run
+    __shared__ unsigned int s_spl[MG_MAXG + 1];
+    __shared__ unsigned short s_lut[256];              // top byte -> first bucket | (splitters inside the byte) << 8
+    __shared__ unsigned int s_tk[2];
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int G = p.G;
+    const unsigned int tiles = (p.n + MG_TILE - 1) / MG_TILE;
+    if (tid <= MG_MAXG) s_spl[tid] = p.plan->spl[tid];
+    if (tid == 0) s_tk[0] = atomicAdd(&p.plan->ticket, 1u);
+    __syncthreads();
+    if (tid < 256) {
+        // buckets that start inside or before this top byte: first = #{b >= 1 : spl[b] <= 256 tid}, inside = those in (256 tid, 256 tid + 255]
+        unsigned int first = 0, inside = 0;
+        for (int b = 1; b < G; ++b) {
+            if (s_spl[b] <= (unsigned int)tid * 256u) ++first;
+            else if (s_spl[b] < (unsigned int)tid * 256u + 256u) ++inside;
+        }
+        s_lut[tid] = (unsigned short)(first | (inside << 8));
+    }
+    unsigned int next_t = 0;
+    if (tid == 0) next_t = atomicAdd(&p.plan->ticket, 1u);
+    __syncthreads();
+
+    for (unsigned int it = 0;; ++it) {
+        const unsigned int t = s_tk[it & 1];
+        if (t >= tiles) break;
+        if (tid < NW * MG_MAXG) (&s_whist[0][0])[tid] = 0;
+        __syncthreads();                                                             // (0)
+        const unsigned int tile_base = t * MG_TILE;
+        const int valid = p.n - tile_base > (unsigned int)MG_TILE ? MG_TILE : (int)(p.n - tile_base);
+        const uint32_t *kin = p.keys + tile_base + tid;
+        uint32_t keys[MG_ITEMS];
+        unsigned int bk[(MG_ITEMS + 3) / 4];           // bucket ids, 8 bits each
+        PackedRanks<MG_ITEMS> ranks;
+#pragma unroll
+        for (int i = 0; i < MG_ITEMS; ++i) keys[i] = (i * MG_NT + tid < valid) ? ldg_stream(kin + i * MG_NT) : 0u;
+#pragma unroll
+        for (int i = 0; i < MG_ITEMS; ++i) {
+            const uint32_t e = IDENT ? keys[i] : key_encode<uint32_t>(keys[i], p.xf);
+            const unsigned int t16 = e >> 16;
+            const unsigned int l = s_lut[t16 >> 8];
+            unsigned int b = l & 0xFFu;
+            for (unsigned int j = 0; j < (l >> 8); ++j) b += (t16 >= s_spl[(l & 0xFFu) + 1 + j]) ? 1u : 0u;
+            unsigned int r = 0;
+            if (i * MG_NT + tid < valid) r = atomicAdd(&s_whist[warp][b], 1u);
+            ranks.set(i, r);
+            if ((i & 3) == 0) bk[i >> 2] = b;
+            else bk[i >> 2] |= b << (8 * (i & 3));
+        }
+        __syncthreads();                                                             // (A)
+        // bucket threads: warp offsets inside the bucket, tile count, publish, scan over the buckets
+        unsigned int cnt = 0;
+        if (tid < MG_MAXG) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { const unsigned int c = s_whist[w][tid]; s_whist[w][tid] = cnt; cnt += c; }
+            if (tid < G) st_relaxed<uint32_t>(p.status + (size_t)t * MG_MAXG + tid, (t == 0 ? LB::INCLUSIVE : LB::PARTIAL) | cnt);
+            unsigned int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < MG_MAXG; o <<= 1) {
+                const unsigned int up = __shfl_up_sync(0x0000ffffu, incl, o);
+                if (tid >= o) incl += up;
+            }
+            s_boff[tid] = incl - cnt;
+        }
+        if (tid == 0) s_tk[(it + 1) & 1] = next_t;
+        __syncthreads();                                                             // (B)
+#pragma unroll
+        for (int i = 0; i < MG_ITEMS; ++i) {
+            if (i * MG_NT + tid < valid) {
+                const unsigned int b = (bk[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                const unsigned int pos = s_boff[b] + s_whist[warp][b] + ranks.get(i);
+                s_keys[pos] = keys[i];
+                s_bkt[pos] = (unsigned char)b;
+            }
+        }
+        if (tid == 0 && s_tk[(it + 1) & 1] < tiles) next_t = atomicAdd(&p.plan->ticket, 1u);
+        // look-back per destination
+        if (tid < MG_MAXG) {
+            unsigned long long excl = 0;
+            if (t > 0 && tid < G) {
+                int u = (int)t - 1;
+                bool done = false;
+                while (!done) {
+                    uint32_t w[RX_LOOK];
+                    bool all_valid;
+                    do {
+                        all_valid = true;
+#pragma unroll
+                        for (int k = 0; k < RX_LOOK; ++k) {
+                            w[k] = LB::INCLUSIVE;
+                            if (u - k >= 0) w[k] = ld_relaxed<uint32_t>(p.status + (size_t)(u - k) * MG_MAXG + tid);
+                            all_valid = all_valid && ((w[k] & LB::FLAGS) != 0);
+                        }
+                    } while (!all_valid);
+#pragma unroll
+                    for (int k = 0; k < RX_LOOK; ++k) {
+                        if (!done) {
+                            excl += w[k] & LB::MASK;
+                            done = (w[k] & LB::FLAGS) == LB::INCLUSIVE;
+                        }
+                    }
+                    u -= RX_LOOK;
+                }
+                st_relaxed<uint32_t>(p.status + (size_t)t * MG_MAXG + tid, LB::INCLUSIVE | (uint32_t)(excl + cnt));
+            }
+            s_gbase[tid] = (tid < G ? p.plan->dst_base[tid] : 0ull) + excl - s_boff[tid];
+        }
+        __syncthreads();                                                             // (C)
+        // write out: consecutive threads -> consecutive addresses of one destination's receive buffer
+#pragma unroll
+        for (int k = 0; k < MG_ITEMS; ++k) {
+            const int i = tid + k * MG_NT;
+            if (i < valid) {
+                const unsigned int b = s_bkt[i];
+                p.dst[b][s_gbase[b] + (unsigned long long)i] = s_keys[i];
+            }
+        }
+        // the next iteration's first barrier (0) separates this write-out from the next tile's staging writes
+    }
+}
+
+}  // namespace b200
+
+extern "C" {
+
+int32_t b200_mgpu_plan_bytes(size_t *bytes) {
+    if (!bytes) return B200_INVALID_VALUE;
+    *bytes = b200::align_up(sizeof(b200::MgpuPlan), 256);
+    return B200_OK;
+}
+
+static bool mgpu_xform(int dtype, int descending, b200::SortXform &xf);
+
+int32_t b200_mgpu_hist16(const void *keys, int32_t dtype_key, int64_t n, int32_t descending, void *hist16_dev,
+                         b200_stream_t stream) {
+    using namespace b200;
+    SortXform xf;
+    if (!mgpu_xform(dtype_key, descending, xf)) return B200_UNSUPPORTED;
+    if (n < 0 || n > (1LL << 30) || !hist16_dev || (n > 0 && !keys)) return B200_INVALID_VALUE;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    B200_CUDA_TRY(cudaMemsetAsync(hist16_dev, 0, (size_t)MSD_BINS * 4, st));
+    if (n == 0) return B200_OK;
+    const bool ident = xf.base_enc == 0 && xf.fmn == 0 && xf.mag_mask == 0 && xf.desc == 0;
+    const size_t smem = (size_t)MSD_H16_WORDS * 4;
+    int64_t grid = devinfo().sm_count;
+    const int64_t need = cdiv(n, (int64_t)MSD_H16_THREADS * MSD_H16_VPT * 4);
+    if (grid > need) grid = need;
+    if (ident) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(msd_hist16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        msd_hist16_kernel<true><<<(unsigned int)grid, MSD_H16_THREADS, smem, st>>>(static_cast<const uint32_t *>(keys), n, xf,
+                                                                                 static_cast<unsigned int *>(hist16_dev));
+    } else {
+        B200_CUDA_TRY(cudaFuncSetAttribute(msd_hist16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        msd_hist16_kernel<false><<<(unsigned int)grid, MSD_H16_THREADS, smem, st>>>(static_cast<const uint32_t *>(keys), n, xf,
+                                                                                  static_cast<unsigned int *>(hist16_dev));
+    }
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
+int32_t b200_mgpu_plan(const void *hist_all_dev, int32_t nranks, int32_t rank, void *plan_dev, void *hist_recv_dev,
+                       b200_stream_t stream) {
+    using namespace b200;
+    if (!hist_all_dev || !plan_dev || !hist_recv_dev || nranks < 1 || nranks > MG_MAXG || rank < 0 || rank >= nranks)
+        return B200_INVALID_VALUE;
+    MgpuPlanParams pp{};
+    pp.hist_all = static_cast<const unsigned int *>(hist_all_dev);
+    pp.plan = static_cast<MgpuPlan *>(plan_dev);
+    pp.hist_recv = static_cast<unsigned int *>(hist_recv_dev);
+    pp.G = nranks; pp.rank = rank;
+    mgpu_plan_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pp);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
+int32_t b200_mgpu_scatter_workspace_bytes(int64_t n, size_t *bytes) {
+    using namespace b200;
+    if (!bytes || n < 0) return B200_INVALID_VALUE;
+    *bytes = align_up((size_t)cdiv(n, MG_TILE) * MG_MAXG * 4, 256);
+    return B200_OK;
+}
+
+int32_t b200_mgpu_scatter(void *workspace, size_t workspace_bytes, const void *keys, int32_t dtype_key, int64_t n,
+                          int32_t descending, void *plan_dev, void *const *dst_keys, int32_t nranks,
+                          b200_stream_t stream) {
+    using namespace b200;
+    SortXform xf;
+    if (!mgpu_xform(dtype_key, descending, xf)) return B200_UNSUPPORTED;
+    if (n < 0 || n > (1LL << 30) || !plan_dev || !dst_keys || nranks < 1 || nranks > MG_MAXG) return B200_INVALID_VALUE;
+    if (n == 0) return B200_OK;
+    size_t need = 0;
+    b200_mgpu_scatter_workspace_bytes(n, &need);
+    if (!workspace || !keys) return B200_INVALID_VALUE;
+    if (workspace_bytes < need) return B200_WORKSPACE_TOO_SMALL;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    B200_CUDA_TRY(cudaMemsetAsync(workspace, 0, need, st));
+    MgpuScatterParams sp{};
+    sp.keys = static_cast<const uint32_t *>(keys);
+    sp.n = (unsigned int)n;
+    sp.plan = static_cast<MgpuPlan *>(plan_dev);
+    sp.status = static_cast<unsigned int *>(workspace);
+    for (int b = 0; b < MG_MAXG; ++b) sp.dst[b] = static_cast<uint32_t *>(b < nranks ? dst_keys[b] : nullptr);
+    sp.xf = xf; sp.G = nranks;
+    const bool ident = xf.base_enc == 0 && xf.fmn == 0 && xf.mag_mask == 0 && xf.desc == 0;
+    const size_t smem = (size_t)MG_TILE * 5;
+    int64_t grid = (int64_t)devinfo().sm_count * 2;
+    const int64_t tiles = cdiv(n, MG_TILE);
+    if (grid > tiles) grid = tiles;
+    if (ident) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(mgpu_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mgpu_scatter_kernel<true><<<(unsigned int)grid, MG_NT, smem, st>>>(sp);
+    } else {
+        B200_CUDA_TRY(cudaFuncSetAttribute(mgpu_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mgpu_scatter_kernel<false><<<(unsigned int)grid, MG_NT, smem, st>>>(sp);
+    }
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
+}  // extern "C"
+
+// Same key transform as api_sort.cu's make_xform for the 32-bit key types (keys-only: NaN payloads kept, sign dropped).
+static bool mgpu_xform(int dtype, int descending, b200::SortXform &x) {
+    using namespace b200;
+    x = SortXform{};
+    const uint64_t all = 0xFFFFFFFFull, sign = 0x80000000ull;
+    x.sign = sign;
+    x.desc = descending ? all : 0;
+    x.inf_bits = all;
+    switch (dtype) {
+        case B200_U32: return true;
+        case B200_I32: x.base_enc = sign; x.base_dec = sign; return true;
+        case B200_F32:
+            x.inf_bits = 0x7F800000ull;
+            x.base_enc = sign; x.base_dec = all; x.fmn = all & ~sign; x.mag_mask = all & ~sign; x.nan_or = 0;
+            return true;
+        default: return false;
+    }
+}

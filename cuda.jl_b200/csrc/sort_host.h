@@ -21,6 +21,10 @@ struct SortCall {
     SortXform xf;
     cudaStream_t stream;
     size_t *query;         // non-null: only compute the workspace size
+    const void *keys_src;  // KEYS: where the unsorted keys are read from (nullptr: `keys` itself, in place).  The sorted
+                           // result always lands in `keys`; `keys_src` is only read (multi-GPU: the receive buffer).
+    const void *hist16_in; // hybrid MSD path: device histogram of the top 16 bits of the order-mapped keys, computed
+                           // by the caller (b200_mgpu_plan) — the sort then skips its own histogram pass
 };
 
 int32_t sort_run_k1(const SortCall &);

@@ -117,7 +117,8 @@ template <bool IDENT>
 static int32_t msd_launch(const SortCall &c, const MsdBuffers &b, uint32_t *alt, cudaStream_t st) {
     const int64_t n = c.n;
     const DevInfo &dev = devinfo();
-    {   // H: histogram of the top 16 bits
+    const void *src = c.keys_src ? c.keys_src : c.keys;
+    if (!c.hist16_in) {   // H: histogram of the top 16 bits
         static thread_local KernelSetup ks;
         int per_sm = 1;
         const size_t smem = (size_t)MSD_H16_WORDS * 4;
@@ -126,12 +127,12 @@ static int32_t msd_launch(const SortCall &c, const MsdBuffers &b, uint32_t *alt,
         int64_t grid = dev.sm_count;
         const int64_t need = cdiv(n, (int64_t)MSD_H16_THREADS * MSD_H16_VPT * 4);
         if (grid > need) grid = need;
-        msd_hist16_kernel<IDENT><<<(unsigned int)grid, MSD_H16_THREADS, smem, st>>>(static_cast<const uint32_t *>(c.keys), n, c.xf, b.hist16);
+        msd_hist16_kernel<IDENT><<<(unsigned int)grid, MSD_H16_THREADS, smem, st>>>(static_cast<const uint32_t *>(src), n, c.xf, b.hist16);
         B200_CHECK_LAUNCH();
     }
     {   // PL
         MsdPlanParams pp{};
-        pp.hist16 = b.hist16; pp.seg_start = b.seg_start; pp.seg_list = b.seg_list; pp.l1_tile_start = b.l1_tile_start;
+        pp.hist16 = c.hist16_in ? static_cast<const unsigned int *>(c.hist16_in) : b.hist16; pp.seg_start = b.seg_start; pp.seg_list = b.seg_list; pp.l1_tile_start = b.l1_tile_start;
         pp.ctl = b.ctl; pp.n = (unsigned int)n; pp.tile2 = MSD_TILE;
         pp.cap_a = LEAF_MAX_SEG; pp.cap_b = 0;
         static const unsigned int min_avg = (unsigned int)tune_int("B200_MSD_MIN_AVG", (int)MSD_MIN_AVG);
@@ -148,7 +149,7 @@ static int32_t msd_launch(const SortCall &c, const MsdBuffers &b, uint32_t *alt,
         auto kern = msd_scatter_kernel<1, MSD_NT, MSD_ITEMS, IDENT>;
         int32_t rc = setup_kernel(ks, kern, MSD_NT, ssmem, &per_sm);
         if (rc != B200_OK) return rc;
-        sp.keys_in = static_cast<const uint32_t *>(c.keys); sp.keys_out = alt; sp.status = b.status1;
+        sp.keys_in = static_cast<const uint32_t *>(src); sp.keys_out = alt; sp.status = b.status1;
         int64_t grid = (int64_t)dev.sm_count * per_sm;
         const int64_t tiles = cdiv(n, MSD_TILE);
         if (grid > tiles) grid = tiles;
@@ -197,7 +198,10 @@ static int32_t msd_launch(const SortCall &c, const MsdBuffers &b, uint32_t *alt,
 static bool msd_eligible(const SortCall &c) {
     static const int on = tune_int("B200_SORT_HYBRID", 1);
     static const int min_log2 = tune_int("B200_MSD_MIN_LOG2N", 27);
-    return on && c.mode == SORT_KEYS && c.n >= (1LL << min_log2) && c.n <= MSD_MAX_N;
+    // with a caller-supplied histogram (multi-GPU slice: dense inside a narrow key range) the plan kernel's density
+    // test decides alone, and the attempt costs no extra pass
+    const int64_t min_n = c.hist16_in ? (1LL << 24) : (1LL << min_log2);
+    return on && c.mode == SORT_KEYS && c.n >= min_n && c.n <= MSD_MAX_N;
 }
 #else
 static bool msd_eligible(const SortCall &) { return false; }
@@ -280,7 +284,7 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
             B200_CUDA_TRY(cudaFuncSetAttribute(radix_hist_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
             hist_attr[hdev] = true;
         }
-        radix_hist_kernel<K><<<(unsigned int)grid, 512, hist_smem, st>>>(static_cast<const K *>(c.keys), n, c.xf, ghist, gate);
+        radix_hist_kernel<K><<<(unsigned int)grid, 512, hist_smem, st>>>(static_cast<const K *>(c.keys_src ? c.keys_src : c.keys), n, c.xf, ghist, gate);
         B200_CHECK_LAUNCH();
         radix_bins_kernel<<<P, RX_RADIX, 0, st>>>(ghist, bins, gate);
         B200_CHECK_LAUNCH();
@@ -317,7 +321,7 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
         } else {
             // ping-pong between the caller's buffer and the workspace copy
             const bool from_user = (pass & 1) == 0;
-            p.keys_in = from_user ? c.keys : kbuf0;
+            p.keys_in = from_user ? (pass == 0 && c.keys_src ? c.keys_src : c.keys) : kbuf0;
             p.keys_out = from_user ? kbuf0 : c.keys;
             if (pay) {
                 p.vals_in = from_user ? c.payload : vbuf0;

@@ -174,7 +174,7 @@ struct MsdPlanParams {
     unsigned int min_avg;           // hybrid only when n / non-empty segments >= min_avg
 };
 
-__global__ void __launch_bounds__(1024, 1) msd_plan_kernel(MsdPlanParams p) {
+static __global__ void __launch_bounds__(1024, 1) msd_plan_kernel(MsdPlanParams p) {
     __shared__ unsigned int s_wsum[32], s_wne[32], s_wmax[32];
     __shared__ unsigned int s_excl[1024];
     __shared__ unsigned int s_t[256];
@@ -372,27 +372,22 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msd_scatter_kernel(MsdScatterPa
             for (int i = 0; i < ITEMS; ++i) keys[i] = key_encode<uint32_t>(keys[i], p.xf);
         }
         PackedRanks<ITEMS> ranks;
-        // Sorted / clustered input: every warp row (32 consecutive keys) carries ONE digit, and 10240 atomics on one
-        // shared counter would serialise.  If all of this warp's rows are digit-uniform, lane 0 reserves 32 ranks per
-        // row with a single atomic (~2 extra instructions per row to find out; random data takes the plain path).
-        bool rows_uniform = false;
+        // Sorted / clustered input: a whole tile carries ONE digit, and 10240 atomics on one shared counter would
+        // serialise.  If all 32 x ITEMS keys of this warp share their digit, lane 0 reserves the warp's ranks with a
+        // single atomic (~1 extra instruction per key row to find out; random data takes the plain path).
+        bool warp_uniform = false;
         if (full) {
-            bool same = true;
+            uint32_t diff = keys[0] ^ __shfl_sync(0xffffffffu, keys[0], 0);
 #pragma unroll
-            for (int i = 0; i < ITEMS; ++i) {
-                const unsigned int d = (keys[i] >> SHIFT) & 0xFFu;
-                const unsigned int d0 = __shfl_sync(0xffffffffu, d, 0);     // every lane executes every shuffle:
-                same = same & (d == d0);                                     // no short-circuit around a .sync op
-            }
-            rows_uniform = __all_sync(0xffffffffu, same);
+            for (int i = 1; i < ITEMS; ++i) diff |= keys[i] ^ keys[0];
+            warp_uniform = __all_sync(0xffffffffu, ((diff >> SHIFT) & 0xFFu) == 0u);
         }
-        if (rows_uniform) {
+        if (warp_uniform) {
+            unsigned int b = 0;
+            if (lane == 0) b = atomicAdd(&s_hist[(keys[0] >> SHIFT) & 0xFFu], 32u * ITEMS);
+            b = __shfl_sync(0xffffffffu, b, 0) + lane;
 #pragma unroll
-            for (int i = 0; i < ITEMS; ++i) {
-                unsigned int b = 0;
-                if (lane == 0) b = atomicAdd(&s_hist[(keys[i] >> SHIFT) & 0xFFu], 32u);
-                ranks.set(i, __shfl_sync(0xffffffffu, b, 0) + lane);
-            }
+            for (int i = 0; i < ITEMS; ++i) ranks.set(i, b + 32u * i);
         } else if (full) {
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) ranks.set(i, atomicAdd(&s_hist[(keys[i] >> SHIFT) & 0xFFu], 1u));
@@ -552,6 +547,7 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
     __shared__ int s_over;
 
     if (ld_cg_u32(&p.ctl->mode) == 0) return;
+    if (BITS == 16 && ld_cg_u32(&p.ctl->pad) == 0) return;               // the 8-bit kernel finished every segment
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int nne = ld_cg_u32(&p.ctl->nne);
     for (int i = tid; i < WORDS / 4; i += NT) reinterpret_cast<uint4 *>(s_bins)[i] = make_uint4(0, 0, 0, 0);
@@ -575,8 +571,12 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
         if (k + 2 * G < nne) seg_n2 = __ldg(p.seg_list + k + 2 * G);
         const int m = (int)(hi - lo);
         bool mine;
-        if constexpr (BITS == 8) mine = m <= (int)p.cap8;
-        else mine = m > (int)p.cap8 || ld_cg_u32(p.redo + k) != 0;
+        if constexpr (BITS == 8) {
+            mine = m <= (int)p.cap8;
+            if (!mine && tid == 0) atomicAdd(&p.ctl->pad, 1u);            // ctl->pad counts the segments left to the 16-bit kernel
+        } else {
+            mine = m > (int)p.cap8 || ld_cg_u32(p.redo + k) != 0;
+        }
         if (mine) {                                          // uniform over the CTA
             uint32_t *base = p.keys + lo;
             // ---- count: one shared atomic per key.  Loads go out CH at a time (a load -> atomic -> load chain would
@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
             if (over) {
                 // a value occurs 128 times or more: hand the segment to the 16-bit kernel and clear the table
                 for (int i = tid; i < WORDS / 4; i += NT) reinterpret_cast<uint4 *>(s_bins)[i] = make_uint4(0, 0, 0, 0);
-                if (tid == 0) { p.redo[k] = 1u; s_over = 0; }
+                if (tid == 0) { p.redo[k] = 1u; s_over = 0; atomicAdd(&p.ctl->pad, 1u); }
             } else {
                 // ---- expand: walk the table in value order; 32 words (32 * PER_WORD values) per step and warp.
                 // A lane emits its word's values `count` times each at consecutive positions, lanes back to back.
@@ -640,7 +640,6 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
                 const uint32_t hi16 = ld_coh(base) & 0xFFFF0000u;        // any key of the segment (read before any write: barrier above)
                 unsigned int *wbw = s_bins + warp * WORDS_PER_WARP;
                 __syncthreads();                                          // every warp has read base[0]
-#pragma unroll 2
                 for (int j = lane; j < WORDS_PER_WARP; j += 32) {
                     const unsigned int w = wbw[j];
                     wbw[j] = 0;                                           // table is clean again for the next segment
@@ -652,15 +651,31 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
                         if (lane >= o) incl += up;
                     }
                     const unsigned int tot = __shfl_sync(0xffffffffu, incl, 31);
-                    if (w) {
-                        unsigned int pos = run + incl - cnt;
-                        const uint32_t v0 = hi16 | (uint32_t)((warp * WORDS_PER_WARP + j) * PER_WORD);
+                    // Output slot q of this step belongs to the lane whose [incl - cnt, incl) holds q: every lane takes
+                    // one slot per round (a per-lane "emit my word's keys" loop ran with 13 of 32 lanes active and
+                    // cost 150 instructions per 32 keys; this costs ~35 and its stores are perfectly coalesced).
+                    for (unsigned int q0 = 0; q0 < tot; q0 += 32) {
+                        const unsigned int q = q0 + lane;
+                        int l = 0;
 #pragma unroll
-                        for (int f = 0; f < PER_WORD; ++f) {
-                            unsigned int c = (w >> (f * BITS)) & FIELD;
-                            const uint32_t key = v0 + f;
-                            const uint32_t outv = IDENT ? key : key_decode<uint32_t>(key, p.xf);
-                            while (c--) base[pos++] = outv;
+                        for (int sft = 16; sft > 0; sft >>= 1) {
+                            const unsigned int v = __shfl_sync(0xffffffffu, incl, l + sft - 1);
+                            if (v <= q) l += sft;
+                        }
+                        const unsigned int wl = __shfl_sync(0xffffffffu, w, l);
+                        const unsigned int il = __shfl_sync(0xffffffffu, incl, l);
+                        const unsigned int cl = __shfl_sync(0xffffffffu, cnt, l);
+                        if (q < tot) {
+                            const unsigned int r = q - (il - cl);             // rank inside the owner's word
+                            unsigned int f;
+                            if constexpr (BITS == 8) {
+                                const unsigned int c0 = wl & 0xFFu, c1 = c0 + ((wl >> 8) & 0xFFu), c2 = c1 + ((wl >> 16) & 0xFFu);
+                                f = (r >= c0) + (r >= c1) + (r >= c2);
+                            } else {
+                                f = r >= (wl & 0xFFFFu);
+                            }
+                            const uint32_t key = hi16 | (uint32_t)((warp * WORDS_PER_WARP + (j - lane) + l) * PER_WORD + f);
+                            base[run + q] = IDENT ? key : key_decode<uint32_t>(key, p.xf);
                         }
                     }
                     run += tot;

@@ -177,6 +177,43 @@ int32_t b200_scan_carry(void *workspace, size_t workspace_bytes,
                         const void *init_host, const void *carry_dev, int32_t carry_count,
                         b200_stream_t stream);
 
+/* ---- multi-GPU keys-only sort (no reference counterpart) -------------------------------------
+ * One process (Julia task) per GPU strings four calls together around ONE all-gather of 256 KB per rank; splitters,
+ * counts and destination offsets never visit the host (csrc/mgpu_sort.cu):
+ *   b200_mgpu_hist16   -> hist16_dev[65536] (uint32): histogram of the top 16 bits of the order-mapped keys
+ *   (all-gather the G histograms into hist_all_dev[G][65536])
+ *   b200_mgpu_plan     -> *plan_dev (b200_mgpu_plan_t) and hist_recv_dev[65536]; identical decisions on every rank
+ *   b200_mgpu_scatter  -> one pass over the shard; bucket b is stored straight into dst_keys[b] (rank b's receive
+ *                         buffer, peer-mapped: NVLink stores) starting at plan.dst_base[b]; every receive buffer must
+ *                         hold plan.max_recv_total keys; the caller synchronises the ranks before and after
+ *   b200_sort_keys_from(src = receive buffer, dst, hist16_dev = hist_recv_dev) -> the rank's sorted slice
+ * Key types: UInt32, Int32, Float32; n <= 2^30 per rank; at most 16 ranks. */
+typedef struct b200_mgpu_plan {
+    uint32_t spl[17];             /* bucket b = 16-bit bins [spl[b], spl[b+1]) */
+    uint32_t ticket;
+    uint32_t pad[2];
+    uint64_t dst_base[16];        /* element index of this rank's first key inside destination b's receive buffer */
+    uint64_t send_count[16];      /* keys this rank sends to destination b */
+    uint64_t recv_count[16];      /* keys this rank receives from source s */
+    uint64_t recv_total;          /* keys this rank receives in total (its slice of the result) */
+    uint64_t max_recv_total;      /* maximum of recv_total over all ranks */
+    uint64_t total;               /* N */
+} b200_mgpu_plan_t;
+int32_t b200_mgpu_plan_bytes(size_t *bytes);
+int32_t b200_mgpu_hist16(const void *keys, int32_t dtype_key, int64_t n, int32_t descending, void *hist16_dev,
+                         b200_stream_t stream);
+int32_t b200_mgpu_plan(const void *hist_all_dev, int32_t nranks, int32_t rank, void *plan_dev, void *hist_recv_dev,
+                       b200_stream_t stream);
+int32_t b200_mgpu_scatter_workspace_bytes(int64_t n, size_t *bytes);
+int32_t b200_mgpu_scatter(void *workspace, size_t workspace_bytes, const void *keys, int32_t dtype_key, int64_t n,
+                          int32_t descending, void *plan_dev, void *const *dst_keys, int32_t nranks,
+                          b200_stream_t stream);
+/* sort! of `n` keys read from `src` into `dst` (src is only read; src == dst sorts in place; workspace as for
+ * b200_sort_workspace_bytes(dtype_key, -1, n, 1)).  hist16_dev, if not NULL, is the exact histogram of the top 16 bits
+ * of the order-mapped keys of `src` (b200_mgpu_plan's hist_recv_dev): the sort then skips its own histogram pass. */
+int32_t b200_sort_keys_from(void *workspace, size_t workspace_bytes, const void *src, void *dst, int32_t dtype_key,
+                            int64_t n, int32_t descending, const void *hist16_dev, b200_stream_t stream);
+
 /* ---- sort: Base.sort! / sortperm! hooks (sorting.jl:1003-1070) ---------- */
 /* Order is Julia's `isless`: -Inf < ... < -0.0 < +0.0 < ... < +Inf < NaN (all
  * NaNs equal, last), two's-complement order for signed ints; `descending` is
