@@ -101,37 +101,44 @@ msd_hist16_kernel(const uint32_t *__restrict__ keys, int64_t n, SortXform xf, un
     }
     constexpr int64_t CHUNK_V = (int64_t)MSD_H16_THREADS * MSD_H16_VPT;
     const int64_t nchunks = (nvec + CHUNK_V - 1) / CHUNK_V;
+    const int lane = tid & 31, warp = tid >> 5;
     for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
-        const int64_t v0 = c * CHUNK_V + tid;
+        // warp w reads the contiguous vectors [c CHUNK_V + w 32 VPT, + 32 VPT): row k = 32 vectors = 128 consecutive keys
+        const int64_t v0 = c * CHUNK_V + (int64_t)warp * (32 * MSD_H16_VPT) + lane;
         Vec16 r[MSD_H16_VPT];
         const bool whole = (c + 1) * CHUNK_V <= nvec;        // uniform: every thread has all its vectors
 #pragma unroll
         for (int k = 0; k < MSD_H16_VPT; ++k) {
-            const int64_t v = v0 + (int64_t)k * MSD_H16_THREADS;
+            const int64_t v = v0 + (int64_t)k * 32;
             if (whole || v < nvec) r[k] = ldg_stream16(body + v * 4);
         }
-        bool uniform = false;
         if (whole) {
-            // Sorted / clustered input: all 1024 keys of the warp fall into one bin, and 32 lanes adding to one word
-            // serialise.  One extra LOP3 per key finds out; lane 0 then adds the warp's whole count in one atomic.
             if constexpr (!IDENT) {
 #pragma unroll
                 for (int k = 0; k < MSD_H16_VPT; ++k)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) r[k].w[j] = key_encode<uint32_t>(r[k].w[j], xf);
             }
-            const uint32_t ref = __shfl_sync(0xffffffffu, r[0].w[0], 0);
-            uint32_t diff = 0;
+            // Sorted / clustered input: a row's 128 keys fall into one bin and 32 lanes adding to one word serialise
+            // (measured 4.5 ms instead of 0.9 ms at 2^30).  Row 0 is the probe; behind it every row tests itself and a
+            // uniform row is counted by lane 0 alone.
+            const uint32_t ref0 = __shfl_sync(0xffffffffu, r[0].w[0], 0);
+            const uint32_t d0 = (r[0].w[0] ^ ref0) | (r[0].w[1] ^ ref0) | (r[0].w[2] ^ ref0) | (r[0].w[3] ^ ref0);
+            if (__all_sync(0xffffffffu, (d0 >> 16) == 0)) {
 #pragma unroll
-            for (int k = 0; k < MSD_H16_VPT; ++k)
+                for (int k = 0; k < MSD_H16_VPT; ++k) {
+                    const uint32_t ref = __shfl_sync(0xffffffffu, r[k].w[0], 0);
+                    const uint32_t d = (r[k].w[0] ^ ref) | (r[k].w[1] ^ ref) | (r[k].w[2] ^ ref) | (r[k].w[3] ^ ref);
+                    if (__all_sync(0xffffffffu, (d >> 16) == 0)) {
+                        if (lane == 0) {
+                            const uint32_t inc = ((ref & 0x10000u) ? 0x10000u : 1u) * 128u;
+                            const uint32_t old = atomicAdd(&sh16[ref >> 17], inc);
+                            if (old & 0xC000C000u) s_flush = 1;
+                        }
+                    } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) diff |= r[k].w[j] ^ ref;
-            uniform = __all_sync(0xffffffffu, (diff >> 16) == 0);
-            if (uniform) {
-                if ((threadIdx.x & 31) == 0) {
-                    const uint32_t inc = ((ref & 0x10000u) ? 0x10000u : 1u) * (32u * MSD_H16_VPT * 4u);
-                    const uint32_t old = atomicAdd(&sh16[ref >> 17], inc);
-                    if (old & 0xC000C000u) s_flush = 1;
+                        for (int j = 0; j < 4; ++j) count_enc(r[k].w[j]);
+                    }
                 }
             } else {
 #pragma unroll
@@ -142,7 +149,7 @@ msd_hist16_kernel(const uint32_t *__restrict__ keys, int64_t n, SortXform xf, un
         } else {
 #pragma unroll
             for (int k = 0; k < MSD_H16_VPT; ++k) {
-                const int64_t v = v0 + (int64_t)k * MSD_H16_THREADS;
+                const int64_t v = v0 + (int64_t)k * 32;
                 if (v < nvec) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) count(r[k].w[j]);
@@ -372,22 +379,30 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msd_scatter_kernel(MsdScatterPa
             for (int i = 0; i < ITEMS; ++i) keys[i] = key_encode<uint32_t>(keys[i], p.xf);
         }
         PackedRanks<ITEMS> ranks;
-        // Sorted / clustered input: a whole tile carries ONE digit, and 10240 atomics on one shared counter would
-        // serialise.  If all 32 x ITEMS keys of this warp share their digit, lane 0 reserves the warp's ranks with a
-        // single atomic (~1 extra instruction per key row to find out; random data takes the plain path).
-        bool warp_uniform = false;
+        // Sorted / clustered input: whole rows (32 consecutive keys) carry ONE digit, and thousands of atomics on one
+        // shared counter would serialise (measured: P2 of a sorted 2^30 input 36 ms instead of 2.7 ms).  Such rows
+        // reserve their 32 ranks with a single atomic by lane 0.
+        // Row 0 is the probe: random data never has 32 equal digits in a row, sorted / clustered data nearly always.
+        bool clustered = false;
         if (full) {
-            uint32_t diff = keys[0] ^ __shfl_sync(0xffffffffu, keys[0], 0);
-#pragma unroll
-            for (int i = 1; i < ITEMS; ++i) diff |= keys[i] ^ keys[0];
-            warp_uniform = __all_sync(0xffffffffu, ((diff >> SHIFT) & 0xFFu) == 0u);
+            const unsigned int d = (keys[0] >> SHIFT) & 0xFFu;
+            clustered = __all_sync(0xffffffffu, d == __shfl_sync(0xffffffffu, d, 0));
         }
-        if (warp_uniform) {
-            unsigned int b = 0;
-            if (lane == 0) b = atomicAdd(&s_hist[(keys[0] >> SHIFT) & 0xFFu], 32u * ITEMS);
-            b = __shfl_sync(0xffffffffu, b, 0) + lane;
+        if (clustered) {
 #pragma unroll
-            for (int i = 0; i < ITEMS; ++i) ranks.set(i, b + 32u * i);
+            for (int i = 0; i < ITEMS; ++i) {
+                const unsigned int d = (keys[i] >> SHIFT) & 0xFFu;
+                const unsigned int d0 = __shfl_sync(0xffffffffu, d, 0);
+                unsigned int r;
+                if (__all_sync(0xffffffffu, d == d0)) {            // warp-uniform branch
+                    unsigned int b = 0;
+                    if (lane == 0) b = atomicAdd(&s_hist[d0], 32u);
+                    r = __shfl_sync(0xffffffffu, b, 0) + lane;
+                } else {
+                    r = atomicAdd(&s_hist[d], 1u);                 // the row that holds a digit boundary
+                }
+                ranks.set(i, r);
+            }
         } else if (full) {
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) ranks.set(i, atomicAdd(&s_hist[(keys[i] >> SHIFT) & 0xFFu], 1u));
@@ -533,6 +548,7 @@ struct MsdLeafParams {
 };
 
 constexpr int MSD_LEAF_CHUNK = 8;      // global loads in flight per thread in the count phase
+constexpr unsigned int MSD_LEAF_HEAVY = 1024;   // 16-bit kernel: values with at least this many copies are written by the whole CTA
 
 template <int BITS, int NT, bool IDENT>
 __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLeafParams p) {
@@ -545,13 +561,15 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
     extern __shared__ __align__(16) unsigned int s_bins[];   // [WORDS] packed counters, all zero between segments
     __shared__ unsigned int s_wtot[NW];
     __shared__ int s_over;
+    __shared__ unsigned int s_nheavy;
+    __shared__ uint4 s_heavy[BITS == 16 ? 65536 / MSD_LEAF_HEAVY + 1 : 1];   // {value, first position, copies}
 
     if (ld_cg_u32(&p.ctl->mode) == 0) return;
     if (BITS == 16 && ld_cg_u32(&p.ctl->pad) == 0) return;               // the 8-bit kernel finished every segment
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int nne = ld_cg_u32(&p.ctl->nne);
     for (int i = tid; i < WORDS / 4; i += NT) reinterpret_cast<uint4 *>(s_bins)[i] = make_uint4(0, 0, 0, 0);
-    if (tid == 0) s_over = 0;
+    if (tid == 0) { s_over = 0; s_nheavy = 0; }
 
     // Segments are dealt round-robin to the persistent CTAs (independent work: no ticket).  Bounds of the next segment
     // and the id of the one after are loaded an iteration early; every thread loads the same words (broadcast).
@@ -586,12 +604,29 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
                 if (i0 + CH * NT <= m) {
 #pragma unroll
                     for (int c = 0; c < CH; ++c) kk[c] = ld_coh(base + i0 + c * NT + tid);
+                    // heavy duplicates (the 16-bit kernel's reason to exist): a row of 32 equal keys is counted by
+                    // lane 0 alone instead of 32 serialised atomics on one word; row 0 is the probe
+                    bool dup_rows = false;
+                    if constexpr (BITS == 16) dup_rows = __all_sync(0xffffffffu, kk[0] == __shfl_sync(0xffffffffu, kk[0], 0));
+                    if (dup_rows) {
 #pragma unroll
-                    for (int c = 0; c < CH; ++c) {
-                        const unsigned int v = kk[c] & 0xFFFFu;
-                        const unsigned int sh = (v % PER_WORD) * BITS;
-                        const unsigned int old = atomicAdd(&s_bins[v / PER_WORD], 1u << sh);
-                        if (BITS == 8 && (old & (0x80u << sh))) s_over = 1;
+                        for (int c = 0; c < CH; ++c) {
+                            const unsigned int v = kk[c] & 0xFFFFu;
+                            const unsigned int sh = (v % PER_WORD) * BITS;
+                            if (__all_sync(0xffffffffu, kk[c] == __shfl_sync(0xffffffffu, kk[c], 0))) {
+                                if (lane == 0) atomicAdd(&s_bins[v / PER_WORD], 32u << sh);
+                            } else {
+                                atomicAdd(&s_bins[v / PER_WORD], 1u << sh);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) {
+                            const unsigned int v = kk[c] & 0xFFFFu;
+                            const unsigned int sh = (v % PER_WORD) * BITS;
+                            const unsigned int old = atomicAdd(&s_bins[v / PER_WORD], 1u << sh);
+                            if (BITS == 8 && (old & (0x80u << sh))) s_over = 1;
+                        }
                     }
                 } else {
 #pragma unroll
@@ -651,34 +686,40 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
                         if (lane >= o) incl += up;
                     }
                     const unsigned int tot = __shfl_sync(0xffffffffu, incl, 31);
-                    // Output slot q of this step belongs to the lane whose [incl - cnt, incl) holds q: every lane takes
-                    // one slot per round (a per-lane "emit my word's keys" loop ran with 13 of 32 lanes active and
-                    // cost 150 instructions per 32 keys; this costs ~35 and its stores are perfectly coalesced).
-                    for (unsigned int q0 = 0; q0 < tot; q0 += 32) {
-                        const unsigned int q = q0 + lane;
-                        int l = 0;
+                    if (w) {
+                        // a lane writes its word's values at consecutive positions, lanes back to back: counts are
+                        // nearly always 0 or 1, so this is one predicated store per field plus a rare copy loop
+                        unsigned int pos = run + incl - cnt;
+                        const uint32_t v0 = hi16 | (uint32_t)((warp * WORDS_PER_WARP + j) * PER_WORD);
 #pragma unroll
-                        for (int sft = 16; sft > 0; sft >>= 1) {
-                            const unsigned int v = __shfl_sync(0xffffffffu, incl, l + sft - 1);
-                            if (v <= q) l += sft;
-                        }
-                        const unsigned int wl = __shfl_sync(0xffffffffu, w, l);
-                        const unsigned int il = __shfl_sync(0xffffffffu, incl, l);
-                        const unsigned int cl = __shfl_sync(0xffffffffu, cnt, l);
-                        if (q < tot) {
-                            const unsigned int r = q - (il - cl);             // rank inside the owner's word
-                            unsigned int f;
-                            if constexpr (BITS == 8) {
-                                const unsigned int c0 = wl & 0xFFu, c1 = c0 + ((wl >> 8) & 0xFFu), c2 = c1 + ((wl >> 16) & 0xFFu);
-                                f = (r >= c0) + (r >= c1) + (r >= c2);
-                            } else {
-                                f = r >= (wl & 0xFFFFu);
+                        for (int f = 0; f < PER_WORD; ++f) {
+                            const unsigned int c = (w >> (f * BITS)) & FIELD;
+                            if (c) {
+                                const uint32_t outv = IDENT ? (v0 + f) : key_decode<uint32_t>(v0 + f, p.xf);
+                                if (BITS == 16 && c >= MSD_LEAF_HEAVY) {
+                                    // thousands of copies of one value: written by the whole CTA after the walk
+                                    const unsigned int e = atomicAdd(&s_nheavy, 1u);
+                                    s_heavy[e] = make_uint4(outv, pos, c, 0u);
+                                } else {
+                                    base[pos] = outv;
+#pragma unroll 1
+                                    for (unsigned int kk = 1; kk < c; ++kk) base[pos + kk] = outv;
+                                }
+                                pos += c;
                             }
-                            const uint32_t key = hi16 | (uint32_t)((warp * WORDS_PER_WARP + (j - lane) + l) * PER_WORD + f);
-                            base[run + q] = IDENT ? key : key_decode<uint32_t>(key, p.xf);
                         }
                     }
                     run += tot;
+                }
+                if constexpr (BITS == 16) {
+                    __syncthreads();
+                    const unsigned int nh = s_nheavy;
+                    for (unsigned int e = 0; e < nh; ++e) {
+                        const uint4 h = s_heavy[e];
+                        for (unsigned int i = tid; i < h.z; i += NT) base[h.y + i] = h.x;
+                    }
+                    __syncthreads();
+                    if (tid == 0) s_nheavy = 0;
                 }
             }
             __syncthreads();        // table clean / redo written before the next segment's atomics

@@ -37,6 +37,30 @@ class DeviceOps:
         mapreducedim_(f, op, R, shard, init=init)
         return R
 
+    def extrema_pair(self, shard):
+        """(min, max) of one shard in ONE pass (B200_OP_EXTREMA); the neutral pair for an empty shard."""
+        from .mapreduce import mapreducedim_, identity, extrema_rf, neutral_element, min_, max_, _fill
+        R = CuArray.undef(shard.eltype, (2, 1), shard.buf.device)
+        if shard.length == 0:
+            host = np.array([neutral_element(min_, shard.eltype), neutral_element(max_, shard.eltype)], dtype=dt.np_dtype(shard.eltype))
+            R.buf.copy_(CuArray(host).buf)
+            return R.reshape((2,))
+        mapreducedim_(identity, extrema_rf, R, shard.vec(), init=0)
+        return R.reshape((2,))
+
+    def extrema_combine(self, g2, R):
+        """g2: (2, G) gathered pairs -> host (min over row 1, max over row 2) with the library's min / max kernels."""
+        from .mapreduce import mapreducedim_, identity, min_, max_, neutral_element
+        G = g2.dims[1]
+        mins = CuArray(g2.buf.view(-1), (2, G), g2.eltype)
+        out = CuArray.undef(g2.eltype, (2, 1), g2.buf.device)
+        # rows of a column-major (2, G) matrix: reduce dims=2 with min gives (min of mins, min of maxs); likewise max
+        mapreducedim_(identity, min_, out, mins, init=neutral_element(min_, g2.eltype))
+        lo = out.to_host().reshape(-1)[0]
+        mapreducedim_(identity, max_, out, mins, init=neutral_element(max_, g2.eltype))
+        hi = out.to_host().reshape(-1)[1]
+        return lo, hi
+
     def scan(self, op, out, shard, init, exclusive, carry=None, carry_count=0):
         from .accumulate import scan_
         return scan_(op, out, shard, 1, init=init, exclusive=exclusive, carry=carry, carry_count=carry_count)
@@ -44,6 +68,77 @@ class DeviceOps:
     def sort_keys(self, c, rev):
         from .sorting import sort_
         return sort_(c, rev=rev)
+
+    # -- device-driven keys-only sample sort (csrc/mgpu_sort.cu) ---------------------------------------------
+    MGPU_KEY_TYPES = (dt.U32, dt.I32, dt.F32)
+
+    def mgpu_hist16(self, shard, rev):
+        """Histogram of the top 16 bits of the order-mapped keys: CuArray{UInt32}(65536)."""
+        from . import _lib
+        lib = _lib.load()
+        hist = CuArray.undef(dt.U32, (65536,), shard.buf.device)
+        _lib.check(lib.b200_mgpu_hist16(shard.pointer if shard.length else None, shard.eltype, shard.length,
+                                        1 if rev else 0, hist.pointer, current_stream_handle(shard.buf.device)))
+        return hist
+
+    def mgpu_plan(self, hist_all, G, r):
+        """(plan buffer, hist_recv) on the device from the all-gathered histograms; then ONE small device-to-host
+        copy of the plan (the only synchronisation of the sort: the slice length sizes the result)."""
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        dev = hist_all.device
+        nb = ctypes.c_size_t(0)
+        _lib.check(lib.b200_mgpu_plan_bytes(ctypes.byref(nb)))
+        plan = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+        hist_recv = CuArray.undef(dt.U32, (65536,), dev)
+        _lib.check(lib.b200_mgpu_plan(hist_all.data_ptr(), G, r, plan.data_ptr(), hist_recv.pointer,
+                                      current_stream_handle(dev)))
+        host = plan.cpu().numpy()
+        u64 = host[80:488].view(np.uint64)                  # dst_base[16], send_count[16], recv_count[16], 3 scalars
+        info = {"spl": host[:68].view(np.uint32)[:G + 1].copy(), "dst_base": u64[:G].copy(), "send_count": u64[16:16 + G].copy(),
+                "recv_count": u64[32:32 + G].copy(), "recv_total": int(u64[48]), "max_recv_total": int(u64[49]),
+                "total": int(u64[50])}
+        return plan, hist_recv, info
+
+    def mgpu_exchange(self, shard, rev, plan, info, group):
+        """Fused partition + all-to-all: one pass over the shard, every bucket stored straight into its destination
+        rank's symmetric receive buffer (NVLink peer stores).  Returns a uint8 view of this rank's received keys."""
+        import ctypes
+        from . import _lib
+        from .cuarray import Workspace
+        lib = _lib.load()
+        G, r = _world(group)
+        dev = shard.buf.device
+        kbuf, khdl = _symm_buffer("keys", max(info["max_recv_total"], 1) * 4, dev, group)
+        nb = ctypes.c_size_t(0)
+        _lib.check(lib.b200_mgpu_scatter_workspace_bytes(shard.length, ctypes.byref(nb)))
+        ws = Workspace(nb.value, dev)
+        ptrs = (ctypes.c_void_p * G)(*[int(x) for x in khdl.buffer_ptrs])
+        khdl.barrier()                                      # nobody still reads its receive buffer from a previous call
+        _lib.check(lib.b200_mgpu_scatter(ws.ptr, ws.nbytes, shard.pointer if shard.length else None, shard.eltype,
+                                         shard.length, 1 if rev else 0, plan.data_ptr(), ptrs, G,
+                                         current_stream_handle(dev)))
+        khdl.barrier()                                      # every rank's peer stores have landed
+        return kbuf[:info["recv_total"] * 4]
+
+    def sort_keys_from(self, src_u8, eltype, n, rev, hist_recv):
+        """Local sort of the received keys: reads the receive buffer, writes a fresh result (no copy in between)."""
+        import ctypes
+        from . import _lib
+        from .cuarray import Workspace
+        lib = _lib.load()
+        dev = src_u8.device
+        out = CuArray.undef(eltype, (n,), dev)
+        if n == 0:
+            return out
+        nb = ctypes.c_size_t(0)
+        _lib.check(lib.b200_sort_workspace_bytes(eltype, -1, n, 1, ctypes.byref(nb)))
+        ws = Workspace(nb.value, dev)
+        _lib.check(lib.b200_sort_keys_from(ws.ptr, ws.nbytes, src_u8.data_ptr(), out.pointer, eltype, n, 1 if rev else 0,
+                                           hist_recv.pointer if hist_recv is not None else None,
+                                           current_stream_handle(dev)))
+        return out
 
     def sort_pairs(self, keys, payload, rev):
         import ctypes
@@ -185,8 +280,24 @@ def dist_mapreduce(f, op, shard, group=None, ops=None):
 
 
 def dist_extrema(shard, group=None, ops=None):
-    from .mapreduce import identity, max_, min_
-    return (dist_mapreduce(identity, min_, shard, group, ops), dist_mapreduce(identity, max_, shard, group, ops))
+    """extrema over the concatenation of all shards: ONE fused pass per shard (B200_OP_EXTREMA writes (min, max)),
+    one all-gather of the G pairs, and the library's own min / max over the gathered values — Julia's rules
+    (NaN-propagating, -0.0 < +0.0) hold across ranks because the same kernels combine the partials."""
+    from .mapreduce import identity, max_, min_, extrema_rf, mapreducedim_
+    ops = ops or DeviceOps()
+    G, r = _world(group)
+    if not hasattr(ops, "extrema_pair"):
+        return (dist_mapreduce(identity, min_, shard, group, ops), dist_mapreduce(identity, max_, shard, group, ops))
+    pair = ops.extrema_pair(shard)                                   # CuArray{T}(2): (min, max), neutral for an empty shard
+    gathered = CuArray.undef(shard.eltype, (2 * G,), shard.buf.device)
+    if shard.buf.is_cuda and hasattr(dist, "all_gather_into_tensor"):
+        dist.all_gather_into_tensor(_typed(gathered), _typed(pair), group=group)
+    else:
+        _all_gather_fallback(_typed(gathered), _typed(pair), group)
+    g2 = gathered.reshape((2, G))                                    # column-major: column k = rank k's (min, max)
+    R = CuArray.undef(shard.eltype, (2, 1), shard.buf.device)
+    h = ops.extrema_combine(g2, R)
+    return h[0], h[1]
 
 
 # ----------------------------------------------------------------------------- scan
@@ -381,6 +492,9 @@ def dist_sort(shard, rev=False, group=None, ops=None):
         local = shard.copy()
         ops.sort_keys(local, rev)
         return local, np.array([[local.length]])
+    if (G <= MAX_PARTITION_BUCKETS and hasattr(ops, "mgpu_hist16") and shard.eltype in ops.MGPU_KEY_TYPES
+            and DEVICE_DRIVEN_SORT and _device_path_available(shard, ops)):
+        return _dist_sort_device(shard, rev, group, ops)
     if G > MAX_PARTITION_BUCKETS or not hasattr(ops, "partition"):
         return _dist_sort_sorted_first(shard, rev, group, ops)
     spl = _splitters(shard, rev, group, ops)            # regular samples of the unsorted shard
@@ -394,6 +508,44 @@ def dist_sort(shard, rev=False, group=None, ops=None):
         (recv,), cmat = _exchange(parted, bounds, group)
     ops.sort_keys(recv, rev)
     return recv, cmat
+
+
+DEVICE_DRIVEN_SORT = _os.environ.get("B200_DEVICE_DRIVEN_SORT", "1") != "0"
+
+
+def _device_path_available(shard, ops):
+    if not shard.buf.is_cuda:
+        return getattr(ops, "emulates_device_path", False)      # CPU tests: numpy stand-in for the kernels
+    try:
+        import torch.distributed._symmetric_memory  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+def _dist_sort_device(shard, rev, group, ops):
+    """Keys-only sample sort whose splitters, count matrix and destination offsets are computed ON THE DEVICE from one
+    all-gather of the ranks' 16-bit key histograms (csrc/mgpu_sort.cu):
+        hist16 (1 read of the shard) -> all-gather 256 KB per rank -> plan kernel -> [one 512-byte read-back: the slice
+        length] -> fused partition + exchange (1 read of the shard, peer stores over NVLink) -> local hybrid MSD sort
+        reading the receive buffer and reusing the plan's histogram.
+    Buckets are ranges of 16-bit bins, so their sizes are within one bin's population of N / G and equal keys always
+    share a rank; max_recv_total sizes the receive buffers before anything is sent."""
+    G, r = _world(group)
+    dev = shard.buf.device
+    if shard.length > (1 << 30):
+        raise NotGraftedError("more than 2^30 keys per rank")
+    hist = ops.mgpu_hist16(shard, rev)
+    ht = hist.typed().view(torch.int32) if hist.buf.numel() else torch.zeros(65536, dtype=torch.int32, device=dev)
+    hist_all = torch.empty(G * 65536, dtype=torch.int32, device=dev)
+    if dev.type == "cuda":
+        dist.all_gather_into_tensor(hist_all, ht, group=group)
+    else:
+        _all_gather_fallback(hist_all, ht, group)
+    plan, hist_recv, info = ops.mgpu_plan(hist_all, G, r)
+    recv = ops.mgpu_exchange(shard, rev, plan, info, group)
+    out = ops.sort_keys_from(recv, shard.eltype, info["recv_total"], rev, hist_recv)
+    return out, info
 
 
 def _dist_sort_sorted_first(shard, rev, group, ops):

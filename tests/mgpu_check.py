@@ -24,7 +24,9 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
-    lg = int(sys.argv[1]) if len(sys.argv) > 1 else 22
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    timing = "--no-timing" not in sys.argv
+    lg = int(args[0]) if args else 22
     n = 1 << lg
     rng = np.random.default_rng(99)
     full_f = rng.standard_normal(n).astype(np.float32)
@@ -63,6 +65,15 @@ def main():
     check("dist mapreduce(abs2,+) BFloat16", abs(a2 - ref) <= 2.0 ** -7 * ref)
     mn, mx = mg.dist_extrema(si)
     check("dist extrema Int64", (int(mn), int(mx)) == (int(full_i.min()), int(full_i.max())))
+    mn, mx = mg.dist_extrema(sfz)
+    check("dist extrema Float32", (float(mn), float(mx)) == (float(fz.min()), float(fz.max())))
+    fb = np.zeros(n, dtype=np.bool_); fb[n - 3] = True                      # only the last rank holds a True
+    sb = b.CuArray(fb[lo:hi])
+    check("dist any / all / max / min over Bool shards",
+          (bool(mg.dist_mapreduce(b.identity, b.or_, sb)), bool(mg.dist_mapreduce(b.identity, b.and_, sb)),
+           bool(mg.dist_mapreduce(b.identity, b.max_, sb)), bool(mg.dist_mapreduce(b.identity, b.min_, sb))) == (True, False, True, False))
+    check("dist maximum / minimum UInt32", (int(mg.dist_mapreduce(b.identity, b.max_, su)), int(mg.dist_mapreduce(b.identity, b.min_, su)))
+          == (int(full_u.max()), int(full_u.min())))
     check("dist cumsum Int64", np.array_equal(gather(mg.dist_accumulate(b.add, si)), np.cumsum(full_i)))
     check("dist exclusive cumsum Int64", np.array_equal(gather(mg.dist_accumulate(b.add, si, exclusive=True)),
                                                          np.concatenate([[0], np.cumsum(full_i)[:-1]])))
@@ -75,7 +86,17 @@ def main():
         perm = gather(mg.dist_sortperm(sf, rev=rev))
         check(f"dist sortperm Float32 rev={rev}", np.array_equal(perm, oracle.sortperm(full_f, rev=rev)))
     check("dist sort! UInt32", np.array_equal(gather(mg.dist_sort(su)[0]), np.sort(full_u)))
+    check("dist sort! UInt32 rev", np.array_equal(gather(mg.dist_sort(su, rev=True)[0]), np.sort(full_u)[::-1]))
+    dupk = (full_u % np.uint32(7)) * np.uint32(600_000_000)                  # 7 distinct keys: whole bins move together
+    check("dist sort! UInt32, 7 distinct keys", np.array_equal(gather(mg.dist_sort(b.CuArray(dupk[lo:hi]))[0]), np.sort(dupk)))
+    si32 = full_i.astype(np.int32)
+    check("dist sort! Int32", np.array_equal(gather(mg.dist_sort(b.CuArray(si32[lo:hi]))[0]), np.sort(si32)))
     check("dist sortperm UInt32", np.array_equal(gather(mg.dist_sortperm(su)), oracle.sortperm(full_u)))
+    if not timing:
+        if rank == 0:
+            print("ALL OK" if ok else "SOME FAILED", flush=True)
+        dist.destroy_process_group()
+        sys.exit(0 if ok else 1)
     # timing of the sharded sort on device-resident shards (max over ranks)
     big = 1 << 28
     g = torch.Generator(device="cuda"); g.manual_seed(1 + rank)

@@ -69,6 +69,63 @@ class FakeOps:
         keys.buf.copy_(torch.from_numpy(np.ascontiguousarray(k[perm]).view(np.uint8).copy()))
         payload.buf.copy_(torch.from_numpy(np.ascontiguousarray(p[perm]).view(np.uint8).copy()))
 
+    # ---- numpy stand-ins for csrc/mgpu_sort.cu (same decisions as the kernels; the kernels themselves are tested
+    #      on one GPU with G emulated ranks in tests/test_mgpu_sort_gpu.py)
+    emulates_device_path = True
+
+    @property
+    def MGPU_KEY_TYPES(self):
+        d = self.b.dtypes
+        return (d.U32, d.I32, d.F32)
+
+    def _bins(self, a, rev):
+        k = self.o.total_order_key(a).astype(np.uint32)
+        return ((~k if rev else k) >> np.uint32(16)).astype(np.int64)
+
+    def mgpu_hist16(self, shard, rev):
+        h = np.bincount(self._bins(shard.to_host(), rev), minlength=65536).astype(np.uint32)
+        return _mk(h, self.b)
+
+    def mgpu_plan(self, hist_all, G, r):
+        H = hist_all.numpy().view(np.uint32).reshape(G, 65536).astype(np.int64)
+        g = H.sum(axis=0)
+        excl = np.concatenate([[0], np.cumsum(g)[:-1]])
+        total = int(g.sum())
+        spl = np.array([0] + [int((excl < (total * b) // G).sum()) for b in range(1, G)] + [65536], dtype=np.int64)
+        cnt = np.array([[H[s, spl[b]:spl[b + 1]].sum() for b in range(G)] for s in range(G)], dtype=np.int64)   # [src, dst]
+        hist_recv = np.where((np.arange(65536) >= spl[r]) & (np.arange(65536) < spl[r + 1]), g, 0).astype(np.uint32)
+        info = {"spl": spl, "dst_base": cnt[:r].sum(axis=0), "send_count": cnt[r], "recv_count": cnt[:, r],
+                "recv_total": int(cnt[:, r].sum()), "max_recv_total": int(cnt.sum(axis=0).max()), "total": total}
+        return None, _mk(hist_recv, self.b), info
+
+    def mgpu_exchange(self, shard, rev, plan, info, group):
+        a = shard.to_host()
+        G = dist.get_world_size(group)
+        r = dist.get_rank(group)
+        bucket = np.searchsorted(info["spl"][1:-1], self._bins(a, rev), side="right")
+        raw = a.view(np.uint32)
+        send = [torch.from_numpy(raw[bucket == d].astype(np.int64)) for d in range(G)]
+        assert [t.numel() for t in send] == [int(x) for x in info["send_count"]]
+        recv = [torch.empty(int(c), dtype=torch.int64) for c in info["recv_count"]]
+        # gloo has no all_to_all on CPU in every build: pairwise send / recv in rank order
+        for src in range(G):
+            for dst in range(G):
+                if src == dst == r:
+                    recv[src].copy_(send[dst])
+                elif src == r:
+                    dist.send(send[dst], dst, group=group)
+                elif dst == r:
+                    dist.recv(recv[src], src, group=group)
+        got = torch.cat(recv).to(torch.int64).numpy().astype(np.uint32)
+        assert got.size == info["recv_total"]
+        return torch.from_numpy(got.view(np.uint8).copy())
+
+    def sort_keys_from(self, src_u8, eltype, n, rev, hist_recv):
+        a = src_u8.numpy().view(self.b.dtypes.np_dtype(eltype))[:n]
+        if n:
+            np.testing.assert_array_equal(np.bincount(self._bins(a, rev), minlength=65536), hist_recv.to_host())
+        return _mk(self.o.sort(a, rev=rev), self.b)
+
     def partition(self, keys, payload, splitters, nbuckets, rev):
         k = keys.to_host()
         ke = self.o.total_order_key(k)
