@@ -182,13 +182,25 @@ def run_product(args, rank, world, local_rank):
     rc = b.CuArray.undef(dt.I64, (1, 1))
     ninf = -np.inf
 
+    coalesce = {"ok": hasattr(dist, "_coalescing_manager")} if dist is not None else {"ok": False}
+
     def exchange():
         if dist is None:
             return
-        # rows are split across ranks (column blocks): dims=2 partial row sums and the scalars need an allreduce
-        dist.all_reduce(r2_32.typed()); dist.all_reduce(r2_16.typed())
-        dist.all_reduce(rm_32.typed(), op=dist.ReduceOp.MAX); dist.all_reduce(rm_16.typed(), op=dist.ReduceOp.MAX)
-        dist.all_reduce(rc.typed())
+        # rows are split across ranks (column blocks): dims=2 partial row sums and the scalars need an allreduce.
+        # The five small collectives go out as ONE NCCL group (one launch) where torch offers it.
+        def five():
+            dist.all_reduce(r2_32.typed()); dist.all_reduce(r2_16.typed())
+            dist.all_reduce(rm_32.typed(), op=dist.ReduceOp.MAX); dist.all_reduce(rm_16.typed(), op=dist.ReduceOp.MAX)
+            dist.all_reduce(rc.typed())
+        if coalesce["ok"]:
+            try:
+                with dist._coalescing_manager(device=dev):
+                    five()
+                return
+            except Exception:
+                coalesce["ok"] = False
+        five()
 
     def step():
         # interleave the matrices so no input is still L2-resident when it is read again
@@ -478,7 +490,7 @@ def finish_with_sharded_extras(line, rank, fn, timeout=None):
     JSON line on rank 0 and ends the process with status 0 — whatever fn does: an exception is recorded in the line, and a
     watchdog prints the line without the extras if fn has not returned after `timeout` seconds (a rank stuck in a
     collective must not hold the headline numbers back).  Never returns."""
-    timeout = float(os.environ.get("B200_BENCH_SHARDED_TIMEOUT", "150")) if timeout is None else timeout
+    timeout = float(os.environ.get("B200_BENCH_SHARDED_TIMEOUT", "240")) if timeout is None else timeout
     lock = threading.Lock()
     state = {"printed": False}
 
@@ -505,7 +517,9 @@ def finish_with_sharded_extras(line, rank, fn, timeout=None):
 def run_extras_sharded(b, dt, torch, dist, dev, rank, world, peak):
     """configs[2..4] on `world` GPUs (one process per GPU, NCCL): cumsum and sort! / sortperm of 2^30 elements in total
     (strong scaling), mapreduce(abs2, +) / extrema over 2^30 BFloat16 per GPU (weak scaling, 2^33 on 8 GPUs).  Device
-    time between CUDA events on every rank, max over ranks."""
+    time between CUDA events on every rank, max over ranks.  Every strong-scaling item carries `ms_1gpu` — the SAME
+    total problem on one GPU through the single-GPU entry points, timed on rank 0 in this very run — and
+    `speedup_vs_1gpu`; every result is verified on the device (`verified`)."""
     from b200arrays import multigpu as mg
     out = {}
 
@@ -521,10 +535,69 @@ def run_extras_sharded(b, dt, torch, dist, dev, rank, world, peak):
             best = float(t.item()) if best is None else min(best, float(t.item()))
         return best
 
-    def item(name, fn, fmt, reps=3):
+    def one_gpu(make, fn, reps=2):
+        """rank 0 times fn(x) on x = make() (the whole problem on one GPU); the others wait."""
+        ms = None
+        if rank == 0:
+            try:
+                x = make()
+                fn(x)
+                ts = []
+                for _ in range(reps):
+                    torch.cuda.synchronize()
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s.record(); fn(x); e.record(); e.synchronize()
+                    ts.append(s.elapsed_time(e))
+                ms = min(ts)
+                del x
+            except Exception as ex:
+                ms = None
+                print(f"1-GPU baseline failed: {ex}", file=sys.stderr)
+            torch.cuda.empty_cache()
+        dist.barrier()
+        return ms
+
+    def all_ok(flag):
+        t = torch.tensor([1 if flag else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def sorted_across_ranks(res, n_total, et_torch, rev=False):
+        """sorted inside the rank, boundary keys ordered across ranks, slice lengths sum to N (all on the device)."""
+        t = res.typed()
+        if et_torch == torch.uint32:
+            t = t.view(torch.int32) ^ -2**31                      # order-preserving signed view
+        ok = bool((t[1:] >= t[:-1]).all()) if t.numel() > 1 else True
+        edge = torch.zeros(3, device=dev, dtype=torch.float64)     # first, last, count
+        if t.numel():
+            edge[0] = t[0].double(); edge[1] = t[-1].double()
+        edge[2] = t.numel()
+        edges = [torch.empty_like(edge) for _ in range(world)]
+        dist.all_gather(edges, edge)
+        last = None
+        total = 0
+        for e in edges:
+            total += int(e[2].item())
+            if int(e[2].item()) == 0:
+                continue
+            if last is not None and float(e[0].item()) < last:
+                ok = False
+            last = float(e[1].item())
+        return all_ok(ok and total == n_total)
+
+    def item(name, fn, fmt, reps=3, base=None, verify=None):
         # every rank runs the same code on the same shapes, so a failure is the same on all of them: record it and go on
         try:
-            out[name] = fmt(timed(fn, reps))
+            ms = timed(fn, reps)
+            d = fmt(ms)
+            if verify is not None:
+                d["verified"] = verify()
+            if base is not None:
+                ms1 = one_gpu(*base)
+                if rank == 0 and ms1:
+                    d["ms_1gpu"] = ms1
+                    d["speedup_vs_1gpu"] = ms1 / ms
+            out[name] = d
         except Exception as e:
             out[name] = {"failed": f"{type(e).__name__}: {e}"}
 
@@ -532,23 +605,72 @@ def run_extras_sharded(b, dt, torch, dist, dev, rank, world, peak):
     total = 1 << lg
     n = total // world
     g = torch.Generator(device=dev); g.manual_seed(0xB200 + 100 + rank)
+    g1 = torch.Generator(device=dev); g1.manual_seed(0xB200 + 99)
+
     V = torch.rand(n, device=dev, generator=g, dtype=torch.float32)
     cV = b.CuArray.from_torch(V)
-    item("cumsum 2^30 Float32 total", lambda: mg.dist_accumulate(b.add, cV),
+    holder = {}
+
+    def cumsum_f32():
+        holder["r"] = mg.dist_accumulate(b.add, cV)
+
+    def verify_cumsum(shard_t, acc_dtype, tol):
+        """last element of every rank's output == sum of all elements up to the end of that rank (computed independently
+        with torch in Float64 / Int64); exact for integers, relative tolerance for floats."""
+        r = holder["r"].typed()
+        part = shard_t.to(acc_dtype).sum()
+        parts = [torch.empty_like(part) for _ in range(world)]
+        dist.all_gather(parts, part)
+        want = sum(float(p.item()) if tol else int(p.item()) for p in parts[:rank + 1])
+        got = float(r[-1].item()) if tol else int(r[-1].item())
+        ok = abs(got - want) <= tol * abs(want) if tol else got == want
+        return all_ok(ok)
+
+    def mk_f32():
+        return b.CuArray.from_torch(torch.rand(total, device=dev, generator=g1, dtype=torch.float32))
+
+    item("cumsum 2^30 Float32 total", cumsum_f32,
          lambda ms: {"ms": ms, "GB/s": 8 * total / ms / 1e6, "per_gpu_frac_of_measured_peak": 8 * total / ms / 1e6 / world / peak,
-                     "note": "shard-local reduce + all-gather of the shard totals + scan with the carry: 3N traffic for 2N algorithmic bytes"})
-    item("sort! 2^30 Float32 total", lambda: mg.dist_sort(cV), lambda ms: {"ms": ms, "Gkeys/s": total / ms / 1e6})
-    item("sortperm 2^30 Float32 total", lambda: mg.dist_sortperm(cV), lambda ms: {"ms": ms, "Gkeys/s": total / ms / 1e6}, reps=2)
+                     "note": "shard-local reduce + all-gather of the shard totals + scan seeded on the device with the totals "
+                             "before this rank (b200_scan_carry): 3N traffic for 2N algorithmic bytes, no host sync"},
+         base=(mk_f32, lambda x: b.accumulate_(b.add, x, x)),
+         verify=lambda: verify_cumsum(V, torch.float64, 4 * 30 * 2.0 ** -24))
+
+    def sort_f32():
+        holder["r"] = mg.dist_sort(cV)[0]
+
+    item("sort! 2^30 Float32 total", sort_f32, lambda ms: {"ms": ms, "Gkeys/s": total / ms / 1e6},
+         base=(mk_f32, lambda x: b.sort_(x)), verify=lambda: sorted_across_ranks(holder["r"], total, torch.float32))
+    item("sortperm 2^30 Float32 total", lambda: mg.dist_sortperm(cV), lambda ms: {"ms": ms, "Gkeys/s": total / ms / 1e6}, reps=2,
+         base=(mk_f32, lambda x: b.sortperm(x)))
+    holder.clear()
     del V, cV
     torch.cuda.empty_cache()
     I = torch.randint(-2**20, 2**20, (n,), device=dev, generator=g, dtype=torch.int64)
     cI = b.CuArray.from_torch(I)
-    item("cumsum 2^30 Int64 total", lambda: mg.dist_accumulate(b.add, cI),
-         lambda ms: {"ms": ms, "GB/s": 16 * total / ms / 1e6, "per_gpu_frac_of_measured_peak": 16 * total / ms / 1e6 / world / peak})
+
+    def cumsum_i64():
+        holder["r"] = mg.dist_accumulate(b.add, cI)
+
+    item("cumsum 2^30 Int64 total", cumsum_i64,
+         lambda ms: {"ms": ms, "GB/s": 16 * total / ms / 1e6, "per_gpu_frac_of_measured_peak": 16 * total / ms / 1e6 / world / peak},
+         base=(lambda: b.CuArray.from_torch(torch.randint(-2**20, 2**20, (total,), device=dev, generator=g1, dtype=torch.int64)),
+               lambda x: b.accumulate_(b.add, x, x)),
+         verify=lambda: verify_cumsum(I, torch.int64, 0))
+    holder.clear()
     del I, cI
+    torch.cuda.empty_cache()
     U = torch.randint(-2**31, 2**31 - 1, (n,), device=dev, generator=g, dtype=torch.int32)
     cU = b.CuArray.from_torch(U, (n,), dt.U32)
-    item("sort! 2^30 UInt32 total", lambda: mg.dist_sort(cU), lambda ms: {"ms": ms, "Gkeys/s": total / ms / 1e6})
+
+    def sort_u32():
+        holder["r"] = mg.dist_sort(cU)[0]
+
+    item("sort! 2^30 UInt32 total", sort_u32, lambda ms: {"ms": ms, "Gkeys/s": total / ms / 1e6},
+         base=(lambda: b.CuArray.from_torch(torch.randint(-2**31, 2**31 - 1, (total,), device=dev, generator=g1, dtype=torch.int32), (total,), dt.U32),
+               lambda x: b.sort_(x)),
+         verify=lambda: sorted_across_ranks(holder["r"], total, torch.uint32))
+    holder.clear()
     del U, cU
     torch.cuda.empty_cache()
     H = torch.randn(total, device=dev, generator=g, dtype=torch.float32).to(torch.bfloat16)
@@ -556,7 +678,8 @@ def run_extras_sharded(b, dt, torch, dist, dev, rank, world, peak):
     item(f"mapreduce(abs2,+) 2^30 BFloat16 per GPU x {world}", lambda: mg.dist_mapreduce(b.abs2, b.add, cH),
          lambda ms: {"ms": ms, "GB/s": 2.0 * total * world / ms / 1e6, "per_gpu_frac_of_measured_peak": 2.0 * total / ms / 1e6 / peak})
     item(f"extrema 2^30 BFloat16 per GPU x {world}", lambda: mg.dist_extrema(cH),
-         lambda ms: {"ms": ms, "GB/s": 2 * 2.0 * total * world / ms / 1e6, "note": "two passes (min, max), one allreduce each"})
+         lambda ms: {"ms": ms, "GB/s": 2.0 * total * world / ms / 1e6, "per_gpu_frac_of_measured_peak": 2.0 * total / ms / 1e6 / peak,
+                     "note": "one fused (min, max) pass per shard, one all-gather of the G pairs"})
     return out
 
 

@@ -317,13 +317,13 @@ int32_t b200_mgpu_plan_bytes(size_t *bytes) {
     return B200_OK;
 }
 
-static bool mgpu_xform(int dtype, int descending, b200::SortXform &xf);
+static bool mgpu_xform(int dtype, int descending, b200::SortXform &xf, int nan_canonical = 0);
 
-int32_t b200_mgpu_hist16(const void *keys, int32_t dtype_key, int64_t n, int32_t descending, void *hist16_dev,
-                         b200_stream_t stream) {
+int32_t b200_mgpu_hist16(const void *keys, int32_t dtype_key, int64_t n, int32_t descending, int32_t nan_canonical,
+                         void *hist16_dev, b200_stream_t stream) {
     using namespace b200;
     SortXform xf;
-    if (!mgpu_xform(dtype_key, descending, xf)) return B200_UNSUPPORTED;
+    if (!mgpu_xform(dtype_key, descending, xf, nan_canonical)) return B200_UNSUPPORTED;
     if (n < 0 || n > (1LL << 30) || !hist16_dev || (n > 0 && !keys)) return B200_INVALID_VALUE;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     B200_CUDA_TRY(cudaMemsetAsync(hist16_dev, 0, (size_t)MSD_BINS * 4, st));
@@ -407,8 +407,9 @@ int32_t b200_mgpu_scatter(void *workspace, size_t workspace_bytes, const void *k
 
 }  // extern "C"
 
-// Same key transform as api_sort.cu's make_xform for the 32-bit key types (keys-only: NaN payloads kept, sign dropped).
-static bool mgpu_xform(int dtype, int descending, b200::SortXform &x) {
+// Same key transform as api_sort.cu's make_xform for the 32-bit key types.  nan_canonical = 0: keys-only sort! (NaN
+// payloads kept, sign dropped); 1: sortperm / pairs (every NaN maps to one key, like partition.cu's part_xform).
+static bool mgpu_xform(int dtype, int descending, b200::SortXform &x, int nan_canonical) {
     using namespace b200;
     x = SortXform{};
     const uint64_t all = 0xFFFFFFFFull, sign = 0x80000000ull;
@@ -420,7 +421,8 @@ static bool mgpu_xform(int dtype, int descending, b200::SortXform &x) {
         case B200_I32: x.base_enc = sign; x.base_dec = sign; return true;
         case B200_F32:
             x.inf_bits = 0x7F800000ull;
-            x.base_enc = sign; x.base_dec = all; x.fmn = all & ~sign; x.mag_mask = all & ~sign; x.nan_or = 0;
+            x.base_enc = sign; x.base_dec = all; x.fmn = all & ~sign; x.mag_mask = all & ~sign;
+            x.nan_or = nan_canonical ? all : 0;
             return true;
         default: return false;
     }

@@ -27,6 +27,8 @@ struct PartParams {
     long long dst_base[16];
     int32_t local_bases;     // 1: dst_base is derived from bucket_counts on the device (packed local output)
     const void *splitters;   // G-1 raw keys (device)
+    const b200_mgpu_plan_t *plan;   // non-null (32-bit keys): splitters are the plan's 16-bit bin boundaries and the
+                                    // destination bases come from the plan — both stay on the device (mgpu_sort.cu)
     long long *tile_counts;  // [G][tiles]: counts, then exclusive prefixes over tiles
     long long *bucket_counts;// [G]
     int64_t n;
@@ -55,7 +57,8 @@ __global__ void __launch_bounds__(RX_THREADS) partition_count_kernel(PartParams 
     __shared__ K s_spl[PT_MAXB];
     __shared__ unsigned int s_cnt[PT_MAXB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < p.G - 1) s_spl[tid] = key_encode<K>(static_cast<const K *>(p.splitters)[tid], p.xf);
+    if (tid < p.G - 1) s_spl[tid] = p.plan ? (K)((unsigned long long)p.plan->spl[tid + 1] << (8 * sizeof(K) - 16))
+                                           : key_encode<K>(static_cast<const K *>(p.splitters)[tid], p.xf);
     if (tid < PT_MAXB) s_cnt[tid] = 0;
     __syncthreads();
     const int64_t t = blockIdx.x, tile_base = t * PT_TILE;
@@ -136,7 +139,8 @@ __global__ void __launch_bounds__(RX_THREADS) partition_scatter_kernel(PartParam
     __shared__ unsigned int s_boff[PT_MAXB];       // start of each bucket run inside the staged tile
     __shared__ long long s_dst[PT_MAXB];           // destination element index of the run's first key
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < p.G - 1) s_spl[tid] = key_encode<K>(static_cast<const K *>(p.splitters)[tid], p.xf);
+    if (tid < p.G - 1) s_spl[tid] = p.plan ? (K)((unsigned long long)p.plan->spl[tid + 1] << (8 * sizeof(K) - 16))
+                                           : key_encode<K>(static_cast<const K *>(p.splitters)[tid], p.xf);
     if (tid < RX_WARPS * PT_MAXB) (&s_wcnt[0][0])[tid] = 0;
     __syncthreads();
     const int64_t t = blockIdx.x, tile_base = t * PT_TILE;
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(RX_THREADS) partition_scatter_kernel(PartParam
         unsigned int run = 0;
         for (int w = 0; w < RX_WARPS; ++w) { const unsigned int c = s_wcnt[w][tid]; s_wcnt[w][tid] = run; run += c; }
         s_boff[tid] = run;                         // bucket total for now
-        long long base = p.dst_base[tid];
+        long long base = p.plan ? (long long)p.plan->dst_base[tid] : p.dst_base[tid];
         if (p.local_bases) { base = 0; for (int b = 0; b < tid; ++b) base += p.bucket_counts[b]; }
         s_dst[tid] = base + p.tile_counts[(int64_t)tid * p.tiles + t];
     }
@@ -296,7 +300,7 @@ static int32_t partition_common(void *workspace, size_t workspace_bytes, const v
                                 int32_t dtype_key, int64_t n, const void *splitters, int32_t nbuckets,
                                 int32_t descending, void *bucket_counts_dev, int phase, void *const *dst_keys,
                                 void *const *dst_payload, const int64_t *dst_base, int local_bases,
-                                b200_stream_t stream) {
+                                b200_stream_t stream, const void *plan_dev = nullptr) {
     using namespace b200;
     if (n < 0 || nbuckets < 1 || nbuckets > PT_MAXB || !bucket_counts_dev) return B200_INVALID_VALUE;
     SortXform xf; int kb;
@@ -306,8 +310,10 @@ static int32_t partition_common(void *workspace, size_t workspace_bytes, const v
         if (phase & 1) B200_CUDA_TRY(cudaMemsetAsync(bucket_counts_dev, 0, sizeof(long long) * nbuckets, st));
         return B200_OK;
     }
-    if (!keys_in || (nbuckets > 1 && !splitters)) return B200_INVALID_VALUE;
+    if (!keys_in || (nbuckets > 1 && !splitters && !plan_dev)) return B200_INVALID_VALUE;
+    if (plan_dev && kb != 4) return B200_UNSUPPORTED;
     PartParams p{};
+    p.plan = static_cast<const b200_mgpu_plan_t *>(plan_dev);
     p.keys_in = keys_in; p.vals_in = payload_in;
     p.splitters = splitters; p.bucket_counts = static_cast<long long *>(bucket_counts_dev);
     p.n = n; p.G = nbuckets; p.xf = xf; p.local_bases = local_bases;
@@ -348,6 +354,18 @@ int32_t b200_partition_scatter(void *workspace, size_t workspace_bytes, const vo
                                void *const *dst_payload, const int64_t *dst_base, b200_stream_t stream) {
     return partition_common(workspace, workspace_bytes, keys_in, payload_in, dtype_key, n, splitters, nbuckets, descending,
                             bucket_counts_dev, 2, dst_keys, dst_payload, dst_base, 0, stream);
+}
+
+// Stable partition of (keys, 8-byte payload) by the plan's 16-bit-bin splitters, every bucket stored straight into
+// its destination rank's receive buffers at the plan's offsets (sortperm's exchange; keys-only sorts use
+// b200_mgpu_scatter).  Workspace: b200_partition_workspace_bytes(n, nranks) + 256.
+int32_t b200_mgpu_partition_pairs(void *workspace, size_t workspace_bytes, const void *keys, const void *payload,
+                                  int32_t dtype_key, int64_t n, int32_t descending, const void *plan_dev,
+                                  void *const *dst_keys, void *const *dst_payload, int32_t nranks, b200_stream_t stream) {
+    if (!plan_dev || !workspace || workspace_bytes < 256) return B200_INVALID_VALUE;
+    // the first 256 bytes of the workspace hold the bucket totals the count phase writes
+    return partition_common(static_cast<char *>(workspace) + 256, workspace_bytes - 256, keys, payload, dtype_key, n, nullptr,
+                            nranks, descending, workspace, 3, dst_keys, dst_payload, nullptr, 0, stream, plan_dev);
 }
 
 }  // extern "C"

@@ -97,7 +97,7 @@ template <class LookT> static int32_t dispatch_pass(const OnesweepParams &p, int
 
 #if B200_KEY_BYTES == 4
 // ---- hybrid MSD path (sort_msd.cuh): dense 32-bit keys-only sorts -------------------------------------------
-constexpr int MSD_NT = 512, MSD_ITEMS = 20, MSD_TILE = MSD_NT * MSD_ITEMS;      // P1 / P2 tile
+constexpr int MSD_TILE_MIN = 4096;            // smallest P1 / P2 tile of any configuration (sizes the look-back arrays)
 constexpr int LEAF_NT = 512;
 constexpr unsigned int LEAF8_CAP = 32768;    // segments up to this many keys go to the 8-bit-bin leaf first
 constexpr unsigned int LEAF_MAX_SEG = 65535; // 16-bit bins cannot overflow up to here; longer segments: LSD fallback
@@ -106,6 +106,12 @@ constexpr int64_t MSD_MIN_N = 1LL << 27;     // below this even a full key range
                                              // non-empty segment unless the keys sit in a narrow range; not worth the histogram
 constexpr int64_t MSD_MAX_N = 1LL << 30;     // 32-bit look-back words carry 30-bit counts
 
+// P1 / P2 tile shape: 0 = 512 threads x 20 keys (default); others only in -DB200_TUNING builds (A/B measurements)
+static int msd_cfg() {
+    static const int cfg = tune_int("B200_MSD_CFG", 0);
+    return cfg;
+}
+
 static bool xform_is_identity(const SortXform &x) { return x.base_enc == 0 && x.fmn == 0 && x.mag_mask == 0 && x.desc == 0; }
 
 struct MsdBuffers {
@@ -113,8 +119,9 @@ struct MsdBuffers {
     unsigned int *hist16, *status1, *status2, *redo, *seg_start, *seg_list, *l1_tile_start;
 };
 
-template <bool IDENT>
+template <bool IDENT, int MSD_NT = 512, int MSD_ITEMS = 20>
 static int32_t msd_launch(const SortCall &c, const MsdBuffers &b, uint32_t *alt, cudaStream_t st) {
+    constexpr int MSD_TILE = MSD_NT * MSD_ITEMS;
     const int64_t n = c.n;
     const DevInfo &dev = devinfo();
     const void *src = c.keys_src ? c.keys_src : c.keys;
@@ -232,8 +239,11 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
     static_assert(sizeof(MsdCtl) <= 256, "control block");
     if (hybrid) {
         mb.hist16 = w.take<unsigned int>(MSD_BINS);
-        mb.status1 = reinterpret_cast<unsigned int *>(status);     // P1 has fewer tiles than an LSD pass
-        mb.status2 = w.take<unsigned int>((size_t)(cdiv(n, MSD_TILE) + 256) * RX_RADIX);
+        // P1 of the default configuration has fewer tiles than an LSD pass and shares its look-back array (only one of
+        // the two paths runs); the tuning configurations with smaller tiles get their own
+        mb.status1 = msd_cfg() == 0 ? reinterpret_cast<unsigned int *>(status)
+                                    : w.take<unsigned int>((size_t)cdiv(n, MSD_TILE_MIN) * RX_RADIX);
+        mb.status2 = w.take<unsigned int>((size_t)(cdiv(n, MSD_TILE_MIN) + 256) * RX_RADIX);
         mb.redo = w.take<unsigned int>(MSD_BINS);
     }
 #endif
@@ -262,8 +272,16 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
     const unsigned int *gate = nullptr;
 #if B200_KEY_BYTES == 4
     if (hybrid) {
-        const int32_t rc = xform_is_identity(c.xf) ? msd_launch<true>(c, mb, reinterpret_cast<uint32_t *>(kbuf0), st)
-                                                    : msd_launch<false>(c, mb, reinterpret_cast<uint32_t *>(kbuf0), st);
+        uint32_t *alt = reinterpret_cast<uint32_t *>(kbuf0);
+        int32_t rc;
+#ifdef B200_TUNING
+        if (msd_cfg() == 1) rc = xform_is_identity(c.xf) ? msd_launch<true, 256, 20>(c, mb, alt, st) : msd_launch<false, 256, 20>(c, mb, alt, st);
+        else if (msd_cfg() == 2) rc = xform_is_identity(c.xf) ? msd_launch<true, 256, 16>(c, mb, alt, st) : msd_launch<false, 256, 16>(c, mb, alt, st);
+        else if (msd_cfg() == 3) rc = xform_is_identity(c.xf) ? msd_launch<true, 1024, 10>(c, mb, alt, st) : msd_launch<false, 1024, 10>(c, mb, alt, st);
+        else if (msd_cfg() == 4) rc = xform_is_identity(c.xf) ? msd_launch<true, 512, 16>(c, mb, alt, st) : msd_launch<false, 512, 16>(c, mb, alt, st);
+        else
+#endif
+        rc = xform_is_identity(c.xf) ? msd_launch<true>(c, mb, alt, st) : msd_launch<false>(c, mb, alt, st);
         if (rc != B200_OK) return rc;
         gate = &ctl->mode;      // the LSD kernels below return at once when the hybrid path took the call
     }

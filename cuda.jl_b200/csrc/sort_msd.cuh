@@ -675,41 +675,84 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
                 const uint32_t hi16 = ld_coh(base) & 0xFFFF0000u;        // any key of the segment (read before any write: barrier above)
                 unsigned int *wbw = s_bins + warp * WORDS_PER_WARP;
                 __syncthreads();                                          // every warp has read base[0]
-                for (int j = lane; j < WORDS_PER_WARP; j += 32) {
-                    const unsigned int w = wbw[j];
-                    wbw[j] = 0;                                           // table is clean again for the next segment
-                    const unsigned int cnt = BITS == 8 ? __dp4a(w, 0x01010101u, 0u) : (w & 0xFFFFu) + (w >> 16);
-                    unsigned int incl = cnt;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += up;
-                    }
-                    const unsigned int tot = __shfl_sync(0xffffffffu, incl, 31);
-                    if (w) {
-                        // a lane writes its word's values at consecutive positions, lanes back to back: counts are
-                        // nearly always 0 or 1, so this is one predicated store per field plus a rare copy loop
-                        unsigned int pos = run + incl - cnt;
-                        const uint32_t v0 = hi16 | (uint32_t)((warp * WORDS_PER_WARP + j) * PER_WORD);
-#pragma unroll
-                        for (int f = 0; f < PER_WORD; ++f) {
-                            const unsigned int c = (w >> (f * BITS)) & FIELD;
-                            if (c) {
-                                const uint32_t outv = IDENT ? (v0 + f) : key_decode<uint32_t>(v0 + f, p.xf);
-                                if (BITS == 16 && c >= MSD_LEAF_HEAVY) {
-                                    // thousands of copies of one value: written by the whole CTA after the walk
-                                    const unsigned int e = atomicAdd(&s_nheavy, 1u);
-                                    s_heavy[e] = make_uint4(outv, pos, c, 0u);
-                                } else {
-                                    base[pos] = outv;
+                // A lane writes its word's values at consecutive positions, lanes back to back.  Counts are nearly always
+                // 0 or 1: the first copy of each field is one predicated store at a precomputed offset; further copies
+                // (10 % of the words) share ONE short loop over the copy number instead of a loop per field.
+                auto emit = [&](unsigned int w, unsigned int pos, uint32_t v0) {
+                    uint32_t *out = base + pos;
+                    if constexpr (BITS == 8) {
+                        const unsigned int c0 = w & 0xFFu, c1 = (w >> 8) & 0xFFu, c2 = (w >> 16) & 0xFFu, c3 = w >> 24;
+                        const unsigned int o1 = c0, o2 = o1 + c1, o3 = o2 + c2;
+                        const uint32_t k0 = IDENT ? v0 : key_decode<uint32_t>(v0, p.xf);
+                        const uint32_t k1 = IDENT ? v0 + 1 : key_decode<uint32_t>(v0 + 1, p.xf);
+                        const uint32_t k2 = IDENT ? v0 + 2 : key_decode<uint32_t>(v0 + 2, p.xf);
+                        const uint32_t k3 = IDENT ? v0 + 3 : key_decode<uint32_t>(v0 + 3, p.xf);
+                        if (c0) out[0] = k0;
+                        if (c1) out[o1] = k1;
+                        if (c2) out[o2] = k2;
+                        if (c3) out[o3] = k3;
+                        if (w & 0xFEFEFEFEu) {
+                            const unsigned int mx = max(max(c0, c1), max(c2, c3));
 #pragma unroll 1
-                                    for (unsigned int kk = 1; kk < c; ++kk) base[pos + kk] = outv;
-                                }
-                                pos += c;
+                            for (unsigned int kk = 1; kk < mx; ++kk) {
+                                if (c0 > kk) out[kk] = k0;
+                                if (c1 > kk) out[o1 + kk] = k1;
+                                if (c2 > kk) out[o2 + kk] = k2;
+                                if (c3 > kk) out[o3 + kk] = k3;
                             }
                         }
+                    } else {
+                        const unsigned int c0 = w & 0xFFFFu, c1 = w >> 16;
+                        const uint32_t k0 = IDENT ? v0 : key_decode<uint32_t>(v0, p.xf);
+                        const uint32_t k1 = IDENT ? v0 + 1 : key_decode<uint32_t>(v0 + 1, p.xf);
+                        // thousands of copies of one value: written by the whole CTA after the walk
+                        if (c0 >= MSD_LEAF_HEAVY) s_heavy[atomicAdd(&s_nheavy, 1u)] = make_uint4(k0, pos, c0, 0u);
+                        else {
+#pragma unroll 1
+                            for (unsigned int kk = 0; kk < c0; ++kk) out[kk] = k0;
+                        }
+                        if (c1 >= MSD_LEAF_HEAVY) s_heavy[atomicAdd(&s_nheavy, 1u)] = make_uint4(k1, pos + c0, c1, 0u);
+                        else {
+#pragma unroll 1
+                            for (unsigned int kk = 0; kk < c1; ++kk) out[c0 + kk] = k1;
+                        }
                     }
-                    run += tot;
+                };
+                if constexpr (BITS == 8) {
+                    // two table rows (2 x 32 words) per step: their word counts share ONE warp scan (16-bit halves;
+                    // a row holds at most 32 * 4 * 128 keys)
+                    for (int j = lane; j < WORDS_PER_WARP; j += 64) {
+                        const unsigned int wA = wbw[j], wB = wbw[j + 32];
+                        wbw[j] = 0; wbw[j + 32] = 0;                      // table is clean again for the next segment
+                        const unsigned int cA = __dp4a(wA, 0x01010101u, 0u), cB = __dp4a(wB, 0x01010101u, 0u);
+                        unsigned int incl = cA | (cB << 16);
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o) incl += up;
+                        }
+                        const unsigned int tot = __shfl_sync(0xffffffffu, incl, 31);
+                        const unsigned int totA = tot & 0xFFFFu, totB = tot >> 16;
+                        const uint32_t v0 = hi16 | (uint32_t)((warp * WORDS_PER_WARP + j) * PER_WORD);
+                        if (wA) emit(wA, run + (incl & 0xFFFFu) - cA, v0);
+                        if (wB) emit(wB, run + totA + (incl >> 16) - cB, v0 + 32 * PER_WORD);
+                        run += totA + totB;
+                    }
+                } else {
+                    for (int j = lane; j < WORDS_PER_WARP; j += 32) {
+                        const unsigned int w = wbw[j];
+                        wbw[j] = 0;
+                        const unsigned int cnt = (w & 0xFFFFu) + (w >> 16);
+                        unsigned int incl = cnt;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o) incl += up;
+                        }
+                        const unsigned int tot = __shfl_sync(0xffffffffu, incl, 31);
+                        if (w) emit(w, run + incl - cnt, hi16 | (uint32_t)((warp * WORDS_PER_WARP + j) * PER_WORD));
+                        run += tot;
+                    }
                 }
                 if constexpr (BITS == 16) {
                     __syncthreads();

@@ -200,14 +200,19 @@ typedef struct b200_mgpu_plan {
     uint64_t total;               /* N */
 } b200_mgpu_plan_t;
 int32_t b200_mgpu_plan_bytes(size_t *bytes);
-int32_t b200_mgpu_hist16(const void *keys, int32_t dtype_key, int64_t n, int32_t descending, void *hist16_dev,
-                         b200_stream_t stream);
+int32_t b200_mgpu_hist16(const void *keys, int32_t dtype_key, int64_t n, int32_t descending, int32_t nan_canonical,
+                         void *hist16_dev, b200_stream_t stream);   /* nan_canonical: 0 for sort!, 1 for sortperm / pairs */
 int32_t b200_mgpu_plan(const void *hist_all_dev, int32_t nranks, int32_t rank, void *plan_dev, void *hist_recv_dev,
                        b200_stream_t stream);
 int32_t b200_mgpu_scatter_workspace_bytes(int64_t n, size_t *bytes);
 int32_t b200_mgpu_scatter(void *workspace, size_t workspace_bytes, const void *keys, int32_t dtype_key, int64_t n,
                           int32_t descending, void *plan_dev, void *const *dst_keys, int32_t nranks,
                           b200_stream_t stream);
+/* sortperm's exchange: STABLE partition of (keys, 8-byte payload) by the plan's splitters, bucket b stored straight into
+ * dst_keys[b] / dst_payload[b] at plan.dst_base[b].  Workspace: b200_partition_workspace_bytes(n, nranks) + 256. */
+int32_t b200_mgpu_partition_pairs(void *workspace, size_t workspace_bytes, const void *keys, const void *payload,
+                                  int32_t dtype_key, int64_t n, int32_t descending, const void *plan_dev,
+                                  void *const *dst_keys, void *const *dst_payload, int32_t nranks, b200_stream_t stream);
 /* sort! of `n` keys read from `src` into `dst` (src is only read; src == dst sorts in place; workspace as for
  * b200_sort_workspace_bytes(dtype_key, -1, n, 1)).  hist16_dev, if not NULL, is the exact histogram of the top 16 bits
  * of the order-mapped keys of `src` (b200_mgpu_plan's hist_recv_dev): the sort then skips its own histogram pass. */
