@@ -244,7 +244,8 @@ int32_t b200_sort_pairs(void *workspace, size_t workspace_bytes, void *keys, voi
     using namespace b200;
     if (n < 0) return B200_INVALID_VALUE;
     SortXform xf; int kb;
-    if (!make_xform(dtype_key, descending, 0, xf, kb)) return B200_UNSUPPORTED;
+    // pairs are sortperm's building block: every NaN is ONE key (isless), so NaNs keep their input order
+    if (!make_xform(dtype_key, descending, 1, xf, kb)) return B200_UNSUPPORTED;
     const int pb = dtype_size(dtype_payload);
     if (pb != 4 && pb != 8) return B200_UNSUPPORTED;
     if (n <= 1) return B200_OK;

@@ -20,7 +20,7 @@
 //   scan_pipe_kernel        decoupled look-back in a persistent TMA ring; used when its tile fits the segments
 //                           better (several segments) or with B200_SCAN_CHAIN=0; scan_pipe_ws_kernel (look-back in
 //                           its own warp, B200_SCAN_WS=1) is a measured experiment
-//   scan_contig_kernel      LSU fallback for unaligned inputs; scan_tma_kernel: first TMA cut, kept for reference
+//   scan_contig_kernel      LSU fallback for unaligned inputs
 //   scan_warpseg_kernel     many short contiguous segments, one warp each
 //   scan_strided_lb_kernel / scan_fewcols_kernel / scan_strided_kernel   scans along a non-leading dimension
 //
@@ -417,146 +417,6 @@ template <class T, int N> __device__ __forceinline__ void sts_chunk(T *sm, const
     } else {
 #pragma unroll
         for (int k = 0; k < N; ++k) sm[k] = e[k];
-    }
-}
-
-template <class Tin, class Tout, class Op, int EPC, int K>
-__global__ void __launch_bounds__(SC_THREADS) scan_tma_kernel(ScanParams p) {
-    using A = typename Op::acc_t;
-    constexpr int WARP_ELEMS = 32 * EPC * K;
-    constexpr int TILE = SC_WARPS * WARP_ELEMS;
-    constexpr bool IN_PLACE = sizeof(Tin) == sizeof(Tout);
-    extern __shared__ __align__(128) unsigned char s_dyn[];
-    Tin *s_in = reinterpret_cast<Tin *>(s_dyn);
-    Tout *s_out = IN_PLACE ? reinterpret_cast<Tout *>(s_dyn) : reinterpret_cast<Tout *>(s_dyn + TILE * sizeof(Tin));
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ A s_warp[SC_WARPS];
-    __shared__ A s_tile_prefix;
-    __shared__ unsigned long long s_ticket;
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int64_t g = 0, seg = 0, t = 0, valid = 0;
-    if (threadIdx.x == 0) {
-        mbar_init(&s_bar, 1);
-        fence_proxy_async_smem();
-        g = (int64_t)atomicAdd(p.ticket, 1ull);
-        s_ticket = (unsigned long long)g;
-        seg = g / p.tiles_per_seg;
-        t = g - seg * p.tiles_per_seg;
-        valid = p.n - t * TILE;
-        if (valid >= TILE) {
-            // full tile: one bulk copy, completion counted in bytes on the mbarrier
-            mbar_expect_tx(&s_bar, TILE * sizeof(Tin));
-            tma_load_1d(s_in, static_cast<const Tin *>(p.in) + seg * p.n + t * TILE, TILE * sizeof(Tin), &s_bar);
-        }
-    }
-    __syncthreads();
-    g = (int64_t)s_ticket;
-    seg = g / p.tiles_per_seg;
-    t = g - seg * p.tiles_per_seg;
-    const int64_t tile_off = seg * p.n + t * TILE;
-    valid = p.n - t * TILE;
-    const bool full = valid >= TILE;
-    if (valid > TILE) valid = TILE;
-    const Tin *tin = static_cast<const Tin *>(p.in) + tile_off;
-    Tout *tout = static_cast<Tout *>(p.out) + tile_off;
-    const int64_t wbase = (int64_t)warp * WARP_ELEMS;
-
-    // ---- pass 1: chunk sums (from shared memory for full tiles, from global for the ragged tail)
-    A csum[K];
-    if (full) {
-        mbar_wait(&s_bar, 0);
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            Tin e[EPC];
-            lds_chunk<Tin, EPC>(s_in + wbase + (k * 32 + lane) * EPC, e);
-            A acc = cvt<A>(e[0]);
-#pragma unroll
-            for (int q = 1; q < EPC; ++q) acc = Op::apply(acc, cvt<A>(e[q]));
-            csum[k] = acc;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            A v[EPC];
-            load_chunk<Tin, A, Op, EPC>(tin, wbase + (k * 32 + lane) * EPC, valid, v);
-            Tin e[EPC];
-            A acc = v[0];
-            e[0] = cvt<Tin>(v[0]);
-#pragma unroll
-            for (int q = 1; q < EPC; ++q) { acc = Op::apply(acc, v[q]); e[q] = cvt<Tin>(v[q]); }
-            csum[k] = acc;
-            sts_chunk<Tin, EPC>(s_in + wbase + (k * 32 + lane) * EPC, e);   // own chunk only: no sync needed
-        }
-    }
-    // ---- K interleaved warp scans over the chunk sums
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            A up = shfl_up_any(csum[k], d);
-            if (lane >= d) csum[k] = Op::apply(up, csum[k]);
-        }
-    }
-    A cpre[K];
-    A run = Op::identity();
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        A excl = shfl_up_any(csum[k], 1);
-        A rtot = shfl_idx_any(csum[k], 31);
-        cpre[k] = lane == 0 ? run : Op::apply(run, excl);
-        run = Op::apply(run, rtot);
-    }
-    if (lane == 0) s_warp[warp] = run;
-    __syncthreads();
-
-    if (warp == 0) {
-        A wagg = lane < SC_WARPS ? s_warp[lane] : Op::identity();
-        A wincl = wagg;
-#pragma unroll
-        for (int d = 1; d < SC_WARPS; d <<= 1) {
-            A up = shfl_up_any(wincl, d);
-            if (lane >= d) wincl = Op::apply(up, wincl);
-        }
-        const A tile_agg = shfl_idx_any(wincl, SC_WARPS - 1);
-        A wexcl = shfl_up_any(wincl, 1);
-        if (lane == 0) wexcl = Op::identity();
-        const A prefix = tile_lookback<Op>(p, seg, t, lane, tile_agg);
-        if (lane == 0) s_tile_prefix = prefix;
-        if (lane < SC_WARPS) s_warp[lane] = wexcl;
-    }
-    __syncthreads();
-    const A base = Op::apply(s_tile_prefix, s_warp[warp]);
-
-    // ---- pass 2: re-read the chunk, apply the prefix, write the result back to shared memory
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        Tin e[EPC];
-        lds_chunk<Tin, EPC>(s_in + wbase + (k * 32 + lane) * EPC, e);
-        A run2 = Op::apply(base, cpre[k]);
-        Tout o[EPC];
-#pragma unroll
-        for (int q = 0; q < EPC; ++q) {
-            const A nxt = Op::apply(run2, cvt<A>(e[q]));
-            o[q] = cvt<Tout>(p.exclusive ? run2 : nxt);
-            run2 = nxt;
-        }
-        if (full) {
-            sts_chunk<Tout, EPC>(s_out + wbase + (k * 32 + lane) * EPC, o);
-        } else {
-            const int64_t off = wbase + (k * 32 + lane) * EPC;
-#pragma unroll
-            for (int q = 0; q < EPC; ++q)
-                if (off + q < valid) tout[off + q] = o[q];
-        }
-    }
-    if (full) {
-        fence_proxy_async_smem();      // make this thread's shared-memory writes visible to the TMA unit
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            tma_store_1d(tout, s_out, TILE * sizeof(Tout));
-            tma_store_wait_read();      // shared memory must outlive the bulk read
-        }
     }
 }
 
@@ -1142,6 +1002,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
 
+#ifdef B200_TUNING   // measured-slower experiment (look-back in its own warp): A/B builds only
 template <class Tin, class Tout, class Op, int EPC, int K, int S, int NT, int LOOK>
 __global__ void __launch_bounds__(NT + 32) scan_pipe_ws_kernel(ScanParams p) {
     using A = typename Op::acc_t;
@@ -1353,6 +1214,8 @@ __global__ void __launch_bounds__(NT + 32) scan_pipe_ws_kernel(ScanParams p) {
         for (int k = 0; k < K; ++k) cpre_cur[k] = cpre_nxt[k];
     }
 }
+
+#endif  // B200_TUNING
 
 // One thread per (i, j) column, marching along n.
 template <class Tin, class Tout, class Op>
@@ -1712,10 +1575,15 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
 #endif
         // B200_SCAN_CHAIN=0 / 2 forces the look-back kernel / chain2 for every shape; B200_SCAN_WS=1 (with the look-back
         // kernel) gives the look-back its own warp (measured slower).
-        static const char *chain_env = getenv("B200_SCAN_CHAIN");
-        static const bool use_ws = getenv("B200_SCAN_WS") != nullptr;
+        // (A/B knobs exist in -DB200_TUNING builds only; the product library reads no environment variable)
+        static const int chain_knob = tune_int("B200_SCAN_CHAIN", -1);
+#ifdef B200_TUNING
+        static const bool use_ws = tune_int("B200_SCAN_WS", 0) != 0;
+#else
+        constexpr bool use_ws = false;        // scan_pipe_ws_kernel (look-back in its own warp, measured slower) is not built
+#endif
         // scan_chain2_kernel: status prefetch issued 0 = before barrier (A), 1 = after the publication
-        static const int chain_at = getenv("B200_SCAN_CHAIN_AT") ? atoi(getenv("B200_SCAN_CHAIN_AT")) : 1;
+        static const int chain_at = tune_int("B200_SCAN_CHAIN_AT", 1);
         p.chain_at = chain_at < 0 ? 0 : chain_at;
         int dev = 0;
         B200_CUDA_TRY(cudaGetDevice(&dev));
@@ -1728,7 +1596,7 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
         constexpr int64_t kTileLook = (int64_t)kLookThreads * S::EPC * kLookK;
         const int64_t pad2 = cdiv(n, kTileChain2) * kTileChain2 - n, pad1 = cdiv(n, kTileLook) * kTileLook - n;
         const bool chain2_fits = post == 1 || pad2 <= pad1 || pad2 * 8 <= n;      // at most 12.5 % of a segment in a ragged tile
-        static const int chain_force = chain_env ? (chain_env[0] == '2' ? 2 : 0) : -1;
+        static const int chain_force = chain_knob < 0 ? -1 : (chain_knob == 2 ? 2 : 0);
         const bool use_chain2 = !use_ws && (chain_force >= 0 ? chain_force == 2 : chain2_fits);
         int64_t pgrid = 0, ptiles = 0;
 #ifdef B200_SCAN_STATS
@@ -1757,8 +1625,12 @@ int32_t launch_scan(void *ws, size_t ws_bytes, const void *in, void *out, int64_
             constexpr int kLook = kWide ? 4 : B200_SCAN_LOOK_NARROW;
             constexpr size_t smem = (size_t)kTileLook * sizeof(Tin) * kStages;
             constexpr int kFit = (200 * 1024) / (int)smem > 0 ? (200 * 1024) / (int)smem : 1;   // CTAs per SM by shared memory
+#ifdef B200_TUNING
             auto kern = use_ws ? scan_pipe_ws_kernel<Tin, Tout, Op, S::EPC, kLookK, kStages, (kLookThreads > 992 ? 992 : kLookThreads), kLook>
                                : scan_pipe_kernel<Tin, Tout, Op, S::EPC, kLookK, kStages, kLookThreads, kLook>;
+#else
+            auto kern = scan_pipe_kernel<Tin, Tout, Op, S::EPC, kLookK, kStages, kLookThreads, kLook>;
+#endif
             static thread_local int attr_dev_mask[64][2];  // cudaFuncSetAttribute once per (thread, device, variant)
             if (dev >= 0 && dev < 64 && !attr_dev_mask[dev][use_ws ? 1 : 0]) {
                 B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

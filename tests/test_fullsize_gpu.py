@@ -79,9 +79,12 @@ def test_cumsum_full_size(b, dtype):
         for i in idx[:64].tolist():                                   # spot prefixes against a Float64 prefix sum
             refp = float(V[:i + 1].double().sum().item())
             assert abs(float(O[i].item()) - refp) <= tol * refp + 1e-6
-        # non-negative input: monotone up to the rounding of differently associated prefixes (a few ulps)
+        # non-negative input: monotone up to the rounding of differently associated prefixes.  Neighbouring outputs on
+        # the two sides of a tile boundary come from different summation trees (tile prefix + local scan), each within
+        # a few ulps of the true prefix — far inside the 4*log2(n)*eps bound asserted above; 8 ulps of slack here
+        # (4 was observed to fail by 0.01 % once in three runs: the chained prefixes' association is timing dependent).
         d = O[1:1 << 26].double() - O[:(1 << 26) - 1].double()
-        assert float(d.min().item()) >= -4 * 2.0 ** -23 * float(O[(1 << 26) - 1].item())
+        assert float(d.min().item()) >= -8 * 2.0 ** -23 * float(O[(1 << 26) - 1].item())
 
 
 @pytest.mark.parametrize("dtype", ["uint32", "float32"])

@@ -25,7 +25,7 @@ def emulate(b, full, G, rev, cuts=None):
     shards = [b.CuArray(full[cuts[r]:cuts[r + 1]]) for r in range(G)]
     hist_all = torch.empty(G * 65536, dtype=torch.int32, device=dev)
     for r, s in enumerate(shards):
-        b._lib.check(lib.b200_mgpu_hist16(s.pointer if s.length else None, et, s.length, int(rev),
+        b._lib.check(lib.b200_mgpu_hist16(s.pointer if s.length else None, et, s.length, int(rev), 0,
                                           hist_all[r * 65536:].data_ptr(), stream))
     nb = ctypes.c_size_t(0)
     b._lib.check(lib.b200_mgpu_plan_bytes(ctypes.byref(nb)))
@@ -118,3 +118,62 @@ def test_dense_slice_takes_the_hybrid_path(b):
     assert bool((got[1:] >= got[:-1]).all()) and got.size == full.size
     np.testing.assert_array_equal(np.bincount(got >> np.uint32(24), minlength=256), np.bincount(full >> np.uint32(24), minlength=256))
     assert int(got.astype(np.uint64).sum()) == int(full.astype(np.uint64).sum())
+
+
+def emulate_sortperm(b, full, G, rev):
+    """sortperm's exchange on one GPU: nan-canonical histogram, plan, stable pairs partition into G local buffers,
+    stable local pairs sort; returns the concatenated global 1-based permutation."""
+    lib = b._lib.load()
+    dt = b.dtypes
+    et = dt.from_np(full.dtype)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    stream = torch.cuda.current_stream().cuda_stream
+    cuts = np.linspace(0, full.size, G + 1).astype(int)
+    shards = [b.CuArray(full[cuts[r]:cuts[r + 1]]) for r in range(G)]
+    hist_all = torch.empty(G * 65536, dtype=torch.int32, device=dev)
+    for r, s in enumerate(shards):
+        b._lib.check(lib.b200_mgpu_hist16(s.pointer, et, s.length, int(rev), 1, hist_all[r * 65536:].data_ptr(), stream))
+    nb = ctypes.c_size_t(0)
+    b._lib.check(lib.b200_mgpu_plan_bytes(ctypes.byref(nb)))
+    plans, totals = [], []
+    for r in range(G):
+        plan = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+        hr = torch.empty(65536, dtype=torch.int32, device=dev)
+        b._lib.check(lib.b200_mgpu_plan(hist_all.data_ptr(), G, r, plan.data_ptr(), hr.data_ptr(), stream))
+        u64 = plan.cpu().numpy()[80:488].view(np.uint64)
+        plans.append(plan); totals.append((int(u64[48]), int(u64[49])))
+    cap = max(totals[0][1], 1)
+    rk = [torch.zeros(cap, dtype=torch.int32, device=dev) for _ in range(G)]
+    rp = [torch.zeros(cap, dtype=torch.int64, device=dev) for _ in range(G)]
+    kp = (ctypes.c_void_p * G)(*[t.data_ptr() for t in rk])
+    pp = (ctypes.c_void_p * G)(*[t.data_ptr() for t in rp])
+    for r, s in enumerate(shards):
+        idx = torch.arange(cuts[r] + 1, cuts[r + 1] + 1, dtype=torch.int64, device=dev)
+        w = ctypes.c_size_t(0)
+        b._lib.check(lib.b200_partition_workspace_bytes(s.length, G, ctypes.byref(w)))
+        ws = torch.empty(w.value + 256, dtype=torch.uint8, device=dev)
+        ws.fill_(0xA5)
+        b._lib.check(lib.b200_mgpu_partition_pairs(ws.data_ptr(), w.value + 256, s.pointer, idx.data_ptr(), et, s.length, int(rev),
+                                                   plans[r].data_ptr(), kp, pp, G, stream))
+    out = []
+    ops = b.multigpu.DeviceOps()
+    for r in range(G):
+        n = totals[r][0]
+        keys = b.CuArray(rk[r][:n].view(torch.uint8), (n,), et)
+        pay = b.CuArray(rp[r][:n].view(torch.uint8), (n,), dt.I64)
+        ops.sort_pairs(keys, pay, rev)
+        out.append(b.Array(pay))
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("G", [2, 5])
+@pytest.mark.parametrize("rev", [False, True])
+def test_emulated_sortperm_is_stable_across_ranks(b, G, rev):
+    rng = np.random.default_rng(31 + G)
+    full = rng.standard_normal(1_500_007).astype(np.float32)
+    full[::97] = 0.25                                   # heavy ties: stability across tiles, ranks and the local sort
+    full[[11, 500_000, 1_400_000]] = np.nan             # several NaNs with the same key: they keep ascending index
+    full[[12, 13]] = [-0.0, 0.0]
+    np.testing.assert_array_equal(emulate_sortperm(b, full, G, rev), oracle.sortperm(full, rev=rev))
+    u = rng.integers(0, 40, size=700_001, dtype=np.uint32) * np.uint32(100_000_000)
+    np.testing.assert_array_equal(emulate_sortperm(b, u, G, rev), oracle.sortperm(u, rev=rev))
