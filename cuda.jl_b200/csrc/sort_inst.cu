@@ -96,21 +96,33 @@ template <class LookT> static int32_t dispatch_pass(const OnesweepParams &p, int
 #define B200_CAT(a, b) B200_CAT2(a, b)
 
 #if B200_KEY_BYTES == 4
+// zero-fill that only runs when the hybrid path declined the call (count is in 16-byte units; 256-byte aligned buffers)
+static __global__ void gated_zero_kernel(uint4 *p, size_t count, const unsigned int *gate) {
+    if (ld_gate(gate) != 0) return;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = make_uint4(0, 0, 0, 0);
+}
+
 // ---- hybrid MSD path (sort_msd.cuh): dense 32-bit keys-only sorts -------------------------------------------
-constexpr int MSD_TILE_MIN = 4096;            // smallest P1 / P2 tile of any configuration (sizes the look-back arrays)
+#ifdef B200_TUNING
+constexpr int MSD_TILE_MIN = 4096;            // smallest P1 / P2 tile of any tuning configuration (sizes the look-back arrays)
+#else
+constexpr int MSD_TILE_MIN = 512 * 20;        // the P1 / P2 tile
+#endif
 constexpr int LEAF_NT = 512;
 constexpr unsigned int LEAF8_CAP = 32768;    // segments up to this many keys go to the 8-bit-bin leaf first
 constexpr unsigned int LEAF_MAX_SEG = 65535; // 16-bit bins cannot overflow up to here; longer segments: LSD fallback
 constexpr unsigned int MSD_MIN_AVG = 3072;   // counting leaf: 65536 bins are walked per segment whatever its length
-constexpr int64_t MSD_MIN_N = 1LL << 27;     // below this even a full key range cannot reach MSD_MIN_AVG ... per
-                                             // non-empty segment unless the keys sit in a narrow range; not worth the histogram
 constexpr int64_t MSD_MAX_N = 1LL << 30;     // 32-bit look-back words carry 30-bit counts
 
-// P1 / P2 tile shape: 0 = 512 threads x 20 keys (default); others only in -DB200_TUNING builds (A/B measurements)
+#ifdef B200_TUNING
+// P1 / P2 tile shape: 0 = 512 threads x 20 keys (default, the only one in the product build); measured on B200, 2^30
+// uniform UInt32: 512x20 12.2 ms, 512x16 13.2 ms, 1024x10 14.3 ms, 256x20 19.1 ms, 256x16 25.4 ms
 static int msd_cfg() {
     static const int cfg = tune_int("B200_MSD_CFG", 0);
     return cfg;
 }
+#endif
 
 static bool xform_is_identity(const SortXform &x) { return x.base_enc == 0 && x.fmn == 0 && x.mag_mask == 0 && x.desc == 0; }
 
@@ -202,15 +214,24 @@ static int32_t msd_launch(const SortCall &c, const MsdBuffers &b, uint32_t *alt,
     return B200_OK;
 }
 
-static bool msd_eligible(const SortCall &c) {
+// The workspace LAYOUT carries the hybrid path's buffers for every keys-only call it could ever be asked to run
+// (so that the size query does not depend on whether the caller will pass a histogram); whether the path is attempted
+// is decided per call.
+static bool msd_layout(const SortCall &c) {
     static const int on = tune_int("B200_SORT_HYBRID", 1);
+    static const int min_log2 = tune_int("B200_MSD_MIN_LOG2N", 27);
+    const int64_t lay_min = min_log2 < 24 ? (1LL << min_log2) : (1LL << 24);
+    return on && c.mode == SORT_KEYS && c.n >= lay_min && c.n <= MSD_MAX_N;
+}
+static bool msd_eligible(const SortCall &c) {
     static const int min_log2 = tune_int("B200_MSD_MIN_LOG2N", 27);
     // with a caller-supplied histogram (multi-GPU slice: dense inside a narrow key range) the plan kernel's density
     // test decides alone, and the attempt costs no extra pass
     const int64_t min_n = c.hist16_in ? (1LL << 24) : (1LL << min_log2);
-    return on && c.mode == SORT_KEYS && c.n >= min_n && c.n <= MSD_MAX_N;
+    return msd_layout(c) && c.n >= min_n;
 }
 #else
+static bool msd_layout(const SortCall &) { return false; }
 static bool msd_eligible(const SortCall &) { return false; }
 #endif
 
@@ -226,30 +247,40 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
     int pay = 0;
     if (c.mode == SORT_PERM) pay = n > 0xFFFFFFFFLL ? 8 : 4;
     else if (c.mode == SORT_PAIRS) pay = c.payload_bytes;
+    const bool hybrid_layout = msd_layout(c);
     const bool hybrid = msd_eligible(c);
 
-    // workspace: [ctl | ghist | status | (hybrid: hist16 | status2)] is zeroed by ONE memset per call
+    // workspace: [ctl | ghist | (hybrid: hist16 | redo | status2) | status] — everything up to the part of `status`
+    // that the first kernels need is zeroed by ONE memset per call; when the hybrid path is attempted, the rest of
+    // `status` (only the LSD fallback reads it) is zeroed by a kernel gated on the fallback
     Carver w(c.ws);
     char *ctl_raw = w.take<char>(256);
     unsigned long long *ghist = w.take<unsigned long long>(P * RX_RADIX);
-    char *status = w.take<char>((size_t)tiles * RX_RADIX * look_bytes);
 #if B200_KEY_BYTES == 4
     MsdBuffers mb{};
     mb.ctl = reinterpret_cast<MsdCtl *>(ctl_raw);
     static_assert(sizeof(MsdCtl) <= 256, "control block");
-    if (hybrid) {
+    if (hybrid_layout) {
         mb.hist16 = w.take<unsigned int>(MSD_BINS);
-        // P1 of the default configuration has fewer tiles than an LSD pass and shares its look-back array (only one of
-        // the two paths runs); the tuning configurations with smaller tiles get their own
-        mb.status1 = msd_cfg() == 0 ? reinterpret_cast<unsigned int *>(status)
-                                    : w.take<unsigned int>((size_t)cdiv(n, MSD_TILE_MIN) * RX_RADIX);
-        mb.status2 = w.take<unsigned int>((size_t)(cdiv(n, MSD_TILE_MIN) + 256) * RX_RADIX);
         mb.redo = w.take<unsigned int>(MSD_BINS);
+        mb.status2 = w.take<unsigned int>((size_t)(cdiv(n, MSD_TILE_MIN) + 256) * RX_RADIX);
     }
 #endif
-    const size_t clear_bytes = w.bytes();
+    // P1 of the hybrid path shares the head of the LSD look-back array (only one of the two paths runs)
+    size_t status_bytes = (size_t)tiles * RX_RADIX * look_bytes;
+    size_t status_head = status_bytes;
 #if B200_KEY_BYTES == 4
-    if (hybrid) {
+    if (hybrid_layout) {
+        status_head = (size_t)cdiv(n, MSD_TILE_MIN) * RX_RADIX * sizeof(unsigned int);
+        if (status_bytes < status_head) status_bytes = status_head;
+    }
+#endif
+    const size_t status_off = w.bytes();
+    char *status = w.take<char>(status_bytes);
+    const size_t clear_bytes = hybrid ? status_off + status_head : w.bytes();
+#if B200_KEY_BYTES == 4
+    if (hybrid_layout) {
+        mb.status1 = reinterpret_cast<unsigned int *>(status);
         mb.seg_start = w.take<unsigned int>(MSD_BINS + 1);
         mb.seg_list = w.take<unsigned int>(MSD_BINS);
         mb.l1_tile_start = w.take<unsigned int>(257);
@@ -279,11 +310,17 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
         else if (msd_cfg() == 2) rc = xform_is_identity(c.xf) ? msd_launch<true, 256, 16>(c, mb, alt, st) : msd_launch<false, 256, 16>(c, mb, alt, st);
         else if (msd_cfg() == 3) rc = xform_is_identity(c.xf) ? msd_launch<true, 1024, 10>(c, mb, alt, st) : msd_launch<false, 1024, 10>(c, mb, alt, st);
         else if (msd_cfg() == 4) rc = xform_is_identity(c.xf) ? msd_launch<true, 512, 16>(c, mb, alt, st) : msd_launch<false, 512, 16>(c, mb, alt, st);
+        else if (msd_cfg() == 5) rc = xform_is_identity(c.xf) ? msd_launch<true, 512, 12>(c, mb, alt, st) : msd_launch<false, 512, 12>(c, mb, alt, st);
         else
 #endif
         rc = xform_is_identity(c.xf) ? msd_launch<true>(c, mb, alt, st) : msd_launch<false>(c, mb, alt, st);
         if (rc != B200_OK) return rc;
         gate = &ctl->mode;      // the LSD kernels below return at once when the hybrid path took the call
+        if (status_bytes > status_head) {
+            gated_zero_kernel<<<devinfo().sm_count * 4, 512, 0, st>>>(reinterpret_cast<uint4 *>(status + status_head),
+                                                                        (status_bytes - status_head) / 16, gate);
+            B200_CHECK_LAUNCH();
+        }
     }
 #endif
 

@@ -291,7 +291,7 @@ struct MsdTile {
 };
 
 template <int LEVEL, int NT, int ITEMS, bool IDENT>
-__global__ void __launch_bounds__(NT, 1024 / NT) msd_scatter_kernel(MsdScatterParams p) {
+__global__ void __launch_bounds__(NT, (NT == 512 && ITEMS <= 16) ? 3 : 1024 / NT) msd_scatter_kernel(MsdScatterParams p) {
     using LB = LookBits<uint32_t>;
     constexpr int TILE = NT * ITEMS;
     constexpr int SHIFT = LEVEL == 1 ? 24 : 16;
@@ -447,6 +447,17 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msd_scatter_kernel(MsdScatterPa
         locate(tn, (it + 1) & 1);
         __syncthreads();                                                                     // (C)
 
+        // ---- the first look-back round trip is requested before the scatter and consumed after it: the predecessors
+        // published their counts before their own scatter, so these words are (at least) PARTIAL when they arrive
+        uint32_t wpre[RX_LOOK];
+#pragma unroll
+        for (int k = 0; k < RX_LOOK; ++k) wpre[k] = LB::INCLUSIVE;
+        if (dthread && !chain_head) {
+#pragma unroll
+            for (int k = 0; k < RX_LOOK; ++k)
+                if ((int)cur.t - 1 - k >= (int)cur.first) wpre[k] = ld_relaxed<uint32_t>(p.status + (size_t)(cur.t - 1 - k) * 256 + tid);
+        }
+
         // ---- scatter into shared memory, grouped by digit
         if (full) {
 #pragma unroll
@@ -472,10 +483,18 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msd_scatter_kernel(MsdScatterPa
                 int u = (int)cur.t - 1;
                 const int floor_t = (int)cur.first;
                 bool done = false;
+                bool pre = true;                           // first round: the words requested before the scatter
                 while (!done) {
                     uint32_t w[RX_LOOK];
-                    bool all_valid;
-                    do {
+                    bool all_valid = true;
+                    if (pre) {
+#pragma unroll
+                        for (int k = 0; k < RX_LOOK; ++k) { w[k] = wpre[k]; all_valid = all_valid && ((w[k] & LB::FLAGS) != 0); }
+                        pre = false;
+                    } else {
+                        all_valid = false;
+                    }
+                    while (!all_valid) {
                         all_valid = true;
 #pragma unroll
                         for (int k = 0; k < RX_LOOK; ++k) {
@@ -483,7 +502,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msd_scatter_kernel(MsdScatterPa
                             if (u - k >= floor_t) w[k] = ld_relaxed<uint32_t>(p.status + (size_t)(u - k) * 256 + tid);
                             all_valid = all_valid && ((w[k] & LB::FLAGS) != 0);
                         }
-                    } while (!all_valid);
+                    }
 #pragma unroll
                     for (int k = 0; k < RX_LOOK; ++k) {
                         if (!done) {
@@ -557,7 +576,6 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
     constexpr int NW = NT / 32;
     constexpr int WORDS_PER_WARP = WORDS / NW;        // contiguous slice of the table walked by one warp
     constexpr int CH = MSD_LEAF_CHUNK;
-    constexpr unsigned int FIELD = (1u << BITS) - 1u;
     extern __shared__ __align__(16) unsigned int s_bins[];   // [WORDS] packed counters, all zero between segments
     __shared__ unsigned int s_wtot[NW];
     __shared__ int s_over;
