@@ -21,13 +21,23 @@ def _factor(dims_tuple, dims):
     return pre, n, post
 
 
-def scan_(f, output, input, dims, init=None, exclusive=False, carry=None, carry_count=0):
+def scan_(f, output, input, dims, init=None, exclusive=False, carry=None, carry_count=0, neutral=None):
     """CUDACore.scan!(f, output, input; dims, init) (accumulate.jl:135).  `init` is the x of
     Some(x).  `exclusive=True` is the extra variant BASELINE config 3 names.  `carry` (a device CuArray of the
     accumulator type) with `carry_count` is the sharded scan's device-side carry (b200_scan_carry): its first
     carry_count values are folded into the seed on the device, no host round trip."""
     if f not in _SCAN_OPS:
         raise NotGraftedError(f"scan!({f}, ...) stays on the reference's generic kernels")
+    # scan!'s `neutral` keyword defaults to GPUArrays.neutral_element(f, T) (accumulate.jl:136) and the reference kernel
+    # loads every element as op(neutral, x) (accumulate.jl:39-43): for integer `&` that default is one(T), so the
+    # reference's own result is x & 1-contaminated.  The graft computes the plain scan, hence it only answers when the
+    # caller's neutral IS neutral (lib/B200Arrays/src/accumulate.jl has the same guard); Bool `&` is unaffected.
+    from .mapreduce import and_, true_neutral
+    if f is and_ and output.eltype != dt.BOOL:
+        if neutral is None or np.asarray(neutral).astype(dt.np_dtype(output.eltype)).tobytes() != \
+                np.asarray(true_neutral(and_, output.eltype), dtype=dt.np_dtype(output.eltype)).tobytes():
+            raise NotGraftedError("accumulate(&, ::CuArray{<:Integer}) with GPUArrays' neutral element one(T) stays on the "
+                                  "reference path")
     if not (isinstance(dims, (int, np.integer)) and dims > 0):
         raise ArgumentError("dims must be a positive integer")            # accumulate.jl:137
     if output.dims != input.dims:

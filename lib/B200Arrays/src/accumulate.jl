@@ -8,6 +8,10 @@ function CUDACore.scan!(f::OP, output::CuArray{To}, input::CuArray{Ti};
     reference() = invoke(CUDACore.scan!, Tuple{Function,CUDACore.AnyCuArray,CUDACore.AnyCuArray},
                          f, output, input; dims, init, neutral)
     enabled() || return reference()
+    # the reference kernel loads every element as op(neutral, x) (accumulate.jl:39-43); GPUArrays' default for integer `&`
+    # is one(T), which is not neutral — that (reference-defined) result is not the plain scan the library computes, so
+    # the graft only answers for a neutral that IS neutral (true_neutral, mapreduce.jl)
+    neutral === true_neutral(f, To) || return reference()
     dims > 0 || throw(ArgumentError("dims must be a positive integer"))          # accumulate.jl:137
     axes(output) == axes(input) || throw(DimensionMismatch("shape of B must match A"))
     dims > ndims(input) && return copyto!(output, input)

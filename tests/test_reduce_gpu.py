@@ -33,7 +33,7 @@ def rand(name, shape):
     return RNG.integers(ii.min, ii.max, size=shape, dtype=d, endpoint=True)
 
 
-def check(b, f, op, A, dims, exact=None):
+def check(b, f, op, A, dims, exact=None, init=None):
     """Run mapreduce on device and compare with the oracle."""
     fn = {"add_sum": b.add_sum, "mul_prod": b.mul_prod, "add": b.add, "mul": b.mul, "max": b.max_, "min": b.min_,
           "and": b.and_, "or": b.or_}[op]
@@ -41,7 +41,7 @@ def check(b, f, op, A, dims, exact=None):
     oop = {"add_sum": "add", "mul_prod": "mul"}.get(op, op)
     out_dt = oracle.widen_add(A.dtype) if op in ("add_sum", "mul_prod") else A.dtype
     d = b.CuArray(A)
-    R = b.mapreduce(ff, fn, d, dims=dims)
+    R = b.mapreduce(ff, fn, d, dims=dims, init=init)
     ds = range(1, A.ndim + 1) if dims is None else ((dims,) if isinstance(dims, int) else dims)
     rdims = tuple(1 if (i + 1) in ds else s for i, s in enumerate(A.shape))
     ref = oracle.mapreducedim(f, oop, A, rdims, out_dt)
@@ -79,10 +79,16 @@ def test_ops_1d(b, dtype, op):
 @pytest.mark.parametrize("op", ["and", "or"])
 def test_bitwise(b, dtype, op):
     A = rand(dtype, (70001,))
+    init = None
     if op == "and":
         A = A | np.uint64(0x0F0F0F0F).astype(npdt(dtype))
-    check(b, "identity", op, A, None)
-    check(b, "identity", op, np.asfortranarray(A[:69993].reshape(7, 9999)), 2)
+        # GPUArrays.neutral_element(&, T) is one(T), NOT neutral for integers: `reduce(&, ints)` without an explicit init
+        # must stay on the reference path (SURVEY section 8 a1'); with the true neutral element (all ones) it is grafted
+        with pytest.raises(b.NotGraftedError):
+            b.mapreduce(b.identity, b.and_, b.CuArray(A))
+        init = b.true_neutral(b.and_, b.dtypes.from_np(A.dtype))
+    check(b, "identity", op, A, None, init=init)
+    check(b, "identity", op, np.asfortranarray(A[:69993].reshape(7, 9999)), 2, init=init)
 
 
 @pytest.mark.parametrize("dtype", FLOATS + INTS)
@@ -104,7 +110,8 @@ def test_small_integers(b, dtype):
         check(b, "identity", "add_sum", A[3:] if n > 3 else A, None)          # unaligned head
     A = rand(dtype, (70001,))
     for op in ("max", "min", "add", "mul", "and", "or", "mul_prod"):
-        check(b, "identity", op, A, None)
+        # integer `&` is grafted only with the TRUE neutral element as init (all ones), see test_bitwise
+        check(b, "identity", op, A, None, init=b.true_neutral(b.and_, b.dtypes.from_np(A.dtype)) if op == "and" else None)
     check(b, "abs2", "add_sum", A, None)
     M = np.asfortranarray(A[:69993].reshape(7, 9999))
     for dims in (1, 2):

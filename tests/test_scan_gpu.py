@@ -148,7 +148,15 @@ def test_other_ops(b, op, dtype):
     if op == "mul" and oracle.is_float(npdt(dtype)):
         A = (1 + (A - 0.5) * 1e-3).astype(npdt(dtype))[:5000]
     if op == "and":
+        # integer `&`: GPUArrays' default neutral one(T) is not neutral and the reference kernel applies it to every element
+        # (accumulate.jl:39-43), so accumulate(&, ints) stays on the reference path; scan! with the true neutral is grafted
         A = A | np.uint64(0x00FF00FF).astype(npdt(dtype))
+        d = b.CuArray(A)
+        with pytest.raises(b.NotGraftedError):
+            b.accumulate(b.and_, d)
+        out = b.scan_(b.and_, d.similar(), d, 1, neutral=b.true_neutral(b.and_, d.eltype))
+        np.testing.assert_array_equal(b.Array(out), oracle.accumulate("and", A, 1, None, A.dtype, False))
+        return
     check_scan(b, op, A)
     check_scan(b, op, np.asfortranarray(A[:69993 if A.size > 69993 else 4998].reshape(3, -1)), dims=2)
 
