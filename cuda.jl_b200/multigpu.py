@@ -318,9 +318,9 @@ def dist_extrema(shard, group=None, ops=None):
     pair = ops.extrema_pair(shard)                                   # CuArray{T}(2): (min, max), neutral for an empty shard
     gathered = CuArray.undef(shard.eltype, (2 * G,), shard.buf.device)
     if shard.buf.is_cuda and hasattr(dist, "all_gather_into_tensor"):
-        dist.all_gather_into_tensor(_typed(gathered), _typed(pair), group=group)
+        dist.all_gather_into_tensor(gathered.buf, pair.buf, group=group)       # bytes: NCCL has no 16-bit integer type
     else:
-        _all_gather_fallback(_typed(gathered), _typed(pair), group)
+        _all_gather_fallback(gathered.buf, pair.buf, group)
     g2 = gathered.reshape((2, G))                                    # column-major: column k = rank k's (min, max)
     R = CuArray.undef(shard.eltype, (2, 1), shard.buf.device)
     h = ops.extrema_combine(g2, R)
@@ -340,8 +340,9 @@ def dist_accumulate(op, shard, exclusive=False, group=None, ops=None, out_eltype
     part_et = _acc_eltype(out_et)
     total = ops.reduce(identity, op, shard, part_et)
     gathered = CuArray.undef(part_et, (G,), shard.buf.device)
-    dist.all_gather_into_tensor(_typed(gathered), _typed(total), group=group) if hasattr(dist, "all_gather_into_tensor") \
-        and shard.buf.is_cuda else _all_gather_fallback(_typed(gathered), _typed(total), group)
+    # bytes on the wire: NCCL has no 16-bit integer type, and a gather only moves bits
+    dist.all_gather_into_tensor(gathered.buf, total.buf, group=group) if hasattr(dist, "all_gather_into_tensor") \
+        and shard.buf.is_cuda else _all_gather_fallback(gathered.buf, total.buf, group)
     out = shard.similar(out_et)
     # the carry of rank r = op over the totals of ranks 0 .. r-1: folded into the scan's seed ON THE DEVICE
     # (b200_scan_carry reads gathered[0:r]) — no host read-back, no extra reduce launch, graph-capturable
