@@ -625,6 +625,8 @@ def run_extras_sharded(b, dt, torch, dist, dev, rank, world, peak):
         want = sum(float(p.item()) if tol else int(p.item()) for p in parts[:rank + 1])
         got = float(r[-1].item()) if tol else int(r[-1].item())
         ok = abs(got - want) <= tol * abs(want) if tol else got == want
+        if not ok:
+            print(f"[rank {rank}] cumsum check: got {got!r} want {want!r} parts {[p.item() for p in parts]}", file=sys.stderr, flush=True)
         return all_ok(ok)
 
     def mk_f32():
