@@ -182,24 +182,16 @@ def run_product(args, rank, world, local_rank):
     rc = b.CuArray.undef(dt.I64, (1, 1))
     ninf = -np.inf
 
-    # cross-rank combine of one step: two collectives instead of five.  Every SUM partial (Float32 / BFloat16 row sums,
-    # the Int64 count) travels in ONE Float64 buffer (exact for the count; the row sums are rounded once from a Float64
-    # total), both maxima in one Float32 buffer.  (dist._coalescing_manager is NOT an option: with mixed dtypes / ops its
-    # exit raises and leaves the process group in a state that corrupted every later collective of the run.)
-    if dist is not None:
-        pack_sum = torch.empty(2 * M + 1, device=dev, dtype=torch.float64)
-        pack_max = torch.empty(2, device=dev, dtype=torch.float32)
-
     def exchange():
         if dist is None:
             return
-        # rows are split across ranks (column blocks): dims=2 partial row sums and the scalars need an allreduce
-        pack_sum[:M].copy_(r2_32.typed().view(-1)); pack_sum[M:2 * M].copy_(r2_16.typed().view(-1)); pack_sum[2 * M:].copy_(rc.typed().view(-1))
-        pack_max[:1].copy_(rm_32.typed().view(-1)); pack_max[1:].copy_(rm_16.typed().view(-1))
-        dist.all_reduce(pack_sum)
-        dist.all_reduce(pack_max, op=dist.ReduceOp.MAX)
-        r2_32.typed().view(-1).copy_(pack_sum[:M]); r2_16.typed().view(-1).copy_(pack_sum[M:2 * M]); rc.typed().view(-1).copy_(pack_sum[2 * M:])
-        rm_32.typed().view(-1).copy_(pack_max[:1]); rm_16.typed().view(-1).copy_(pack_max[1:])
+        # rows are split across ranks (column blocks): dims=2 partial row sums and the scalars need an allreduce.
+        # Measured at 2 GPUs: these five small allreduces 0.79 ms per step; packing them into two buffers (Float64 sums,
+        # Float32 maxima) costs ten tiny copy kernels and was SLOWER (0.86 ms); torch's _coalescing_manager raises on
+        # mixed dtypes and left the process group in a state that corrupted later collectives.  So: five plain calls.
+        dist.all_reduce(r2_32.typed()); dist.all_reduce(r2_16.typed())
+        dist.all_reduce(rm_32.typed(), op=dist.ReduceOp.MAX); dist.all_reduce(rm_16.typed(), op=dist.ReduceOp.MAX)
+        dist.all_reduce(rc.typed())
 
     def step():
         # interleave the matrices so no input is still L2-resident when it is read again
@@ -534,21 +526,25 @@ def run_extras_sharded(b, dt, torch, dist, dev, rank, world, peak):
             best = float(t.item()) if best is None else min(best, float(t.item()))
         return best
 
-    def one_gpu(make, fn, reps=2):
-        """rank 0 times fn(x) on x = make() (the whole problem on one GPU); the others wait."""
+    def one_gpu(make, fn, reps=2, restore=False):
+        """rank 0 times fn(x) on x = make() (the whole problem on one GPU); the others wait.  restore: fn works in place
+        (sort!), so x is reset from a pristine copy before every run, outside the timed region."""
         ms = None
         if rank == 0:
             try:
                 x = make()
+                keep = x.copy() if restore else None
                 fn(x)
                 ts = []
                 for _ in range(reps):
+                    if restore:
+                        x.buf.copy_(keep.buf)
                     torch.cuda.synchronize()
                     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     s.record(); fn(x); e.record(); e.synchronize()
                     ts.append(s.elapsed_time(e))
                 ms = min(ts)
-                del x
+                del x, keep
             except Exception as ex:
                 ms = None
                 print(f"1-GPU baseline failed: {ex}", file=sys.stderr)
@@ -642,7 +638,7 @@ def run_extras_sharded(b, dt, torch, dist, dev, rank, world, peak):
         holder["r"] = mg.dist_sort(cV)[0]
 
     item("sort! 2^30 Float32 total", sort_f32, lambda ms: {"ms": ms, "Gkeys/s": total / ms / 1e6},
-         base=(mk_f32, lambda x: b.sort_(x)), verify=lambda: sorted_across_ranks(holder["r"], total, torch.float32))
+         base=(mk_f32, lambda x: b.sort_(x), 2, True), verify=lambda: sorted_across_ranks(holder["r"], total, torch.float32))
     item("sortperm 2^30 Float32 total", lambda: mg.dist_sortperm(cV), lambda ms: {"ms": ms, "Gkeys/s": total / ms / 1e6}, reps=2,
          base=(mk_f32, lambda x: b.sortperm(x)))
     holder.clear()
@@ -670,7 +666,7 @@ def run_extras_sharded(b, dt, torch, dist, dev, rank, world, peak):
 
     item("sort! 2^30 UInt32 total", sort_u32, lambda ms: {"ms": ms, "Gkeys/s": total / ms / 1e6},
          base=(lambda: b.CuArray.from_torch(torch.randint(-2**31, 2**31 - 1, (total,), device=dev, generator=g1, dtype=torch.int32), (total,), dt.U32),
-               lambda x: b.sort_(x)),
+               lambda x: b.sort_(x), 2, True),
          verify=lambda: sorted_across_ranks(holder["r"], total, torch.uint32))
     holder.clear()
     del U, cU

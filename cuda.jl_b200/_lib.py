@@ -39,6 +39,8 @@ SIGNATURES = {
     "b200_mgpu_plan_bytes": (_i32, [_c.POINTER(_sz)]),
     "b200_mgpu_hist16": (_i32, [_vp, _i32, _i64, _i32, _i32, _vp, _vp]),
     "b200_mgpu_partition_pairs": (_i32, [_vp, _sz, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _i32, _vp]),
+    "b200_mgpu_partition_index": (_i32, [_vp, _sz, _vp, _i32, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp]),
+    "b200_mgpu_widen_index": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "b200_mgpu_plan": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "b200_mgpu_scatter_workspace_bytes": (_i32, [_i64, _c.POINTER(_sz)]),
     "b200_mgpu_scatter": (_i32, [_vp, _sz, _vp, _i32, _i64, _i32, _vp, _vp, _i32, _vp]),

@@ -153,7 +153,17 @@ __global__ void __launch_bounds__(1024, 1) mgpu_plan_kernel(MgpuPlanParams p) {
             const unsigned long long other = __shfl_xor_sync(0x0000ffffu, mx, o);
             mx = mx > other ? mx : other;
         }
+        // longest shard (source b's keys over all buckets): sizes sortperm's 4-byte tagged index
+        unsigned long long len = 0;
+        for (int d = 0; d < G; ++d) len += b < G ? s_cnt[b][d] : 0;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0x0000ffffu, len, o);
+            len = len > other ? len : other;
+        }
         if (tid == 0) {
+            p.plan->max_shard_len = (uint32_t)(len > 0xFFFFFFFFull ? 0xFFFFFFFFull : len);
+            p.plan->pad = 0;
             unsigned long long rt = 0;
             for (int s = 0; s < G; ++s) rt += s_cnt[s][p.rank];
             p.plan->recv_total = rt;

@@ -19,6 +19,7 @@ struct PartParams {
     const void *keys_in;
     void *keys_out;
     const void *vals_in;     // optional 8-byte payload
+    uint32_t index_tag;      // VM == 2: the payload is generated, index_tag | (element index in keys_in), 4 bytes
     void *vals_out;
     // scatter destinations: bucket b goes to dst_keys[b] (+ dst_vals[b]) starting at element dst_base[b];
     // local partition: all the same buffer with the packed bucket bases; multi-GPU: peer (NVLink-mapped) buffers
@@ -128,12 +129,14 @@ __global__ void __launch_bounds__(256) partition_scan_kernel(PartParams p) {
 // Ranked scatter.  Keys (and payload) are first staged in shared memory grouped by bucket, then
 // written out with consecutive threads on consecutive addresses of each bucket run (~TILE/G keys,
 // i.e. full 128-byte lines): this is what makes stores into PEER memory over NVLink efficient.
-template <class K, bool HAS_V>
+// VM: 0 keys only, 1 an 8-byte payload read from vals_in, 2 a generated 4-byte payload (tagged source index)
+template <class K, int VM>
 __global__ void __launch_bounds__(RX_THREADS) partition_scatter_kernel(PartParams p) {
+    using V = typename std::conditional<VM == 2, unsigned int, unsigned long long>::type;
     extern __shared__ __align__(16) unsigned char s_raw[];
     K *s_keys = reinterpret_cast<K *>(s_raw);                                        // [PT_TILE]
     unsigned char *s_bid = reinterpret_cast<unsigned char *>(s_keys + PT_TILE);      // [PT_TILE]
-    unsigned long long *s_vals = reinterpret_cast<unsigned long long *>(s_bid + PT_TILE);   // [PT_TILE] (HAS_V)
+    V *s_vals = reinterpret_cast<V *>(s_bid + PT_TILE);                              // [PT_TILE] (VM != 0)
     __shared__ K s_spl[PT_MAXB];
     __shared__ unsigned int s_wcnt[RX_WARPS][PT_MAXB];
     __shared__ unsigned int s_boff[PT_MAXB];       // start of each bucket run inside the staged tile
@@ -194,7 +197,8 @@ __global__ void __launch_bounds__(RX_THREADS) partition_scatter_kernel(PartParam
             const unsigned int pos = s_boff[bid[i]] + s_wcnt[warp][bid[i]] + ranks[i];
             s_keys[pos] = keys[i];
             s_bid[pos] = bid[i];
-            if constexpr (HAS_V) s_vals[pos] = ldg_stream(vin + i * 32);
+            if constexpr (VM == 1) s_vals[pos] = ldg_stream(vin + i * 32);
+            if constexpr (VM == 2) s_vals[pos] = p.index_tag | (unsigned int)(tile_base + idx0 + i * 32);
         }
     }
     __syncthreads();
@@ -202,15 +206,31 @@ __global__ void __launch_bounds__(RX_THREADS) partition_scatter_kernel(PartParam
         const int b = s_bid[i];
         const long long dst = s_dst[b] + (i - (int)s_boff[b]);
         static_cast<K *>(p.dst_keys[b])[dst] = s_keys[i];
-        if constexpr (HAS_V) static_cast<unsigned long long *>(p.dst_vals[b])[dst] = s_vals[i];
+        if constexpr (VM != 0) static_cast<V *>(p.dst_vals[b])[dst] = s_vals[i];
     }
 }
 
-static size_t scatter_smem(int kb, bool has_v) { return (size_t)PT_TILE * (kb + 1) + 16 + (has_v ? (size_t)PT_TILE * 8 : 0); }
+static size_t scatter_smem(int kb, int vm) { return (size_t)PT_TILE * (kb + 1) + 16 + (vm == 1 ? (size_t)PT_TILE * 8 : vm == 2 ? (size_t)PT_TILE * 4 : 0); }
+
+template <class K, int VM>
+static int32_t launch_scatter(const PartParams &p, cudaStream_t st) {
+    const size_t smem = scatter_smem((int)sizeof(K), VM);
+    static thread_local bool attr_set[64];
+    int dev = 0;
+    B200_CUDA_TRY(cudaGetDevice(&dev));
+    auto kern = partition_scatter_kernel<K, VM>;
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[dev] = true;
+    }
+    kern<<<(unsigned int)p.tiles, RX_THREADS, smem, st>>>(p);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
 
 // phase: 1 = count + scan (leaves the per-tile prefixes in the workspace), 2 = scatter, 3 = both
 template <class K>
-static int32_t run_partition(void *ws, size_t wsb, PartParams p, bool has_v, int phase, cudaStream_t st, size_t *query) {
+static int32_t run_partition(void *ws, size_t wsb, PartParams p, int vm, int phase, cudaStream_t st, size_t *query) {
     p.tiles = cdiv(p.n, PT_TILE);
     Carver c(ws);
     long long *tile_counts = c.take<long long>((size_t)p.G * p.tiles);
@@ -226,26 +246,8 @@ static int32_t run_partition(void *ws, size_t wsb, PartParams p, bool has_v, int
         B200_CHECK_LAUNCH();
     }
     if (phase & 2) {
-        const size_t smem = scatter_smem((int)sizeof(K), has_v);
-        static thread_local bool attr_set[64][2];
-        int dev = 0;
-        B200_CUDA_TRY(cudaGetDevice(&dev));
-        if (has_v) {
-            auto kern = partition_scatter_kernel<K, true>;
-            if (dev >= 0 && dev < 64 && !attr_set[dev][1]) {
-                B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_set[dev][1] = true;
-            }
-            kern<<<(unsigned int)p.tiles, RX_THREADS, smem, st>>>(p);
-        } else {
-            auto kern = partition_scatter_kernel<K, false>;
-            if (dev >= 0 && dev < 64 && !attr_set[dev][0]) {
-                B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_set[dev][0] = true;
-            }
-            kern<<<(unsigned int)p.tiles, RX_THREADS, smem, st>>>(p);
-        }
-        B200_CHECK_LAUNCH();
+        const int32_t rc = vm == 1 ? launch_scatter<K, 1>(p, st) : vm == 2 ? launch_scatter<K, 2>(p, st) : launch_scatter<K, 0>(p, st);
+        if (rc != B200_OK) return rc;
     }
     return B200_OK;
 }
@@ -282,6 +284,34 @@ static bool part_xform(int dtype, int descending, SortXform &x, int &kb) {
     return true;
 }
 
+// sortperm's last step on every rank: tagged 32-bit source indices -> global 1-based Int64 indices
+__global__ void __launch_bounds__(256) mgpu_widen_index_kernel(const unsigned int *__restrict__ in, long long *__restrict__ out,
+                                                               int64_t n, int shift, const long long *__restrict__ offsets) {
+    __shared__ long long s_off[PT_MAXB];
+    if (threadIdx.x < PT_MAXB) s_off[threadIdx.x] = (int)threadIdx.x < (1 << (32 - shift)) && shift < 32 ? offsets[threadIdx.x] : 0;
+    __syncthreads();
+    const unsigned int low = shift >= 32 ? 0xFFFFFFFFu : ((1u << shift) - 1u);
+    const int64_t stride = (int64_t)gridDim.x * 256 * 4;
+    for (int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 4 <= n) {
+            const Vec16 v = ldg_stream16(in + i);
+            const unsigned int w[4] = {v.w[0], v.w[1], v.w[2], v.w[3]};
+            longlong2 o[2];
+            o[0].x = s_off[shift >= 32 ? 0 : (w[0] >> shift)] + (w[0] & low) + 1;
+            o[0].y = s_off[shift >= 32 ? 0 : (w[1] >> shift)] + (w[1] & low) + 1;
+            o[1].x = s_off[shift >= 32 ? 0 : (w[2] >> shift)] + (w[2] & low) + 1;
+            o[1].y = s_off[shift >= 32 ? 0 : (w[3] >> shift)] + (w[3] & low) + 1;
+            reinterpret_cast<longlong2 *>(out + i)[0] = o[0];
+            reinterpret_cast<longlong2 *>(out + i)[1] = o[1];
+        } else {
+            for (int64_t j = i; j < n; ++j) {
+                const unsigned int w = in[j];
+                out[j] = s_off[shift >= 32 ? 0 : (w >> shift)] + (w & low) + 1;
+            }
+        }
+    }
+}
+
 }  // namespace b200
 
 extern "C" {
@@ -293,14 +323,15 @@ int32_t b200_partition_workspace_bytes(int64_t n, int32_t nbuckets, size_t *byte
     if (n == 0) return B200_OK;
     PartParams p{};
     p.n = n; p.G = nbuckets;
-    return run_partition<uint32_t>(nullptr, 0, p, false, 3, nullptr, bytes);
+    return run_partition<uint32_t>(nullptr, 0, p, 0, 3, nullptr, bytes);
 }
 
 static int32_t partition_common(void *workspace, size_t workspace_bytes, const void *keys_in, const void *payload_in,
                                 int32_t dtype_key, int64_t n, const void *splitters, int32_t nbuckets,
                                 int32_t descending, void *bucket_counts_dev, int phase, void *const *dst_keys,
                                 void *const *dst_payload, const int64_t *dst_base, int local_bases,
-                                b200_stream_t stream, const void *plan_dev = nullptr) {
+                                b200_stream_t stream, const void *plan_dev = nullptr, int gen_index = 0,
+                                uint32_t index_tag = 0) {
     using namespace b200;
     if (n < 0 || nbuckets < 1 || nbuckets > PT_MAXB || !bucket_counts_dev) return B200_INVALID_VALUE;
     SortXform xf; int kb;
@@ -317,7 +348,8 @@ static int32_t partition_common(void *workspace, size_t workspace_bytes, const v
     p.keys_in = keys_in; p.vals_in = payload_in;
     p.splitters = splitters; p.bucket_counts = static_cast<long long *>(bucket_counts_dev);
     p.n = n; p.G = nbuckets; p.xf = xf; p.local_bases = local_bases;
-    const bool has_v = payload_in != nullptr;
+    const bool has_v = payload_in != nullptr || gen_index;
+    p.index_tag = index_tag;
     if (phase & 2) {
         if (!dst_keys || (has_v && !dst_payload)) return B200_INVALID_VALUE;
         for (int b = 0; b < nbuckets; ++b) {
@@ -327,7 +359,7 @@ static int32_t partition_common(void *workspace, size_t workspace_bytes, const v
             p.dst_base[b] = dst_base ? dst_base[b] : 0;
         }
     }
-    return run_partition_kb(kb, workspace, workspace_bytes, p, has_v, phase, st, (size_t *)nullptr);
+    return run_partition_kb(kb, workspace, workspace_bytes, p, gen_index ? 2 : (has_v ? 1 : 0), phase, st, (size_t *)nullptr);
 }
 
 int32_t b200_partition(void *workspace, size_t workspace_bytes, const void *keys_in, void *keys_out,
@@ -366,6 +398,35 @@ int32_t b200_mgpu_partition_pairs(void *workspace, size_t workspace_bytes, const
     // the first 256 bytes of the workspace hold the bucket totals the count phase writes
     return partition_common(static_cast<char *>(workspace) + 256, workspace_bytes - 256, keys, payload, dtype_key, n, nullptr,
                             nranks, descending, workspace, 3, dst_keys, dst_payload, nullptr, 0, stream, plan_dev);
+}
+
+// sortperm's exchange without a payload to read: the payload is GENERATED as (rank << shift) | source index, 4 bytes
+// (needs nranks <= 2^(32 - shift) and n <= 2^shift).  dst_index: per-rank UInt32 receive buffers.
+int32_t b200_mgpu_partition_index(void *workspace, size_t workspace_bytes, const void *keys, int32_t dtype_key, int64_t n,
+                                  int32_t descending, const void *plan_dev, int32_t rank, int32_t shift,
+                                  void *const *dst_keys, void *const *dst_index, int32_t nranks, b200_stream_t stream) {
+    if (!plan_dev || !workspace || workspace_bytes < 256) return B200_INVALID_VALUE;
+    if (shift < 1 || shift > 32 || rank < 0 || rank >= nranks || n > (1ll << shift)) return B200_INVALID_VALUE;
+    if (shift < 32 ? ((int64_t)nranks > (1ll << (32 - shift))) : nranks > 1) return B200_INVALID_VALUE;
+    const uint32_t tag = shift < 32 ? ((uint32_t)rank << shift) : 0u;
+    return partition_common(static_cast<char *>(workspace) + 256, workspace_bytes - 256, keys, nullptr, dtype_key, n, nullptr,
+                            nranks, descending, workspace, 3, dst_keys, dst_index, nullptr, 0, stream, plan_dev, 1, tag);
+}
+
+// out[i] = offsets[index[i] >> shift] + (index[i] & (2^shift - 1)) + 1   (global 1-based Int64 indices); offsets: Int64[16]
+// on the device (entries past the rank count are not read when the tags are valid, but must be readable).
+int32_t b200_mgpu_widen_index(const void *index_u32, int64_t n, int32_t shift, const void *offsets_dev, void *out_i64,
+                              b200_stream_t stream) {
+    using namespace b200;
+    if (n < 0 || shift < 1 || shift > 32) return B200_INVALID_VALUE;
+    if (n == 0) return B200_OK;
+    if (!index_u32 || !offsets_dev || !out_i64) return B200_INVALID_VALUE;
+    const int64_t blocks = std::min<int64_t>(cdiv(n, 1024), 148 * 16);
+    mgpu_widen_index_kernel<<<(unsigned int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        static_cast<const unsigned int *>(index_u32), static_cast<long long *>(out_i64), n, shift,
+        static_cast<const long long *>(offsets_dev));
+    B200_CHECK_LAUNCH();
+    return B200_OK;
 }
 
 }  // extern "C"

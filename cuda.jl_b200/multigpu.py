@@ -108,6 +108,40 @@ class DeviceOps:
         n = info["recv_total"]
         return kbuf[:n * 4], pbuf[:n * 8]
 
+    def mgpu_exchange_index(self, shard, rev, plan, info, group, shift):
+        """sortperm's exchange with a generated payload: stable partition of the keys, each carrying the 4-byte tagged
+        index (rank << shift) | position in this shard.  Returns uint8 views (keys, tagged UInt32 indices)."""
+        import ctypes
+        from . import _lib
+        from .cuarray import Workspace
+        lib = _lib.load()
+        G, r = _world(group)
+        dev = shard.buf.device
+        cap = max(info["max_recv_total"], 1)
+        kbuf, khdl = _symm_buffer("keys", cap * 4, dev, group)
+        pbuf, phdl = _symm_buffer("index", cap * 4, dev, group)
+        nb = ctypes.c_size_t(0)
+        _lib.check(lib.b200_partition_workspace_bytes(shard.length, G, ctypes.byref(nb)))
+        ws = Workspace(nb.value + 256, dev)
+        kp = (ctypes.c_void_p * G)(*[int(x) for x in khdl.buffer_ptrs])
+        pp = (ctypes.c_void_p * G)(*[int(x) for x in phdl.buffer_ptrs])
+        khdl.barrier()
+        _lib.check(lib.b200_mgpu_partition_index(ws.ptr, ws.nbytes, shard.pointer if shard.length else None, shard.eltype,
+                                                 shard.length, 1 if rev else 0, plan.data_ptr(), r, shift, kp, pp, G,
+                                                 current_stream_handle(dev)))
+        khdl.barrier()
+        n = info["recv_total"]
+        return kbuf[:n * 4], pbuf[:n * 4]
+
+    def widen_index(self, index_u8, n, shift, offsets):
+        """tagged UInt32 indices -> global 1-based Int64 indices (offsets: Int64[16] on the device)."""
+        from . import _lib
+        lib = _lib.load()
+        out = CuArray.undef(dt.I64, (n,), index_u8.device)
+        _lib.check(lib.b200_mgpu_widen_index(index_u8.data_ptr() if n else None, n, shift, offsets.data_ptr(),
+                                             out.pointer if n else None, current_stream_handle(index_u8.device)))
+        return out
+
     def mgpu_plan(self, hist_all, G, r):
         """(plan buffer, hist_recv) on the device from the all-gathered histograms; then ONE small device-to-host
         copy of the plan (the only synchronisation of the sort: the slice length sizes the result)."""
@@ -125,7 +159,7 @@ class DeviceOps:
         u64 = host[80:488].view(np.uint64)                  # dst_base[16], send_count[16], recv_count[16], 3 scalars
         info = {"spl": host[:68].view(np.uint32)[:G + 1].copy(), "dst_base": u64[:G].copy(), "send_count": u64[16:16 + G].copy(),
                 "recv_count": u64[32:32 + G].copy(), "recv_total": int(u64[48]), "max_recv_total": int(u64[49]),
-                "total": int(u64[50])}
+                "total": int(u64[50]), "max_shard_len": int(host[72:76].view(np.uint32)[0])}
         return plan, hist_recv, info
 
     def mgpu_exchange(self, shard, rev, plan, info, group):
@@ -588,11 +622,23 @@ def _dist_sortperm_device(shard, rev, group, ops):
     hist_all = torch.empty(G * 65536, dtype=torch.int32, device=dev)
     dist.all_gather_into_tensor(hist_all, hist.typed().view(torch.int32), group=group)
     plan, _, info = ops.mgpu_plan(hist_all, G, r)
-    offset = hist_all.view(G, 65536)[:r].sum(dtype=torch.int64) if r > 0 else torch.zeros((), dtype=torch.int64, device=dev)
+    tot = hist_all.view(G, 65536).sum(dim=1, dtype=torch.int64)         # shard lengths, on the device
+    n = info["recv_total"]
+    # the payload that travels and is sorted is 4 bytes: (source rank, position in its shard); it fits whenever
+    # bits(G - 1) + bits(longest shard - 1) <= 32, i.e. up to 2^32 keys in total with even shards
+    shift = max(1, (max(int(info.get("max_shard_len", 1 << 33)), 1) - 1).bit_length())
+    if shift + max(G - 1, 1).bit_length() <= 32 and hasattr(ops, "mgpu_exchange_index"):
+        offsets = torch.zeros(16, dtype=torch.int64, device=dev)
+        offsets[1:G] = torch.cumsum(tot, 0)[:G - 1]
+        kview, iview = ops.mgpu_exchange_index(shard, rev, plan, info, group, shift)
+        rk = CuArray(kview, (n,), shard.eltype)
+        ri = CuArray(iview, (n,), dt.U32)
+        ops.sort_pairs(rk, ri, rev)                     # in place inside the symmetric buffers, 8 bytes per pair
+        return ops.widen_index(iview, n, shift, offsets)
+    offset = tot[:r].sum() if r > 0 else torch.zeros((), dtype=torch.int64, device=dev)
     idx = torch.arange(1, shard.length + 1, dtype=torch.int64, device=dev) + offset
     payload = CuArray(idx.view(torch.uint8), (shard.length,), dt.I64)
     kview, pview = ops.mgpu_exchange_pairs(shard, payload, rev, plan, info, group)
-    n = info["recv_total"]
     rk = CuArray(kview, (n,), shard.eltype)
     rp = CuArray(pview, (n,), dt.I64)
     ops.sort_pairs(rk, rp, rev)                     # in place inside the symmetric buffers

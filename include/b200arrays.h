@@ -191,7 +191,8 @@ int32_t b200_scan_carry(void *workspace, size_t workspace_bytes,
 typedef struct b200_mgpu_plan {
     uint32_t spl[17];             /* bucket b = 16-bit bins [spl[b], spl[b+1]) */
     uint32_t ticket;
-    uint32_t pad[2];
+    uint32_t max_shard_len;       /* keys held by the longest shard (saturating) */
+    uint32_t pad;
     uint64_t dst_base[16];        /* element index of this rank's first key inside destination b's receive buffer */
     uint64_t send_count[16];      /* keys this rank sends to destination b */
     uint64_t recv_count[16];      /* keys this rank receives from source s */
@@ -213,6 +214,16 @@ int32_t b200_mgpu_scatter(void *workspace, size_t workspace_bytes, const void *k
 int32_t b200_mgpu_partition_pairs(void *workspace, size_t workspace_bytes, const void *keys, const void *payload,
                                   int32_t dtype_key, int64_t n, int32_t descending, const void *plan_dev,
                                   void *const *dst_keys, void *const *dst_payload, int32_t nranks, b200_stream_t stream);
+/* The same exchange with a GENERATED 4-byte payload instead of one read from memory: (rank << shift) | source index
+ * (needs n <= 2^shift and nranks <= 2^(32 - shift)); dst_index[b]: UInt32 receive buffers.  After the local pairs sort,
+ * b200_mgpu_widen_index turns the tagged indices into global 1-based Int64 indices:
+ * out[i] = offsets[index[i] >> shift] + (index[i] & (2^shift - 1)) + 1, offsets = Int64[16] on the device (the number of
+ * keys held by the ranks before each source rank). */
+int32_t b200_mgpu_partition_index(void *workspace, size_t workspace_bytes, const void *keys, int32_t dtype_key, int64_t n,
+                                  int32_t descending, const void *plan_dev, int32_t rank, int32_t shift,
+                                  void *const *dst_keys, void *const *dst_index, int32_t nranks, b200_stream_t stream);
+int32_t b200_mgpu_widen_index(const void *index_u32, int64_t n, int32_t shift, const void *offsets_dev, void *out_i64,
+                              b200_stream_t stream);
 /* sort! of `n` keys read from `src` into `dst` (src is only read; src == dst sorts in place; workspace as for
  * b200_sort_workspace_bytes(dtype_key, -1, n, 1)).  hist16_dev, if not NULL, is the exact histogram of the top 16 bits
  * of the order-mapped keys of `src` (b200_mgpu_plan's hist_recv_dev): the sort then skips its own histogram pass. */

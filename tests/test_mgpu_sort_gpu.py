@@ -120,9 +120,10 @@ def test_dense_slice_takes_the_hybrid_path(b):
     assert int(got.astype(np.uint64).sum()) == int(full.astype(np.uint64).sum())
 
 
-def emulate_sortperm(b, full, G, rev):
+def emulate_sortperm(b, full, G, rev, tagged=False):
     """sortperm's exchange on one GPU: nan-canonical histogram, plan, stable pairs partition into G local buffers,
-    stable local pairs sort; returns the concatenated global 1-based permutation."""
+    stable local pairs sort; returns the concatenated global 1-based permutation.  tagged: the 4-byte generated payload
+    (rank << shift | position) and the widening kernel instead of an Int64 payload read from memory."""
     lib = b._lib.load()
     dt = b.dtypes
     et = dt.from_np(full.dtype)
@@ -142,9 +143,12 @@ def emulate_sortperm(b, full, G, rev):
         b._lib.check(lib.b200_mgpu_plan(hist_all.data_ptr(), G, r, plan.data_ptr(), hr.data_ptr(), stream))
         u64 = plan.cpu().numpy()[80:488].view(np.uint64)
         plans.append(plan); totals.append((int(u64[48]), int(u64[49])))
+        max_shard = int(plan.cpu().numpy()[72:76].view(np.uint32)[0])
+        assert max_shard == max(s.length for s in shards)
+    shift = max(1, (max_shard - 1).bit_length())
     cap = max(totals[0][1], 1)
     rk = [torch.zeros(cap, dtype=torch.int32, device=dev) for _ in range(G)]
-    rp = [torch.zeros(cap, dtype=torch.int64, device=dev) for _ in range(G)]
+    rp = [torch.zeros(cap, dtype=torch.int32 if tagged else torch.int64, device=dev) for _ in range(G)]
     kp = (ctypes.c_void_p * G)(*[t.data_ptr() for t in rk])
     pp = (ctypes.c_void_p * G)(*[t.data_ptr() for t in rp])
     for r, s in enumerate(shards):
@@ -153,27 +157,34 @@ def emulate_sortperm(b, full, G, rev):
         b._lib.check(lib.b200_partition_workspace_bytes(s.length, G, ctypes.byref(w)))
         ws = torch.empty(w.value + 256, dtype=torch.uint8, device=dev)
         ws.fill_(0xA5)
-        b._lib.check(lib.b200_mgpu_partition_pairs(ws.data_ptr(), w.value + 256, s.pointer, idx.data_ptr(), et, s.length, int(rev),
-                                                   plans[r].data_ptr(), kp, pp, G, stream))
+        if tagged:
+            b._lib.check(lib.b200_mgpu_partition_index(ws.data_ptr(), w.value + 256, s.pointer, et, s.length, int(rev),
+                                                       plans[r].data_ptr(), r, shift, kp, pp, G, stream))
+        else:
+            b._lib.check(lib.b200_mgpu_partition_pairs(ws.data_ptr(), w.value + 256, s.pointer, idx.data_ptr(), et, s.length,
+                                                       int(rev), plans[r].data_ptr(), kp, pp, G, stream))
     out = []
     ops = b.multigpu.DeviceOps()
+    offsets = torch.zeros(16, dtype=torch.int64, device=dev)
+    offsets[:G] = torch.as_tensor(cuts[:G].astype(np.int64), device=dev)
     for r in range(G):
         n = totals[r][0]
         keys = b.CuArray(rk[r][:n].view(torch.uint8), (n,), et)
-        pay = b.CuArray(rp[r][:n].view(torch.uint8), (n,), dt.I64)
+        pay = b.CuArray(rp[r][:n].view(torch.uint8), (n,), dt.U32 if tagged else dt.I64)
         ops.sort_pairs(keys, pay, rev)
-        out.append(b.Array(pay))
+        out.append(b.Array(ops.widen_index(rp[r][:n].view(torch.uint8), n, shift, offsets)) if tagged else b.Array(pay))
     return np.concatenate(out)
 
 
+@pytest.mark.parametrize("tagged", [False, True])
 @pytest.mark.parametrize("G", [2, 5])
 @pytest.mark.parametrize("rev", [False, True])
-def test_emulated_sortperm_is_stable_across_ranks(b, G, rev):
+def test_emulated_sortperm_is_stable_across_ranks(b, G, rev, tagged):
     rng = np.random.default_rng(31 + G)
     full = rng.standard_normal(1_500_007).astype(np.float32)
     full[::97] = 0.25                                   # heavy ties: stability across tiles, ranks and the local sort
     full[[11, 500_000, 1_400_000]] = np.nan             # several NaNs with the same key: they keep ascending index
     full[[12, 13]] = [-0.0, 0.0]
-    np.testing.assert_array_equal(emulate_sortperm(b, full, G, rev), oracle.sortperm(full, rev=rev))
+    np.testing.assert_array_equal(emulate_sortperm(b, full, G, rev, tagged), oracle.sortperm(full, rev=rev))
     u = rng.integers(0, 40, size=700_001, dtype=np.uint32) * np.uint32(100_000_000)
-    np.testing.assert_array_equal(emulate_sortperm(b, u, G, rev), oracle.sortperm(u, rev=rev))
+    np.testing.assert_array_equal(emulate_sortperm(b, u, G, rev, tagged), oracle.sortperm(u, rev=rev))
