@@ -60,6 +60,22 @@ __device__ __forceinline__ unsigned int ld_cg_u32(const unsigned int *p) {
     return v;
 }
 
+// Store v to p[OFF] when c > TH.  The address is computed once, unconditionally, and only the store is predicated
+// (left to itself the compiler re-derives every 64-bit address under its store's predicate: 55 instructions per table
+// word of the leaf's expand loop instead of ~30).
+template <int TH, int OFF> __device__ __forceinline__ void st_if_gt(uint32_t *p, uint32_t v, unsigned int c) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.gt.u32 q, %2, %3;\n\t@q st.global.u32 [%0+%4], %1;\n\t}"
+                 :: "l"(p), "r"(v), "r"(c), "n"(TH), "n"(OFF * 4) : "memory");
+}
+// Inclusive warp scan with the shuffle's own range predicate (SHFL.UP P + predicated add: 2 instructions per step).
+__device__ __forceinline__ unsigned int warp_incl_scan(unsigned int v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+        asm volatile("{\n\t.reg .pred q;\n\t.reg .u32 t;\n\tshfl.sync.up.b32 t|q, %0, %1, 0, 0xffffffff;\n\t@q add.u32 %0, %0, t;\n\t}"
+                     : "+r"(v) : "r"(o));
+    return v;
+}
+
 // ------------------------------------------------------------------ H: histogram of the top 16 bits
 // IDENT: the key transform is the identity (unsigned ascending) and is skipped.
 template <bool IDENT>
@@ -578,7 +594,6 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
     constexpr int CH = MSD_LEAF_CHUNK;
     extern __shared__ __align__(16) unsigned int s_bins[];   // [WORDS] packed counters, all zero between segments
     __shared__ unsigned int s_wtot[NW];
-    __shared__ int s_over;
     __shared__ unsigned int s_nheavy;
     __shared__ uint4 s_heavy[BITS == 16 ? 65536 / MSD_LEAF_HEAVY + 1 : 1];   // {value, first position, copies}
 
@@ -587,7 +602,7 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int nne = ld_cg_u32(&p.ctl->nne);
     for (int i = tid; i < WORDS / 4; i += NT) reinterpret_cast<uint4 *>(s_bins)[i] = make_uint4(0, 0, 0, 0);
-    if (tid == 0) { s_over = 0; s_nheavy = 0; }
+    if (tid == 0) s_nheavy = 0;
 
     // Segments are dealt round-robin to the persistent CTAs (independent work: no ticket).  Bounds of the next segment
     // and the id of the one after are loaded an iteration early; every thread loads the same words (broadcast).
@@ -617,6 +632,17 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
             uint32_t *base = p.keys + lo;
             // ---- count: one shared atomic per key.  Loads go out CH at a time (a load -> atomic -> load chain would
             // expose one memory round trip per key).
+            // 8-bit bins: the add needs no return value and no per-key overflow test — a field that wraps loses 255 (carry
+            // into the next field) or 256 (carry out of the word) from the table's byte sum, so "sum of all bins != m"
+            // after the count detects every overflow (fields hold up to 255 copies).
+            auto count_one = [&](uint32_t key) {
+                if constexpr (BITS == 8) {
+                    const unsigned int inc = __funnelshift_l(0u, 1u, key << 3);              // 1 << 8 * (key & 3)
+                    atomicAdd(reinterpret_cast<unsigned int *>(reinterpret_cast<unsigned char *>(s_bins) + (key & 0xFFFCu)), inc);
+                } else {
+                    atomicAdd(&s_bins[(key & 0xFFFFu) >> 1], (key & 1u) ? 0x10000u : 1u);
+                }
+            };
             for (int i0 = 0; i0 < m; i0 += CH * NT) {
                 uint32_t kk[CH];
                 if (i0 + CH * NT <= m) {
@@ -639,12 +665,7 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
                         }
                     } else {
 #pragma unroll
-                        for (int c = 0; c < CH; ++c) {
-                            const unsigned int v = kk[c] & 0xFFFFu;
-                            const unsigned int sh = (v % PER_WORD) * BITS;
-                            const unsigned int old = atomicAdd(&s_bins[v / PER_WORD], 1u << sh);
-                            if (BITS == 8 && (old & (0x80u << sh))) s_over = 1;
-                        }
+                        for (int c = 0; c < CH; ++c) count_one(kk[c]);
                     }
                 } else {
 #pragma unroll
@@ -653,22 +674,14 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
                         kk[c] = i < m ? ld_coh(base + i) : 0u;
                     }
 #pragma unroll
-                    for (int c = 0; c < CH; ++c) {
-                        const int i = i0 + c * NT + tid;
-                        if (i < m) {
-                            const unsigned int v = kk[c] & 0xFFFFu;
-                            const unsigned int sh = (v % PER_WORD) * BITS;
-                            const unsigned int old = atomicAdd(&s_bins[v / PER_WORD], 1u << sh);
-                            if (BITS == 8 && (old & (0x80u << sh))) s_over = 1;
-                        }
-                    }
+                    for (int c = 0; c < CH; ++c)
+                        if (i0 + c * NT + tid < m) count_one(kk[c]);
                 }
             }
             __syncthreads();
-            const bool over = BITS == 8 && s_over != 0;      // uniform
             // ---- warp totals: warp w owns table words [w * WORDS_PER_WARP, (w + 1) * WORDS_PER_WARP)
             const unsigned int *wb = s_bins + warp * WORDS_PER_WARP;
-            if (!over) {
+            {
                 unsigned int acc = 0;
 #pragma unroll 8
                 for (int j = lane; j < WORDS_PER_WARP; j += 32) {
@@ -680,24 +693,30 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
                 if (lane == 0) s_wtot[warp] = acc;
             }
             __syncthreads();
+            unsigned int run = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const unsigned int t = s_wtot[w];
+                run += (w < warp) ? t : 0u;
+                total += t;
+            }
+            const bool over = BITS == 8 && total != (unsigned int)m;      // uniform: some 8-bit field wrapped
             if (over) {
-                // a value occurs 128 times or more: hand the segment to the 16-bit kernel and clear the table
+                // a value occurs 256 times or more: hand the segment to the 16-bit kernel and clear the table
+                __syncthreads();                                          // every thread has read s_wtot / the table
                 for (int i = tid; i < WORDS / 4; i += NT) reinterpret_cast<uint4 *>(s_bins)[i] = make_uint4(0, 0, 0, 0);
-                if (tid == 0) { p.redo[k] = 1u; s_over = 0; atomicAdd(&p.ctl->pad, 1u); }
+                if (tid == 0) { p.redo[k] = 1u; atomicAdd(&p.ctl->pad, 1u); }
             } else {
                 // ---- expand: walk the table in value order; 32 words (32 * PER_WORD values) per step and warp.
                 // A lane emits its word's values `count` times each at consecutive positions, lanes back to back.
-                unsigned int run = 0;
-#pragma unroll
-                for (int w = 0; w < NW; ++w) run += (w < warp) ? s_wtot[w] : 0u;
-                const uint32_t hi16 = ld_coh(base) & 0xFFFF0000u;        // any key of the segment (read before any write: barrier above)
+                const uint32_t hi16 = seg << 16;                          // the segment id IS the keys' top 16 bits
                 unsigned int *wbw = s_bins + warp * WORDS_PER_WARP;
-                __syncthreads();                                          // every warp has read base[0]
+                uint32_t *const kall = p.keys;                            // 32-bit element index + kernel parameter: one IMAD.WIDE per address
                 // A lane writes its word's values at consecutive positions, lanes back to back.  Counts are nearly always
                 // 0 or 1: the first copy of each field is one predicated store at a precomputed offset; further copies
                 // (10 % of the words) share ONE short loop over the copy number instead of a loop per field.
                 auto emit = [&](unsigned int w, unsigned int pos, uint32_t v0) {
-                    uint32_t *out = base + pos;
+                    const unsigned int g0 = lo + pos;                     // element index into the whole key array (< 2^30)
                     if constexpr (BITS == 8) {
                         const unsigned int c0 = w & 0xFFu, c1 = (w >> 8) & 0xFFu, c2 = (w >> 16) & 0xFFu, c3 = w >> 24;
                         const unsigned int o1 = c0, o2 = o1 + c1, o3 = o2 + c2;
@@ -707,15 +726,15 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
                         const uint32_t k3 = IDENT ? v0 + 3 : key_decode<uint32_t>(v0 + 3, p.xf);
                         // first and second copies: straight-line predicated stores (98 % of the non-empty bins hold one key,
                         // 2.4 % two); a bin with three or more copies anywhere in the word takes the loop below
-                        uint32_t *a1 = out + o1, *a2 = out + o2, *a3 = out + o3;
-                        if (c0) out[0] = k0;
-                        if (c1) a1[0] = k1;
-                        if (c2) a2[0] = k2;
-                        if (c3) a3[0] = k3;
-                        if (c0 > 1) out[1] = k0;
-                        if (c1 > 1) a1[1] = k1;
-                        if (c2 > 1) a2[1] = k2;
-                        if (c3 > 1) a3[1] = k3;
+                        uint32_t *out = kall + g0, *a1 = kall + (g0 + o1), *a2 = kall + (g0 + o2), *a3 = kall + (g0 + o3);
+                        st_if_gt<0, 0>(out, k0, c0);
+                        st_if_gt<0, 0>(a1, k1, c1);
+                        st_if_gt<0, 0>(a2, k2, c2);
+                        st_if_gt<0, 0>(a3, k3, c3);
+                        st_if_gt<1, 1>(out, k0, c0);
+                        st_if_gt<1, 1>(a1, k1, c1);
+                        st_if_gt<1, 1>(a2, k2, c2);
+                        st_if_gt<1, 1>(a3, k3, c3);
                         if ((w & 0xFCFCFCFCu) | (w & (w >> 1) & 0x01010101u)) {       // some count >= 3
                             const unsigned int mx = max(max(c0, c1), max(c2, c3));
 #pragma unroll 1
@@ -727,6 +746,7 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
                             }
                         }
                     } else {
+                        uint32_t *out = kall + g0;
                         const unsigned int c0 = w & 0xFFFFu, c1 = w >> 16;
                         const uint32_t k0 = IDENT ? v0 : key_decode<uint32_t>(v0, p.xf);
                         const uint32_t k1 = IDENT ? v0 + 1 : key_decode<uint32_t>(v0 + 1, p.xf);
@@ -750,17 +770,13 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
                         const unsigned int wA = wbw[j], wB = wbw[j + 32];
                         wbw[j] = 0; wbw[j + 32] = 0;                      // table is clean again for the next segment
                         const unsigned int cA = __dp4a(wA, 0x01010101u, 0u), cB = __dp4a(wB, 0x01010101u, 0u);
-                        unsigned int incl = cA | (cB << 16);
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
-                            if (lane >= o) incl += up;
-                        }
+                        const unsigned int incl = warp_incl_scan(cA | (cB << 16));
                         const unsigned int tot = __shfl_sync(0xffffffffu, incl, 31);
                         const unsigned int totA = tot & 0xFFFFu, totB = tot >> 16;
                         const uint32_t v0 = hi16 | (uint32_t)((warp * WORDS_PER_WARP + j) * PER_WORD);
-                        if (wA) emit(wA, run + (incl & 0xFFFFu) - cA, v0);
-                        if (wB) emit(wB, run + totA + (incl >> 16) - cB, v0 + 32 * PER_WORD);
+                        // no `if (w)` around the calls: an empty word's stores are all predicated off
+                        emit(wA, run + (incl & 0xFFFFu) - cA, v0);
+                        emit(wB, run + totA + (incl >> 16) - cB, v0 + 32 * PER_WORD);
                         run += totA + totB;
                     }
                 } else {
