@@ -239,12 +239,44 @@ __global__ void __launch_bounds__(MG_NT, 2) mgpu_scatter_kernel(MgpuScatterParam
             const unsigned int l = s_lut[t16 >> 8];
             unsigned int b = l & 0xFFu;
             for (unsigned int j = 0; j < (l >> 8); ++j) b += (t16 >= s_spl[(l & 0xFFu) + 1 + j]) ? 1u : 0u;
-            unsigned int r = 0;
-            if (i * MG_NT + tid < valid) r = atomicAdd(&s_whist[warp][b], 1u);
-            ranks.set(i, r);
+            if (i * MG_NT + tid >= valid) b = 0xFFu;          // past the end: no bucket
             if ((i & 3) == 0) bk[i >> 2] = b;
             else bk[i >> 2] |= b << (8 * (i & 3));
         }
+        // Ranks without atomics (G <= 16 buckets: 32 lanes adding to a handful of shared counters would serialise).
+        // Every lane counts its own keys per bucket, one warp scan per bucket turns the counts into a block of ranks
+        // per lane and the warp's bucket totals, and a second sweep hands the ranks out in item order.
+        auto rank_all = [&](auto gp_tag) {
+            constexpr int GP = decltype(gp_tag)::value;
+            unsigned int nxt[GP];
+#pragma unroll
+            for (int g = 0; g < GP; ++g) nxt[g] = 0;
+#pragma unroll
+            for (int i = 0; i < MG_ITEMS; ++i) {
+                const unsigned int b = (bk[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+#pragma unroll
+                for (int g = 0; g < GP; ++g) nxt[g] += (b == (unsigned int)g) ? 1u : 0u;
+            }
+#pragma unroll
+            for (int g = 0; g < GP; ++g) {
+                const unsigned int incl = warp_incl_scan(nxt[g]);
+                if ((tid & 31) == 31) s_whist[warp][g] = incl;
+                nxt[g] = incl - nxt[g];
+            }
+#pragma unroll
+            for (int i = 0; i < MG_ITEMS; ++i) {
+                const unsigned int b = (bk[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                unsigned int r = 0;
+#pragma unroll
+                for (int g = 0; g < GP; ++g)
+                    if (b == (unsigned int)g) { r = nxt[g]; nxt[g] += 1u; }
+                ranks.set(i, r);
+            }
+        };
+        if (G <= 2) rank_all(std::integral_constant<int, 2>{});
+        else if (G <= 4) rank_all(std::integral_constant<int, 4>{});
+        else if (G <= 8) rank_all(std::integral_constant<int, 8>{});
+        else rank_all(std::integral_constant<int, 16>{});
         __syncthreads();                                                             // (A)
         // bucket threads: warp offsets inside the bucket, tile count, publish, scan over the buckets
         unsigned int cnt = 0;

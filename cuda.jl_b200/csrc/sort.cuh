@@ -166,7 +166,7 @@ struct SortCtl {
     unsigned int nne;           // non-empty 16-bit segments
     unsigned int tiles2;        // level-2 tiles
     unsigned int max_seg;       // longest 16-bit segment (diagnostic)
-    unsigned int ticket1, ticket2, ticket_leaf, pad;
+    unsigned int ticket1, ticket2, ticket_leaf, n16;   // n16: entries of the 16-bit leaf's work list
     unsigned long long lsd_ticket[8];   // one tile ticket per LSD pass (persistent CTAs, no per-pass memset)
 };
 

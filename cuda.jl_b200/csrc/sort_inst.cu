@@ -110,8 +110,9 @@ constexpr int MSD_TILE_MIN = 4096;            // smallest P1 / P2 tile of any tu
 constexpr int MSD_TILE_MIN = 512 * 20;        // the P1 / P2 tile
 #endif
 constexpr int LEAF_NT = 512;
-constexpr unsigned int LEAF8_CAP = 32768;    // segments up to this many keys go to the 8-bit-bin leaf first
-constexpr unsigned int LEAF_MAX_SEG = 65535; // 16-bit bins cannot overflow up to here; longer segments: LSD fallback
+constexpr int LEAF16_NT = 1024;              // the 128 KB table leaves one CTA per SM: make it a full one
+constexpr unsigned int LEAF8_CAP = 1u << 18;  // segments up to this many keys (4 per value on average; a bin holds 255) go to the 8-bit-bin leaf first
+constexpr unsigned int LEAF_MAX_SEG = 65535; // always admitted; beyond it a segment may hold at most n / 64 keys (one CTA sorts it)
 constexpr unsigned int MSD_MIN_AVG = 3072;   // counting leaf: 65536 bins are walked per segment whatever its length
 constexpr int64_t MSD_MAX_N = 1LL << 30;     // 32-bit look-back words carry 30-bit counts
 
@@ -128,7 +129,7 @@ static bool xform_is_identity(const SortXform &x) { return x.base_enc == 0 && x.
 
 struct MsdBuffers {
     MsdCtl *ctl;
-    unsigned int *hist16, *status1, *status2, *redo, *seg_start, *seg_list, *l1_tile_start;
+    unsigned int *hist16, *status1, *status2, *list16, *spill, *seg_start, *seg_list, *l1_tile_start;
 };
 
 template <bool IDENT, int MSD_NT = 512, int MSD_ITEMS = 20>
@@ -152,8 +153,10 @@ static int32_t msd_launch(const SortCall &c, const MsdBuffers &b, uint32_t *alt,
     {   // PL
         MsdPlanParams pp{};
         pp.hist16 = c.hist16_in ? static_cast<const unsigned int *>(c.hist16_in) : b.hist16; pp.seg_start = b.seg_start; pp.seg_list = b.seg_list; pp.l1_tile_start = b.l1_tile_start;
+        pp.list16 = b.list16;
         pp.ctl = b.ctl; pp.n = (unsigned int)n; pp.tile2 = MSD_TILE;
-        pp.cap_a = LEAF_MAX_SEG; pp.cap_b = 0;
+        pp.cap8 = LEAF8_CAP;
+        pp.cap_a = (unsigned int)(n >> 6) > LEAF_MAX_SEG ? (unsigned int)(n >> 6) : LEAF_MAX_SEG;
         static const unsigned int min_avg = (unsigned int)tune_int("B200_MSD_MIN_AVG", (int)MSD_MIN_AVG);
         pp.min_avg = min_avg;
         msd_plan_kernel<<<1, 1024, 0, st>>>(pp);
@@ -190,11 +193,11 @@ static int32_t msd_launch(const SortCall &c, const MsdBuffers &b, uint32_t *alt,
     }
     MsdLeafParams lp{};
     lp.keys = static_cast<uint32_t *>(c.keys); lp.seg_start = b.seg_start; lp.seg_list = b.seg_list; lp.ctl = b.ctl; lp.xf = c.xf;
-    lp.redo = b.redo; lp.cap8 = LEAF8_CAP;
+    lp.list16 = b.list16; lp.spill = b.spill; lp.cap8 = LEAF8_CAP;
     {   // 8-bit bins: segments up to LEAF8_CAP keys without heavy duplicates
         static thread_local KernelSetup ks;
         int per_sm = 1;
-        auto kern = msd_leaf_kernel<8, LEAF_NT, IDENT>;
+        auto kern = msd_leaf_kernel<LEAF_NT, IDENT>;
         const size_t smem = (size_t)MSD_BINS;
         int32_t rc = setup_kernel(ks, kern, LEAF_NT, smem, &per_sm);
         if (rc != B200_OK) return rc;
@@ -204,11 +207,11 @@ static int32_t msd_launch(const SortCall &c, const MsdBuffers &b, uint32_t *alt,
     {   // 16-bit bins: what the 8-bit kernel skipped or gave up on
         static thread_local KernelSetup ks;
         int per_sm = 1;
-        auto kern = msd_leaf_kernel<16, LEAF_NT, IDENT>;
+        auto kern = msd_leaf16_kernel<LEAF16_NT, IDENT>;
         const size_t smem = (size_t)MSD_BINS * 2;
-        int32_t rc = setup_kernel(ks, kern, LEAF_NT, smem, &per_sm);
+        int32_t rc = setup_kernel(ks, kern, LEAF16_NT, smem, &per_sm);
         if (rc != B200_OK) return rc;
-        kern<<<(unsigned int)(dev.sm_count * per_sm), LEAF_NT, smem, st>>>(lp);
+        kern<<<(unsigned int)dev.sm_count, LEAF16_NT, smem, st>>>(lp);      // one spill table per CTA: grid == sm_count
         B200_CHECK_LAUNCH();
     }
     return B200_OK;
@@ -250,7 +253,7 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
     const bool hybrid_layout = msd_layout(c);
     const bool hybrid = msd_eligible(c);
 
-    // workspace: [ctl | ghist | (hybrid: hist16 | redo | status2) | status] — everything up to the part of `status`
+    // workspace: [ctl | ghist | (hybrid: hist16 | list16 | status2) | status] — everything up to the part of `status`
     // that the first kernels need is zeroed by ONE memset per call; when the hybrid path is attempted, the rest of
     // `status` (only the LSD fallback reads it) is zeroed by a kernel gated on the fallback
     Carver w(c.ws);
@@ -262,7 +265,7 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
     static_assert(sizeof(MsdCtl) <= 256, "control block");
     if (hybrid_layout) {
         mb.hist16 = w.take<unsigned int>(MSD_BINS);
-        mb.redo = w.take<unsigned int>(MSD_BINS);
+        mb.list16 = w.take<unsigned int>(MSD_BINS);
         mb.status2 = w.take<unsigned int>((size_t)(cdiv(n, MSD_TILE_MIN) + 256) * RX_RADIX);
     }
 #endif
@@ -284,6 +287,7 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
         mb.seg_start = w.take<unsigned int>(MSD_BINS + 1);
         mb.seg_list = w.take<unsigned int>(MSD_BINS);
         mb.l1_tile_start = w.take<unsigned int>(257);
+        mb.spill = w.take<unsigned int>((size_t)devinfo().sm_count * MSD_BINS);   // zeroed by the 16-bit leaf itself
     }
 #endif
     unsigned long long *bins = w.take<unsigned long long>(P * RX_RADIX);
@@ -419,28 +423,61 @@ int32_t B200_CAT(block_sort_k, B200_KEY_BYTES)(const BlockSortParams &bp, int pe
     return small ? launch_block_sort<false, 4>(bp, nseg, st) : launch_block_sort<false, RB_ITEMS>(bp, nseg, st);
 }
 
-// k-th smallest key of `keys` (0-based k) -> out[0]; workspace = SelectState + one 256-bin histogram per pass.
+// k-th smallest key of `keys` (0-based k) -> out[0]; workspace = SelectState + one 256-bin histogram per pass
+// (+ for large n: the sampled fast path's bracket, a second set of histograms and the candidate buffer of n / 8 keys).
+constexpr int64_t SELECT_FAST_MIN_N = 1LL << 22;
 int32_t B200_CAT(select_kth_k, B200_KEY_BYTES)(void *ws, size_t wsb, const void *keys, int64_t n, int64_t k,
                                                const SortXform &xf, void *out, cudaStream_t st, size_t *query) {
+    static const int fast_on = tune_int("B200_SELECT_FAST", 1);
+    const bool fastp = fast_on && n >= SELECT_FAST_MIN_N && sizeof(K) >= 2;
+    const unsigned long long cap = fastp ? (unsigned long long)(n / 8) : 0;
     Carver w(ws);
     SelectState *state = w.take<SelectState>(1);
     unsigned int *hist = w.take<unsigned int>(P * RX_RADIX);
+    SelectState *cstate = fastp ? w.take<SelectState>(1) : nullptr;
+    unsigned int *chist = fastp ? w.take<unsigned int>(P * RX_RADIX) : nullptr;
+    SelectFast *fast = fastp ? w.take<SelectFast>(1) : nullptr;
+    const size_t clear = w.bytes();
+    K *cand = fastp ? w.take<K>((size_t)cap) : nullptr;
     if (query) { *query = w.bytes(); return B200_OK; }
     if (w.bytes() > wsb) return B200_WORKSPACE_TOO_SMALL;
     if (ws == nullptr) return B200_INVALID_VALUE;
-    B200_CUDA_TRY(cudaMemsetAsync(ws, 0, w.bytes(), st));
+    B200_CUDA_TRY(cudaMemsetAsync(ws, 0, clear, st));
     const DevInfo &dev = devinfo();
     int64_t grid = (int64_t)dev.sm_count * 4;
     const int64_t need = cdiv(n, 512 * (16 / (int64_t)sizeof(K)));
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
+    if (fastp) {
+        select_sample_kernel<K><<<1, 1024, 0, st>>>(static_cast<const K *>(keys), n, (unsigned long long)k, xf, fast);
+        B200_CHECK_LAUNCH();
+        select_filter_kernel<K><<<(unsigned int)grid, 512, 0, st>>>(static_cast<const K *>(keys), n, xf, fast, cand, cap);
+        B200_CHECK_LAUNCH();
+        select_decide_kernel<<<1, 1, 0, st>>>(fast, cstate, (unsigned long long)k, cap);
+        B200_CHECK_LAUNCH();
+        // byte passes over the candidates (already in ordered-key space: identity transform; the count is on the device)
+        SortXform ident{};
+        ident.inf_bits = ~0ull;
+        int64_t cgrid = (int64_t)dev.sm_count * 2;
+        const int64_t cneed = cdiv((int64_t)cap, 512 * (16 / (int64_t)sizeof(K)));
+        if (cgrid > cneed) cgrid = cneed;
+        if (cgrid < 1) cgrid = 1;
+        for (int pass = 0; pass < P; ++pass) {
+            const int shift = 8 * (P - 1 - pass);
+            unsigned int *h = chist + pass * RX_RADIX;
+            select_hist_kernel<K><<<(unsigned int)cgrid, 512, 0, st>>>(cand, 0, ident, shift, cstate, h, fast, 1, true);
+            B200_CHECK_LAUNCH();
+            select_pick_kernel<K><<<1, RX_RADIX, 0, st>>>(h, cstate, shift, 0, 0ull, pass == P - 1, xf, static_cast<K *>(out), fast, 1);
+            B200_CHECK_LAUNCH();
+        }
+    }
     for (int pass = 0; pass < P; ++pass) {
         const int shift = 8 * (P - 1 - pass);
         unsigned int *h = hist + pass * RX_RADIX;
-        select_hist_kernel<K><<<(unsigned int)grid, 512, 0, st>>>(static_cast<const K *>(keys), n, xf, shift, state, h);
+        select_hist_kernel<K><<<(unsigned int)grid, 512, 0, st>>>(static_cast<const K *>(keys), n, xf, shift, state, h, fast, fastp ? 2 : 0, false);
         B200_CHECK_LAUNCH();
         select_pick_kernel<K><<<1, RX_RADIX, 0, st>>>(h, state, shift, pass == 0, (unsigned long long)k, pass == P - 1, xf,
-                                                      static_cast<K *>(out));
+                                                      static_cast<K *>(out), fast, fastp ? 2 : 0);
         B200_CHECK_LAUNCH();
     }
     return B200_OK;

@@ -25,6 +25,7 @@
 // Replaces (for this input class) CUDACore/src/sorting.jl:909-974 `bitonic_sort!`; keys keep Julia's `isless`
 // order through key_encode / key_decode exactly as in the LSD path.
 #pragma once
+#include <type_traits>
 #include "sort.cuh"
 
 namespace b200 {
@@ -190,48 +191,55 @@ struct MsdPlanParams {
     unsigned int *seg_start;        // [65537] exclusive scan, seg_start[65536] = n
     unsigned int *seg_list;         // [65536] ids of the non-empty segments, ascending
     unsigned int *l1_tile_start;    // [257] first level-2 tile of every level-1 bucket
+    unsigned int *list16;           // [65536] segments longer than cap8 (the 16-bit leaf's work list), ascending
     MsdCtl *ctl;
     unsigned int n;
     unsigned int tile2;             // keys per level-2 tile
-    unsigned int cap_a, cap_b;      // leaf capacities (cap_b == 0: no second leaf)
+    unsigned int cap8;              // longest segment the 8-bit leaf takes
+    unsigned int cap_a;             // longest segment admitted at all (one CTA sorts a segment: load balance)
     unsigned int min_avg;           // hybrid only when n / non-empty segments >= min_avg
 };
 
 static __global__ void __launch_bounds__(1024, 1) msd_plan_kernel(MsdPlanParams p) {
-    __shared__ unsigned int s_wsum[32], s_wne[32], s_wmax[32];
+    __shared__ unsigned int s_wsum[32], s_wne[32], s_wmax[32], s_wnb[32];
     __shared__ unsigned int s_excl[1024];
     __shared__ unsigned int s_t[256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint4 *h4 = reinterpret_cast<const uint4 *>(p.hist16) + tid * 16;   // 64 consecutive bins per thread
-    unsigned int sum = 0, ne = 0, mx = 0;
+    unsigned int sum = 0, ne = 0, mx = 0, nb = 0;
+    const unsigned int cap8 = p.cap8;
 #pragma unroll 4
     for (int k = 0; k < 16; ++k) {
         const uint4 v = h4[k];
         sum += v.x + v.y + v.z + v.w;
         ne += (v.x != 0) + (v.y != 0) + (v.z != 0) + (v.w != 0);
+        nb += (v.x > cap8) + (v.y > cap8) + (v.z > cap8) + (v.w > cap8);
         mx = max(max(mx, v.x), max(v.y, max(v.z, v.w)));
     }
-    unsigned int isum = sum, ine = ne, imx = mx;
+    unsigned int isum = sum, ine = ne, imx = mx, inb = nb;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const unsigned int a = __shfl_up_sync(0xffffffffu, isum, o);
         const unsigned int b = __shfl_up_sync(0xffffffffu, ine, o);
         const unsigned int c = __shfl_xor_sync(0xffffffffu, imx, o);
-        if (lane >= o) { isum += a; ine += b; }
+        const unsigned int d = __shfl_up_sync(0xffffffffu, inb, o);
+        if (lane >= o) { isum += a; ine += b; inb += d; }
         imx = max(imx, c);
     }
-    if (lane == 31) { s_wsum[warp] = isum; s_wne[warp] = ine; }
+    if (lane == 31) { s_wsum[warp] = isum; s_wne[warp] = ine; s_wnb[warp] = inb; }
     if (lane == 0) s_wmax[warp] = imx;
     __syncthreads();
-    unsigned int bsum = 0, bne = 0, tot_ne = 0, gmx = 0;
+    unsigned int bsum = 0, bne = 0, bnb = 0, tot_ne = 0, tot_nb = 0, gmx = 0;
 #pragma unroll
     for (int w = 0; w < 32; ++w) {
-        if (w < warp) { bsum += s_wsum[w]; bne += s_wne[w]; }
+        if (w < warp) { bsum += s_wsum[w]; bne += s_wne[w]; bnb += s_wnb[w]; }
         tot_ne += s_wne[w];
+        tot_nb += s_wnb[w];
         gmx = max(gmx, s_wmax[w]);
     }
     unsigned int run = bsum + isum - sum;       // exclusive prefix of this thread's first bin
     unsigned int idx = bne + ine - ne;
+    unsigned int idx16 = bnb + inb - nb;
     s_excl[tid] = run;
     uint4 *o4 = reinterpret_cast<uint4 *>(p.seg_start) + tid * 16;
     const unsigned int bin0 = (unsigned int)tid * 64;
@@ -239,10 +247,10 @@ static __global__ void __launch_bounds__(1024, 1) msd_plan_kernel(MsdPlanParams 
     for (int k = 0; k < 16; ++k) {
         const uint4 v = h4[k];
         uint4 o;
-        o.x = run; if (v.x) p.seg_list[idx++] = bin0 + k * 4 + 0; run += v.x;
-        o.y = run; if (v.y) p.seg_list[idx++] = bin0 + k * 4 + 1; run += v.y;
-        o.z = run; if (v.z) p.seg_list[idx++] = bin0 + k * 4 + 2; run += v.z;
-        o.w = run; if (v.w) p.seg_list[idx++] = bin0 + k * 4 + 3; run += v.w;
+        o.x = run; if (v.x) p.seg_list[idx++] = bin0 + k * 4 + 0; if (v.x > cap8) p.list16[idx16++] = bin0 + k * 4 + 0; run += v.x;
+        o.y = run; if (v.y) p.seg_list[idx++] = bin0 + k * 4 + 1; if (v.y > cap8) p.list16[idx16++] = bin0 + k * 4 + 1; run += v.y;
+        o.z = run; if (v.z) p.seg_list[idx++] = bin0 + k * 4 + 2; if (v.z > cap8) p.list16[idx16++] = bin0 + k * 4 + 2; run += v.z;
+        o.w = run; if (v.w) p.seg_list[idx++] = bin0 + k * 4 + 3; if (v.w > cap8) p.list16[idx16++] = bin0 + k * 4 + 3; run += v.w;
         o4[k] = o;
     }
     if (tid == 1023) p.seg_start[MSD_BINS] = run;
@@ -272,11 +280,10 @@ static __global__ void __launch_bounds__(1024, 1) msd_plan_kernel(MsdPlanParams 
         }
     }
     if (tid == 0) {
-        unsigned int mode = 0;
-        if (gmx <= p.cap_a) mode = 1;
-        else if (p.cap_b && gmx <= p.cap_b) mode = 2;
+        unsigned int mode = gmx <= p.cap_a ? 1u : 0u;
         if (tot_ne == 0 || (unsigned long long)p.n < (unsigned long long)p.min_avg * tot_ne) mode = 0;
         p.ctl->nne = tot_ne;
+        p.ctl->n16 = tot_nb;             // the 8-bit leaf appends the segments it gives up on
         p.ctl->max_seg = gmx;
         p.ctl->mode = mode;
     }
@@ -322,6 +329,8 @@ __global__ void __launch_bounds__(NT, (NT == 512 && ITEMS <= 16) ? 3 : 1024 / NT
     __shared__ unsigned int s_seg[2][4];                     // {bucket, first tile, first key, end key} of a ticket
     __shared__ unsigned int s_l1ts[LEVEL == 2 ? 257 : 1];    // first tile of every level-1 bucket (loaded once)
     __shared__ unsigned int s_l1lo[LEVEL == 2 ? 257 : 1];    // first key of every level-1 bucket
+    __shared__ unsigned int s_hv[2][4];                      // heavy digits of the chain a ticket belongs to (see `detect`)
+    __shared__ unsigned int s_nh[2];
 
     if (ld_cg_u32(&p.ctl->mode) == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -364,9 +373,20 @@ __global__ void __launch_bounds__(NT, (NT == 512 && ITEMS <= 16) ? 3 : 1024 / NT
         }
     };
 
+    // Skewed digits (Float32 keys: half of uniform [0, 1) floats share ONE top byte): 16 lanes of a warp adding to
+    // one shared counter serialise.  A digit that holds at least 1/8 of its chain's keys is "heavy": its keys are ranked
+    // by ballot + ONE atomic of the leading lane (at most 4 heavy digits get this treatment; the digit threads find
+    // them from the bucket's exact counts, an iteration before the tile is ranked).
+    auto detect = [&](int slot, unsigned int my_cnt, unsigned int total) {
+        if (total >= 4u * (unsigned int)TILE && my_cnt >= (total >> 3)) {
+            const unsigned int k = atomicAdd(&s_nh[slot], 1u);
+            if (k < 4) s_hv[slot][k] = (unsigned int)tid;
+        }
+    };
+
     // ---- prologue: tables, first ticket, first tile's loads
     unsigned int next_t = 0;                       // thread 0: ticket after the current one, requested a tile early
-    if (tid == 0) s_tk[0] = atomicAdd(ticket, 1u);
+    if (tid == 0) { s_tk[0] = atomicAdd(ticket, 1u); s_nh[0] = 0; s_nh[1] = 0; }
     if constexpr (LEVEL == 2) {
         for (int i = tid; i < 257; i += NT) {
             s_l1ts[i] = p.l1_tile_start[i];
@@ -381,6 +401,11 @@ __global__ void __launch_bounds__(NT, (NT == 512 && ITEMS <= 16) ? 3 : 1024 / NT
     if constexpr (LEVEL == 2) __syncthreads();
     MsdTile cur = describe(s_tk[0], 0);
     load_tile(cur);
+    if (dthread) {
+        if constexpr (LEVEL == 1) detect(0, p.seg_start[(tid + 1) * 256] - p.seg_start[tid * 256], p.n);
+        else detect(0, p.seg_start[cur.seg * 256 + tid + 1] - p.seg_start[cur.seg * 256 + tid], s_seg[0][3] - s_seg[0][2]);
+    }
+    __syncthreads();
 
     for (unsigned int it = 0;; ++it) {
         const bool full = cur.valid == TILE;
@@ -419,6 +444,46 @@ __global__ void __launch_bounds__(NT, (NT == 512 && ITEMS <= 16) ? 3 : 1024 / NT
                 }
                 ranks.set(i, r);
             }
+        } else if (full && s_nh[LEVEL == 1 ? 0 : (it & 1)] != 0) {
+            // heavy digits: no atomic and no ballot per key.  Pass 1: every lane counts its own keys of each heavy digit;
+            // one warp scan + ONE atomic per heavy digit reserve a block of ranks per lane; pass 2 hands a lane's ranks
+            // out in item order (equal keys are indistinguishable, any unique rank will do).  The other digits keep
+            // their per-key atomics.
+            const int hslot = LEVEL == 1 ? 0 : (int)(it & 1);
+            auto heavy_rank = [&](auto nh_tag) {
+                constexpr int NH = decltype(nh_tag)::value;
+                unsigned int hv[NH], nxt_rank[NH];
+#pragma unroll
+                for (int h = 0; h < NH; ++h) { hv[h] = s_hv[hslot][h]; nxt_rank[h] = 0; }
+#pragma unroll
+                for (int i = 0; i < ITEMS; ++i) {
+                    const unsigned int d = (keys[i] >> SHIFT) & 0xFFu;
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) nxt_rank[h] += (d == hv[h]) ? 1u : 0u;
+                }
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    const unsigned int incl = warp_incl_scan(nxt_rank[h]);
+                    unsigned int b = 0;
+                    if (lane == 31 && incl) b = atomicAdd(&s_hist[hv[h]], incl);
+                    nxt_rank[h] = __shfl_sync(0xffffffffu, b, 31) + incl - nxt_rank[h];
+                }
+#pragma unroll
+                for (int i = 0; i < ITEMS; ++i) {
+                    const unsigned int d = (keys[i] >> SHIFT) & 0xFFu;
+                    unsigned int r = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int h = 0; h < NH; ++h)
+                        if (d == hv[h]) { r = nxt_rank[h]; nxt_rank[h] += 1u; }
+                    if (r == 0xFFFFFFFFu) r = atomicAdd(&s_hist[d], 1u);
+                    ranks.set(i, r);
+                }
+            };
+            const unsigned int nh = s_nh[hslot];                   // uniform over the CTA
+            if (nh == 1) heavy_rank(std::integral_constant<int, 1>{});
+            else if (nh == 2) heavy_rank(std::integral_constant<int, 2>{});
+            else if (nh == 3) heavy_rank(std::integral_constant<int, 3>{});
+            else heavy_rank(std::integral_constant<int, 4>{});
         } else if (full) {
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) ranks.set(i, atomicAdd(&s_hist[(keys[i] >> SHIFT) & 0xFFu], 1u));
@@ -439,7 +504,10 @@ __global__ void __launch_bounds__(NT, (NT == 512 && ITEMS <= 16) ? 3 : 1024 / NT
             s_hist[tid] = 0;                       // ready for the next tile's ranking (two barriers away)
             st_relaxed<uint32_t>(p.status + (size_t)cur.t * 256 + tid, (chain_head ? LB::INCLUSIVE : LB::PARTIAL) | cnt);
         }
-        if (tid == 0) s_tk[(it + 1) & 1] = next_t;  // the ticket requested during the previous tile has long arrived
+        if (tid == 0) {
+            s_tk[(it + 1) & 1] = next_t;          // the ticket requested during the previous tile has long arrived
+            if constexpr (LEVEL == 2) s_nh[(it + 1) & 1] = 0;     // last read before barrier (A); next written after (C)
+        }
         unsigned int incl = cnt;
         if (warp < 8) {
 #pragma unroll
@@ -490,6 +558,17 @@ __global__ void __launch_bounds__(NT, (NT == 512 && ITEMS <= 16) ? 3 : 1024 / NT
             if (tid == 0) next_t = atomicAdd(ticket, 1u);
             nxt = describe(tn, (it + 1) & 1);
             load_tile(nxt);
+            if constexpr (LEVEL == 2) {
+                if (nxt.seg != cur.seg) {                 // a new chain: its heavy digits
+                    if (dthread) {
+                        const unsigned int a = p.seg_start[nxt.seg * 256 + tid], b = p.seg_start[nxt.seg * 256 + tid + 1];
+                        detect((int)((it + 1) & 1), b - a, s_seg[(it + 1) & 1][3] - s_seg[(it + 1) & 1][2]);
+                    }
+                } else if (tid < 5) {                     // same chain: the list carries over
+                    if (tid < 4) s_hv[(it + 1) & 1][tid] = s_hv[it & 1][tid];
+                    else s_nh[(it + 1) & 1] = s_nh[it & 1];
+                }
+            }
         }
 
         // ---- decoupled look-back over this chain's earlier tiles
@@ -565,44 +644,43 @@ __global__ void __launch_bounds__(NT, (NT == 512 && ITEMS <= 16) ? 3 : 1024 / NT
 // All keys of a segment share their top 16 bits, and equal keys are indistinguishable: the sorted segment is fully
 // described by the HISTOGRAM of the low 16 bits.  With dense keys (2^30 keys over a 32-bit range: 4 bins per key) the
 // cheapest sort is therefore: count (one shared atomic per key into a packed 65536-bin table), then walk the table in
-// order and emit every value `count` times.  Per 32 keys: ~60 instructions and ~7 shared-memory wavefronts, against
-// ~106 / 44 for the group-wise counting sort this replaces (profiles/r2_sort_msd_v2.md).
+// order and emit every value `count` times.
 //
-//   BITS = 8 : four bins per word, 64 KB table, 3 CTAs per SM; a bin that reaches 128 marks the segment in `redo`
-//              (heavy duplicates) and the 16-bit kernel takes it.  Segments longer than CAP8 are skipped (also 16-bit).
-//   BITS = 16: two bins per word, 128 KB table, 1 CTA per SM; cannot overflow (the plan kernel admits the hybrid path
-//              only when every segment has at most 65535 keys).  Takes the segments the 8-bit kernel left.
+//   msd_leaf_kernel   : 8-bit bins, four per word, 64 KB table, 3 CTAs per SM; segments up to `cap8` keys, dealt
+//                       round-robin.  A bin that reaches 256 copies is detected by the table's byte sum and the segment
+//                       is appended to `list16`.
+//   msd_leaf16_kernel : 16-bit bins, two per word, 128 KB table, 1 CTA per SM; takes `list16` — the segments longer than
+//                       `cap8` (listed by the plan kernel) and the ones the 8-bit kernel gave up on — ONE SEGMENT PER
+//                       TICKET, whatever its length (Float32 keys: the 128 segments of [0.5, 1) hold 2^22 keys each).
+//                       Values with 32768 copies or more spill into a per-CTA table in global memory.
 struct MsdLeafParams {
     uint32_t *keys;                   // encoded keys grouped by their top 16 bits; sorted + decoded in place
     const unsigned int *seg_start;    // [65537]
     const unsigned int *seg_list;     // non-empty segment ids
-    unsigned int *redo;               // [65536] per list slot: 1 = the 8-bit kernel gave up on it (zeroed by the memset)
+    unsigned int *list16;             // [65536] segment ids for the 16-bit kernel; ctl->n16 entries
+    unsigned int *spill;              // [grid of the 16-bit kernel][65536] all zero between segments
     MsdCtl *ctl;
     SortXform xf;
     unsigned int cap8;                // longest segment the 8-bit kernel takes
 };
 
 constexpr int MSD_LEAF_CHUNK = 8;      // global loads in flight per thread in the count phase
-constexpr unsigned int MSD_LEAF_HEAVY = 1024;   // 16-bit kernel: values with at least this many copies are written by the whole CTA
+constexpr unsigned int MSD_LEAF_HEAVY = 1024;   // 16-bit kernel: values with at least this many copies (and 1/64 of the segment) are written by the whole CTA
 
-template <int BITS, int NT, bool IDENT>
-__global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLeafParams p) {
-    constexpr int PER_WORD = 32 / BITS;               // bins per 32-bit word
-    constexpr int WORDS = MSD_BINS / PER_WORD;        // 16384 (8-bit) / 32768 (16-bit)
+template <int NT, bool IDENT>
+__global__ void __launch_bounds__(NT, 3) msd_leaf_kernel(MsdLeafParams p) {
+    constexpr int PER_WORD = 4;                       // bins per 32-bit word
+    constexpr int WORDS = MSD_BINS / PER_WORD;        // 16384
     constexpr int NW = NT / 32;
     constexpr int WORDS_PER_WARP = WORDS / NW;        // contiguous slice of the table walked by one warp
     constexpr int CH = MSD_LEAF_CHUNK;
     extern __shared__ __align__(16) unsigned int s_bins[];   // [WORDS] packed counters, all zero between segments
     __shared__ unsigned int s_wtot[NW];
-    __shared__ unsigned int s_nheavy;
-    __shared__ uint4 s_heavy[BITS == 16 ? 65536 / MSD_LEAF_HEAVY + 1 : 1];   // {value, first position, copies}
 
     if (ld_cg_u32(&p.ctl->mode) == 0) return;
-    if (BITS == 16 && ld_cg_u32(&p.ctl->pad) == 0) return;               // the 8-bit kernel finished every segment
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int nne = ld_cg_u32(&p.ctl->nne);
     for (int i = tid; i < WORDS / 4; i += NT) reinterpret_cast<uint4 *>(s_bins)[i] = make_uint4(0, 0, 0, 0);
-    if (tid == 0) s_nheavy = 0;
 
     // Segments are dealt round-robin to the persistent CTAs (independent work: no ticket).  Bounds of the next segment
     // and the id of the one after are loaded an iteration early; every thread loads the same words (broadcast).
@@ -621,52 +699,23 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
         if (k + G < nne) { nlo = __ldg(p.seg_start + seg_n1); nhi = __ldg(p.seg_start + seg_n1 + 1); }
         if (k + 2 * G < nne) seg_n2 = __ldg(p.seg_list + k + 2 * G);
         const int m = (int)(hi - lo);
-        bool mine;
-        if constexpr (BITS == 8) {
-            mine = m <= (int)p.cap8;
-            if (!mine && tid == 0) atomicAdd(&p.ctl->pad, 1u);            // ctl->pad counts the segments left to the 16-bit kernel
-        } else {
-            mine = m > (int)p.cap8 || ld_cg_u32(p.redo + k) != 0;
-        }
-        if (mine) {                                          // uniform over the CTA
+        if (m <= (int)p.cap8) {                              // uniform over the CTA (longer ones: the plan kernel listed them)
             uint32_t *base = p.keys + lo;
             // ---- count: one shared atomic per key.  Loads go out CH at a time (a load -> atomic -> load chain would
-            // expose one memory round trip per key).
-            // 8-bit bins: the add needs no return value and no per-key overflow test — a field that wraps loses 255 (carry
-            // into the next field) or 256 (carry out of the word) from the table's byte sum, so "sum of all bins != m"
-            // after the count detects every overflow (fields hold up to 255 copies).
+            // expose one memory round trip per key).  The add needs no return value and no per-key overflow test — a
+            // field that wraps loses 255 (carry into the next field) or 256 (carry out of the word) from the table's byte
+            // sum, so "sum of all bins != m" after the count detects every overflow (fields hold up to 255 copies).
             auto count_one = [&](uint32_t key) {
-                if constexpr (BITS == 8) {
-                    const unsigned int inc = __funnelshift_l(0u, 1u, key << 3);              // 1 << 8 * (key & 3)
-                    atomicAdd(reinterpret_cast<unsigned int *>(reinterpret_cast<unsigned char *>(s_bins) + (key & 0xFFFCu)), inc);
-                } else {
-                    atomicAdd(&s_bins[(key & 0xFFFFu) >> 1], (key & 1u) ? 0x10000u : 1u);
-                }
+                const unsigned int inc = __funnelshift_l(0u, 1u, key << 3);              // 1 << 8 * (key & 3)
+                atomicAdd(reinterpret_cast<unsigned int *>(reinterpret_cast<unsigned char *>(s_bins) + (key & 0xFFFCu)), inc);
             };
             for (int i0 = 0; i0 < m; i0 += CH * NT) {
                 uint32_t kk[CH];
                 if (i0 + CH * NT <= m) {
 #pragma unroll
                     for (int c = 0; c < CH; ++c) kk[c] = ld_coh(base + i0 + c * NT + tid);
-                    // heavy duplicates (the 16-bit kernel's reason to exist): a row of 32 equal keys is counted by
-                    // lane 0 alone instead of 32 serialised atomics on one word; row 0 is the probe
-                    bool dup_rows = false;
-                    if constexpr (BITS == 16) dup_rows = __all_sync(0xffffffffu, kk[0] == __shfl_sync(0xffffffffu, kk[0], 0));
-                    if (dup_rows) {
 #pragma unroll
-                        for (int c = 0; c < CH; ++c) {
-                            const unsigned int v = kk[c] & 0xFFFFu;
-                            const unsigned int sh = (v % PER_WORD) * BITS;
-                            if (__all_sync(0xffffffffu, kk[c] == __shfl_sync(0xffffffffu, kk[c], 0))) {
-                                if (lane == 0) atomicAdd(&s_bins[v / PER_WORD], 32u << sh);
-                            } else {
-                                atomicAdd(&s_bins[v / PER_WORD], 1u << sh);
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < CH; ++c) count_one(kk[c]);
-                    }
+                    for (int c = 0; c < CH; ++c) count_one(kk[c]);
                 } else {
 #pragma unroll
                     for (int c = 0; c < CH; ++c) {
@@ -680,14 +729,11 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
             }
             __syncthreads();
             // ---- warp totals: warp w owns table words [w * WORDS_PER_WARP, (w + 1) * WORDS_PER_WARP)
-            const unsigned int *wb = s_bins + warp * WORDS_PER_WARP;
             {
+                const unsigned int *wb = s_bins + warp * WORDS_PER_WARP;
                 unsigned int acc = 0;
 #pragma unroll 8
-                for (int j = lane; j < WORDS_PER_WARP; j += 32) {
-                    const unsigned int w = wb[j];
-                    acc += BITS == 8 ? __dp4a(w, 0x01010101u, 0u) : (w & 0xFFFFu) + (w >> 16);
-                }
+                for (int j = lane; j < WORDS_PER_WARP; j += 32) acc += __dp4a(wb[j], 0x01010101u, 0u);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                 if (lane == 0) s_wtot[warp] = acc;
@@ -700,115 +746,272 @@ __global__ void __launch_bounds__(NT, (BITS == 8 ? 3 : 1)) msd_leaf_kernel(MsdLe
                 run += (w < warp) ? t : 0u;
                 total += t;
             }
-            const bool over = BITS == 8 && total != (unsigned int)m;      // uniform: some 8-bit field wrapped
-            if (over) {
+            if (total != (unsigned int)m) {                               // uniform: some 8-bit field wrapped
                 // a value occurs 256 times or more: hand the segment to the 16-bit kernel and clear the table
                 __syncthreads();                                          // every thread has read s_wtot / the table
                 for (int i = tid; i < WORDS / 4; i += NT) reinterpret_cast<uint4 *>(s_bins)[i] = make_uint4(0, 0, 0, 0);
-                if (tid == 0) { p.redo[k] = 1u; atomicAdd(&p.ctl->pad, 1u); }
+                if (tid == 0) p.list16[atomicAdd(&p.ctl->n16, 1u)] = seg;
             } else {
-                // ---- expand: walk the table in value order; 32 words (32 * PER_WORD values) per step and warp.
-                // A lane emits its word's values `count` times each at consecutive positions, lanes back to back.
+                // ---- expand: walk the table in value order; 2 x 32 words (256 values) per step and warp.
+                // A lane writes its word's values at consecutive positions, lanes back to back.  Counts are nearly always
+                // 0 or 1: first and second copies are straight-line predicated stores at precomputed addresses (98 % of the
+                // non-empty bins hold one key, 2.4 % two); a bin with three or more copies anywhere in the word takes a loop.
                 const uint32_t hi16 = seg << 16;                          // the segment id IS the keys' top 16 bits
                 unsigned int *wbw = s_bins + warp * WORDS_PER_WARP;
                 uint32_t *const kall = p.keys;                            // 32-bit element index + kernel parameter: one IMAD.WIDE per address
-                // A lane writes its word's values at consecutive positions, lanes back to back.  Counts are nearly always
-                // 0 or 1: the first copy of each field is one predicated store at a precomputed offset; further copies
-                // (10 % of the words) share ONE short loop over the copy number instead of a loop per field.
                 auto emit = [&](unsigned int w, unsigned int pos, uint32_t v0) {
                     const unsigned int g0 = lo + pos;                     // element index into the whole key array (< 2^30)
-                    if constexpr (BITS == 8) {
-                        const unsigned int c0 = w & 0xFFu, c1 = (w >> 8) & 0xFFu, c2 = (w >> 16) & 0xFFu, c3 = w >> 24;
-                        const unsigned int o1 = c0, o2 = o1 + c1, o3 = o2 + c2;
-                        const uint32_t k0 = IDENT ? v0 : key_decode<uint32_t>(v0, p.xf);
-                        const uint32_t k1 = IDENT ? v0 + 1 : key_decode<uint32_t>(v0 + 1, p.xf);
-                        const uint32_t k2 = IDENT ? v0 + 2 : key_decode<uint32_t>(v0 + 2, p.xf);
-                        const uint32_t k3 = IDENT ? v0 + 3 : key_decode<uint32_t>(v0 + 3, p.xf);
-                        // first and second copies: straight-line predicated stores (98 % of the non-empty bins hold one key,
-                        // 2.4 % two); a bin with three or more copies anywhere in the word takes the loop below
-                        uint32_t *out = kall + g0, *a1 = kall + (g0 + o1), *a2 = kall + (g0 + o2), *a3 = kall + (g0 + o3);
-                        st_if_gt<0, 0>(out, k0, c0);
-                        st_if_gt<0, 0>(a1, k1, c1);
-                        st_if_gt<0, 0>(a2, k2, c2);
-                        st_if_gt<0, 0>(a3, k3, c3);
-                        st_if_gt<1, 1>(out, k0, c0);
-                        st_if_gt<1, 1>(a1, k1, c1);
-                        st_if_gt<1, 1>(a2, k2, c2);
-                        st_if_gt<1, 1>(a3, k3, c3);
-                        if ((w & 0xFCFCFCFCu) | (w & (w >> 1) & 0x01010101u)) {       // some count >= 3
-                            const unsigned int mx = max(max(c0, c1), max(c2, c3));
+                    const unsigned int c0 = w & 0xFFu, c1 = (w >> 8) & 0xFFu, c2 = (w >> 16) & 0xFFu, c3 = w >> 24;
+                    const unsigned int o1 = c0, o2 = o1 + c1, o3 = o2 + c2;
+                    const uint32_t k0 = IDENT ? v0 : key_decode<uint32_t>(v0, p.xf);
+                    const uint32_t k1 = IDENT ? v0 + 1 : key_decode<uint32_t>(v0 + 1, p.xf);
+                    const uint32_t k2 = IDENT ? v0 + 2 : key_decode<uint32_t>(v0 + 2, p.xf);
+                    const uint32_t k3 = IDENT ? v0 + 3 : key_decode<uint32_t>(v0 + 3, p.xf);
+                    uint32_t *out = kall + g0, *a1 = kall + (g0 + o1), *a2 = kall + (g0 + o2), *a3 = kall + (g0 + o3);
+                    st_if_gt<0, 0>(out, k0, c0);
+                    st_if_gt<0, 0>(a1, k1, c1);
+                    st_if_gt<0, 0>(a2, k2, c2);
+                    st_if_gt<0, 0>(a3, k3, c3);
+                    st_if_gt<1, 1>(out, k0, c0);
+                    st_if_gt<1, 1>(a1, k1, c1);
+                    st_if_gt<1, 1>(a2, k2, c2);
+                    st_if_gt<1, 1>(a3, k3, c3);
+                    if ((w & 0xFCFCFCFCu) | (w & (w >> 1) & 0x01010101u)) {       // some count >= 3
+                        const unsigned int mx = max(max(c0, c1), max(c2, c3));
 #pragma unroll 1
-                            for (unsigned int kk = 2; kk < mx; ++kk) {
-                                if (c0 > kk) out[kk] = k0;
-                                if (c1 > kk) a1[kk] = k1;
-                                if (c2 > kk) a2[kk] = k2;
-                                if (c3 > kk) a3[kk] = k3;
-                            }
-                        }
-                    } else {
-                        uint32_t *out = kall + g0;
-                        const unsigned int c0 = w & 0xFFFFu, c1 = w >> 16;
-                        const uint32_t k0 = IDENT ? v0 : key_decode<uint32_t>(v0, p.xf);
-                        const uint32_t k1 = IDENT ? v0 + 1 : key_decode<uint32_t>(v0 + 1, p.xf);
-                        // thousands of copies of one value: written by the whole CTA after the walk
-                        if (c0 >= MSD_LEAF_HEAVY) s_heavy[atomicAdd(&s_nheavy, 1u)] = make_uint4(k0, pos, c0, 0u);
-                        else {
-#pragma unroll 1
-                            for (unsigned int kk = 0; kk < c0; ++kk) out[kk] = k0;
-                        }
-                        if (c1 >= MSD_LEAF_HEAVY) s_heavy[atomicAdd(&s_nheavy, 1u)] = make_uint4(k1, pos + c0, c1, 0u);
-                        else {
-#pragma unroll 1
-                            for (unsigned int kk = 0; kk < c1; ++kk) out[c0 + kk] = k1;
+                        for (unsigned int kk = 2; kk < mx; ++kk) {
+                            if (c0 > kk) out[kk] = k0;
+                            if (c1 > kk) a1[kk] = k1;
+                            if (c2 > kk) a2[kk] = k2;
+                            if (c3 > kk) a3[kk] = k3;
                         }
                     }
                 };
-                if constexpr (BITS == 8) {
-                    // two table rows (2 x 32 words) per step: their word counts share ONE warp scan (16-bit halves;
-                    // a row holds at most 32 * 4 * 128 keys)
-                    for (int j = lane; j < WORDS_PER_WARP; j += 64) {
-                        const unsigned int wA = wbw[j], wB = wbw[j + 32];
-                        wbw[j] = 0; wbw[j + 32] = 0;                      // table is clean again for the next segment
-                        const unsigned int cA = __dp4a(wA, 0x01010101u, 0u), cB = __dp4a(wB, 0x01010101u, 0u);
-                        const unsigned int incl = warp_incl_scan(cA | (cB << 16));
-                        const unsigned int tot = __shfl_sync(0xffffffffu, incl, 31);
-                        const unsigned int totA = tot & 0xFFFFu, totB = tot >> 16;
-                        const uint32_t v0 = hi16 | (uint32_t)((warp * WORDS_PER_WARP + j) * PER_WORD);
-                        // no `if (w)` around the calls: an empty word's stores are all predicated off
-                        emit(wA, run + (incl & 0xFFFFu) - cA, v0);
-                        emit(wB, run + totA + (incl >> 16) - cB, v0 + 32 * PER_WORD);
-                        run += totA + totB;
-                    }
-                } else {
-                    for (int j = lane; j < WORDS_PER_WARP; j += 32) {
-                        const unsigned int w = wbw[j];
-                        wbw[j] = 0;
-                        const unsigned int cnt = (w & 0xFFFFu) + (w >> 16);
-                        unsigned int incl = cnt;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
-                            if (lane >= o) incl += up;
-                        }
-                        const unsigned int tot = __shfl_sync(0xffffffffu, incl, 31);
-                        if (w) emit(w, run + incl - cnt, hi16 | (uint32_t)((warp * WORDS_PER_WARP + j) * PER_WORD));
-                        run += tot;
-                    }
-                }
-                if constexpr (BITS == 16) {
-                    __syncthreads();
-                    const unsigned int nh = s_nheavy;
-                    for (unsigned int e = 0; e < nh; ++e) {
-                        const uint4 h = s_heavy[e];
-                        for (unsigned int i = tid; i < h.z; i += NT) base[h.y + i] = h.x;
-                    }
-                    __syncthreads();
-                    if (tid == 0) s_nheavy = 0;
+                // two table rows (2 x 32 words) per step: their word counts share ONE warp scan (16-bit halves;
+                // a row holds at most 32 * 4 * 255 keys)
+                for (int j = lane; j < WORDS_PER_WARP; j += 64) {
+                    const unsigned int wA = wbw[j], wB = wbw[j + 32];
+                    wbw[j] = 0; wbw[j + 32] = 0;                      // table is clean again for the next segment
+                    const unsigned int cA = __dp4a(wA, 0x01010101u, 0u), cB = __dp4a(wB, 0x01010101u, 0u);
+                    const unsigned int incl = warp_incl_scan(cA | (cB << 16));
+                    const unsigned int tot = __shfl_sync(0xffffffffu, incl, 31);
+                    const unsigned int totA = tot & 0xFFFFu, totB = tot >> 16;
+                    const uint32_t v0 = hi16 | (uint32_t)((warp * WORDS_PER_WARP + j) * PER_WORD);
+                    // no `if (w)` around the calls: an empty word's stores are all predicated off
+                    emit(wA, run + (incl & 0xFFFFu) - cA, v0);
+                    emit(wB, run + totA + (incl >> 16) - cB, v0 + 32 * PER_WORD);
+                    run += totA + totB;
                 }
             }
-            __syncthreads();        // table clean / redo written before the next segment's atomics
+            __syncthreads();        // table clean / list16 written before the next segment's atomics
         }
         lo = nlo; hi = nhi; seg = seg_n1; seg_n1 = seg_n2;
+    }
+}
+
+// 16-bit bins.  One ticket = one entry of list16 = one whole segment of any length (a CTA's count loop walks it).
+template <int NT, bool IDENT>
+__global__ void __launch_bounds__(NT, 1) msd_leaf16_kernel(MsdLeafParams p) {
+    constexpr int WORDS = MSD_BINS / 2;               // 32768 words, two 16-bit bins each
+    constexpr int NW = NT / 32;
+    constexpr int WORDS_PER_WARP = WORDS / NW;
+    constexpr int CH = 16;                            // one CTA per SM: more loads in flight per thread
+    constexpr int MAXH = 64;                          // heavy values per segment (each holds >= 1/64 of it)
+    extern __shared__ __align__(16) unsigned int s_bins[];   // [WORDS] packed counters, all zero between segments
+    __shared__ unsigned int s_wtot[NW];
+    __shared__ unsigned int s_nheavy, s_spilled;
+    __shared__ unsigned int s_tk[2];
+    __shared__ uint4 s_heavy[MAXH + 1];               // {value, first position, copies}
+
+    if (ld_cg_u32(&p.ctl->mode) == 0) return;
+    const unsigned int n16 = ld_cg_u32(&p.ctl->n16);  // final: the 8-bit kernel has finished (stream order)
+    if (n16 == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < WORDS / 4; i += NT) reinterpret_cast<uint4 *>(s_bins)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { s_nheavy = 0; s_spilled = 0; s_tk[0] = atomicAdd(&p.ctl->ticket_leaf, 1u); }
+    unsigned int *const spill = p.spill + (size_t)blockIdx.x * MSD_BINS;
+    for (int i = tid; i < MSD_BINS / 4; i += NT) reinterpret_cast<uint4 *>(spill)[i] = make_uint4(0, 0, 0, 0);   // workspace is uninitialised
+    uint32_t *const kall = p.keys;
+    __threadfence();
+    __syncthreads();
+    unsigned int next_t = 0;
+    if (tid == 0 && s_tk[0] < n16) next_t = atomicAdd(&p.ctl->ticket_leaf, 1u);
+
+    for (unsigned int it = 0;; ++it) {
+        const unsigned int t = s_tk[it & 1];
+        if (t >= n16) break;
+        const unsigned int seg = ld_cg_u32(p.list16 + t);
+        const unsigned int lo = __ldg(p.seg_start + seg), hi = __ldg(p.seg_start + seg + 1);
+        const unsigned int m = hi - lo;
+        const uint32_t *base = p.keys + lo;
+        // ---- count.  Optimistic first: plain adds without return value; a 16-bit field that wraps loses 65535 or 65536
+        // from the table's sum, so "sum != m" detects it and the segment is counted again carefully: the thread whose
+        // add takes a field across 0x8000 moves 0x8000 counts to the CTA's spill table in global memory (exactly one
+        // thread sees the crossing; the counts in flight are bounded by max(1024 threads x 16 loads, 32 warps
+        // x 16 rows x 32) = 16384 < 0x8000, so a field never reaches 0x10000).  Rows of 32 equal keys are counted by lane 0 alone
+        // (heavy duplicates would serialise 32 atomics on one word); row 0 is the probe.
+        auto count_all = [&](auto careful_tag) {
+            constexpr bool CAREFUL = decltype(careful_tag)::value;
+            auto add = [&](uint32_t key, unsigned int inc) {
+                const unsigned int sh = (key & 1u) << 4;
+                unsigned int *word = &s_bins[(key & 0xFFFFu) >> 1];
+                if constexpr (!CAREFUL) {
+                    atomicAdd(word, inc << sh);
+                } else {
+                    const unsigned int old = (atomicAdd(word, inc << sh) >> sh) & 0xFFFFu;
+                    if (old < 0x8000u && old + inc >= 0x8000u) {
+                        atomicSub(word, 0x8000u << sh);
+                        atomicAdd(spill + (key & 0xFFFFu), 0x8000u);
+                        s_spilled = 1u;
+                    }
+                }
+            };
+            for (unsigned int i0 = 0; i0 < m; i0 += CH * NT) {
+                uint32_t kk[CH];
+                if (i0 + CH * NT <= m) {
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) kk[c] = ld_coh(base + i0 + c * NT + tid);
+                    const bool dup_rows = __all_sync(0xffffffffu, kk[0] == __shfl_sync(0xffffffffu, kk[0], 0));
+                    if (dup_rows) {
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) {
+                            if (__all_sync(0xffffffffu, kk[c] == __shfl_sync(0xffffffffu, kk[c], 0))) {
+                                if (lane == 0) add(kk[c], 32u);
+                            } else {
+                                add(kk[c], 1u);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) add(kk[c], 1u);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) {
+                        const unsigned int i = i0 + c * NT + tid;
+                        kk[c] = i < m ? ld_coh(base + i) : 0u;
+                    }
+#pragma unroll
+                    for (int c = 0; c < CH; ++c)
+                        if (i0 + c * NT + tid < m) add(kk[c], 1u);
+                }
+            }
+        };
+        unsigned int *wbw = s_bins + warp * WORDS_PER_WARP;
+        // warp totals: warp w owns table words [w * WORDS_PER_WARP, (w + 1) * WORDS_PER_WARP)
+        auto warp_totals = [&](bool spilled) {
+            unsigned int acc = 0;
+            for (int j = lane; j < WORDS_PER_WARP; j += 32) {
+                const unsigned int w = wbw[j];
+                acc += (w & 0xFFFFu) + (w >> 16);
+                if (spilled) {
+                    const uint2 sp = __ldcg(reinterpret_cast<const uint2 *>(spill + 2 * (warp * WORDS_PER_WARP + j)));
+                    acc += sp.x + sp.y;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) s_wtot[warp] = acc;
+        };
+        count_all(std::false_type{});
+        if (tid == 0) s_tk[(it + 1) & 1] = next_t;
+        __syncthreads();
+        const unsigned int tn = s_tk[(it + 1) & 1];
+        if (tid == 0 && tn < n16) next_t = atomicAdd(&p.ctl->ticket_leaf, 1u);
+        warp_totals(false);
+        __syncthreads();
+        unsigned int run = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const unsigned int t2 = s_wtot[w];
+            run += (w < warp) ? t2 : 0u;
+            total += t2;
+        }
+        bool spilled = false;
+        if (total != m) {                                         // uniform: some value has 65536 copies or more
+            __syncthreads();                                      // everyone has read s_wtot
+            for (int i = tid; i < WORDS / 4; i += NT) reinterpret_cast<uint4 *>(s_bins)[i] = make_uint4(0, 0, 0, 0);
+            __syncthreads();
+            count_all(std::true_type{});
+            __threadfence();                                      // spill adds visible to the CTA's other threads
+            __syncthreads();
+            spilled = s_spilled != 0;
+            warp_totals(spilled);
+            __syncthreads();
+            if (tid == 0) s_spilled = 0;                          // everyone holds `spilled`; the next careful count is barriers away
+            run = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) run += (w < warp) ? s_wtot[w] : 0u;
+        }
+        const uint32_t hi16 = seg << 16;
+        unsigned int heavy_th = m >> 6;
+        if (heavy_th < MSD_LEAF_HEAVY) heavy_th = MSD_LEAF_HEAVY;
+        // ---- expand: 32 words (64 values) per step and warp
+        for (int j = lane; j < WORDS_PER_WARP; j += 32) {
+            const unsigned int w = wbw[j];
+            wbw[j] = 0;
+            unsigned int c0 = w & 0xFFFFu, c1 = w >> 16;
+            if (spilled) {
+                uint2 *sp = reinterpret_cast<uint2 *>(spill + 2 * (warp * WORDS_PER_WARP + j));
+                const uint2 v = __ldcg(sp);
+                if (v.x | v.y) { c0 += v.x; c1 += v.y; *sp = make_uint2(0u, 0u); }
+            }
+            const unsigned int cnt = c0 + c1;
+            const unsigned int incl = warp_incl_scan(cnt);
+            const unsigned int tot = __shfl_sync(0xffffffffu, incl, 31);
+            const unsigned int pos = lo + run + incl - cnt;                       // element index of this word's first key
+            const uint32_t v0 = hi16 | (uint32_t)((warp * WORDS_PER_WARP + j) * 2);
+            const uint32_t k0 = IDENT ? v0 : key_decode<uint32_t>(v0, p.xf);
+            const uint32_t k1 = IDENT ? v0 + 1 : key_decode<uint32_t>(v0 + 1, p.xf);
+            if (tot < 256u) {
+                // few copies per value: every lane writes its own two runs — the first three copies as straight-line
+                // predicated stores at precomputed addresses, the rest in a loop
+                uint32_t *o0 = kall + pos, *o1 = kall + (pos + c0);
+                st_if_gt<0, 0>(o0, k0, c0);
+                st_if_gt<0, 0>(o1, k1, c1);
+                st_if_gt<1, 1>(o0, k0, c0);
+                st_if_gt<1, 1>(o1, k1, c1);
+                st_if_gt<2, 2>(o0, k0, c0);
+                st_if_gt<2, 2>(o1, k1, c1);
+                if (max(c0, c1) > 3u) {
+#pragma unroll 1
+                    for (unsigned int q = 3; q < c0; ++q) o0[q] = k0;
+#pragma unroll 1
+                    for (unsigned int q = 3; q < c1; ++q) o1[q] = k1;
+                }
+            } else {
+                // many copies per value (Float32 keys: 64 on average): the warp writes one lane's two adjacent runs at
+                // a time with coalesced stores; runs of at least heavy_th keys (at most 64 per segment) are left to the
+                // whole CTA
+#pragma unroll 1
+                for (int src = 0; src < 32; ++src) {
+                    const unsigned int sc0 = __shfl_sync(0xffffffffu, c0, src), sc = __shfl_sync(0xffffffffu, cnt, src);
+                    const unsigned int sp0 = __shfl_sync(0xffffffffu, pos, src);
+                    const uint32_t sk0 = __shfl_sync(0xffffffffu, k0, src), sk1 = __shfl_sync(0xffffffffu, k1, src);
+                    if (sc == 0) continue;                                       // uniform
+                    if (max(sc0, sc - sc0) < heavy_th) {
+                        for (unsigned int q = lane; q < sc; q += 32) kall[sp0 + q] = q < sc0 ? sk0 : sk1;
+                    } else {
+                        const unsigned int sc1 = sc - sc0;
+                        if (sc0 >= heavy_th) { if (lane == 0) s_heavy[min(atomicAdd(&s_nheavy, 1u), (unsigned int)MAXH)] = make_uint4(sk0, sp0, sc0, 0u); }
+                        else for (unsigned int q = lane; q < sc0; q += 32) kall[sp0 + q] = sk0;
+                        if (sc1 >= heavy_th) { if (lane == 0) s_heavy[min(atomicAdd(&s_nheavy, 1u), (unsigned int)MAXH)] = make_uint4(sk1, sp0 + sc0, sc1, 0u); }
+                        else for (unsigned int q = lane; q < sc1; q += 32) kall[sp0 + sc0 + q] = sk1;
+                    }
+                }
+            }
+            run += tot;
+        }
+        __syncthreads();
+        {
+            const unsigned int nh = min(s_nheavy, (unsigned int)MAXH);   // at most 64 values hold >= m / 64 keys each
+            for (unsigned int e = 0; e < nh; ++e) {
+                const uint4 h = s_heavy[e];
+                for (unsigned int i = tid; i < h.z; i += NT) kall[h.y + i] = h.x;
+            }
+        }
+        __syncthreads();            // table clean, heavy list consumed before the next segment
+        if (tid == 0) s_nheavy = 0;
     }
 }
 

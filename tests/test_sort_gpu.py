@@ -325,3 +325,28 @@ def test_partialsort_radix_select(b, dtype, rev):
         np.testing.assert_array_equal(bits(b.Array(d)), bits(a))
     with pytest.raises(IndexError):
         b.partialsort(b.CuArray(rand(dtype, 5)), 6)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "uint32", "int64", "float64", "int16"])
+@pytest.mark.parametrize("case", ["random", "dups", "constant", "sorted"])
+def test_partialsort_sampled_path(b, dtype, case):
+    """n >= 2^22: b200_select_kth brackets rank k from a sorted sample, compacts the bracket in ONE read and finishes on the
+    candidates; a bracket that misses (or overflows its buffer: constant input) falls back to the streaming passes on the
+    device.  Same answer as sort(c)[k] either way, input untouched."""
+    n = (1 << 22) + 12345
+    a = rand(dtype, n)
+    if case == "dups":
+        a[: n // 2] = a[7]                                        # half the array is one value: bracket = N/2 candidates
+    elif case == "constant":
+        a[:] = a[3]
+    elif case == "sorted":
+        a = np.sort(a)
+    if dtype.startswith("float") and case == "random":
+        a[1] = np.nan; a[2] = -0.0; a[3] = 0.0; a[4] = np.inf; a[5] = -np.inf
+    d = b.CuArray(a)
+    for rev in (False, True):
+        ref = oracle.sort(a, rev=rev)
+        for k in (1, 2, n // 1000, n // 3 + 1, n // 2, n - 1, n):
+            got = b.partialsort(d, k, rev=rev)
+            np.testing.assert_array_equal(bits(np.asarray([got], dtype=a.dtype)), bits(ref[k - 1:k]))
+    np.testing.assert_array_equal(bits(b.Array(d)), bits(a))

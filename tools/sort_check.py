@@ -38,6 +38,14 @@ def gen(n, dist, seed=1):
         return torch.full((n,), 123456789, device="cuda", dtype=torch.int32)
     if dist == "hi16only":     # low 16 bits zero: every leaf segment is one byte-1 group of identical-low keys
         return torch.randint(-2**15, 2**15 - 1, (n,), device="cuda", dtype=torch.int32, generator=g) << 16
+    if dist == "randf":        # bit pattern of uniform [0, 1) floats: half the keys share one top byte, 64 copies per value at 2^30
+        return torch.rand(n, device="cuda", generator=g).view(torch.int32)
+    if dist == "skew2":        # half the keys uniform, half inside one top byte
+        x = torch.randint(-2**31, 2**31 - 1, (n,), device="cuda", dtype=torch.int32, generator=g)
+        y = torch.randint(0, 2**24, (n,), device="cuda", dtype=torch.int32, generator=g) + (0x5A << 24)
+        return torch.where(x > 0, x, y)
+    if dist == "bigval":       # 1024 distinct values over the key space, n / 1024 copies each (> 65535 copies from 2^27 keys)
+        return (torch.randint(0, 1024, (n,), device="cuda", dtype=torch.int32, generator=g) * 4194301) ^ -2**31
     if dist == "sorted":
         return torch.arange(n, device="cuda", dtype=torch.int64).mul_(3).to(torch.int32)
     raise ValueError(dist)
@@ -97,17 +105,23 @@ def main():
     all_ok = True
     if os.environ.get("SORT_CHECK_ONE"):            # listed distributions only, UInt32 (ncu launch lists, A/B timing)
         ok = True
-        for dist in os.environ["SORT_CHECK_ONE"].split(","):
-            ok &= run(1 << logs[0], dt.U32, dist, False, reps=int(os.environ.get("SORT_CHECK_REPS", "2")))
+        for dist in os.environ["SORT_CHECK_ONE"].split(","):          # "dist" (UInt32) or "f32:dist" / "i32:dist"
+            e = dt.U32
+            if ":" in dist:
+                pre, dist = dist.split(":")
+                e = {"f32": dt.F32, "i32": dt.I32, "u32": dt.U32}[pre]
+            ok &= run(1 << logs[0], e, dist, False, reps=int(os.environ.get("SORT_CHECK_REPS", "2")))
         sys.exit(0 if ok else 1)
     for lg in logs:
         n = 1 << lg
-        for dist in ("uniform", "narrow8", "lowbits", "normalf", "dup16", "const", "hi16only", "sorted"):
+        for dist in ("uniform", "narrow8", "lowbits", "normalf", "dup16", "const", "hi16only", "sorted", "randf", "skew2", "bigval"):
             all_ok &= run(n, dt.U32, dist, False)
         all_ok &= run(n, dt.U32, "uniform", True)
         all_ok &= run(n, dt.I32, "uniform", False)
         all_ok &= run(n, dt.F32, "uniform", False)
         all_ok &= run(n, dt.F32, "normalf", True)
+        all_ok &= run(n, dt.F32, "randf", False)
+        all_ok &= run(n, dt.F32, "randf", True)
         all_ok &= run(n - 12345, dt.U32, "uniform", False)
         all_ok &= run(n + 4097, dt.F32, "uniform", False) if lg < 30 else True
     print("ALL OK" if all_ok else "FAILURES", flush=True)
