@@ -35,24 +35,36 @@ struct MgpuPlanParams {
     const unsigned int *hist_all;            // [G][65536]
     MgpuPlan *plan;
     unsigned int *hist_recv;                 // [65536] histogram of the keys this rank will receive
+    unsigned long long *ghist;               // [65536] scratch behind the plan: global histogram
+    unsigned long long *cnt;                 // [16][16] scratch: exact count matrix [source][bucket]
     int G, rank;
 };
 
-__global__ void __launch_bounds__(1024, 1) mgpu_plan_kernel(MgpuPlanParams p) {
+// The plan is four small kernels (a single CTA walking the G x 65536 table three times took 0.43 ms at G = 8):
+//   A  (64 CTAs, a thread per bin)  global histogram = sum over the ranks, coalesced
+//   B  (1 CTA)                      scan of the global histogram -> G - 1 splitters at bin granularity
+//   C  (64 CTAs, a thread per bin)  bucket of every bin, the histogram this rank receives, the G x G count matrix
+//                                   (warp-reduced: a warp's 32 bins nearly always share their bucket)
+//   D  (1 warp)                     offsets / totals for this rank
+__global__ void __launch_bounds__(1024) mgpu_plan_sum_kernel(MgpuPlanParams p) {
+    const unsigned int bin = blockIdx.x * 1024u + threadIdx.x;
+    unsigned long long g = 0;
+    for (int s = 0; s < p.G; ++s) g += p.hist_all[(size_t)s * MSD_BINS + bin];
+    p.ghist[bin] = g;
+    if (blockIdx.x == 0 && threadIdx.x < MG_MAXG * MG_MAXG) p.cnt[threadIdx.x] = 0;
+}
+
+__global__ void __launch_bounds__(1024, 1) mgpu_plan_split_kernel(MgpuPlanParams p) {
     __shared__ unsigned long long s_w[32];
     __shared__ unsigned int s_spl[MG_MAXG + 1];
-    __shared__ unsigned long long s_cnt[MG_MAXG][MG_MAXG];     // [source][bucket]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = p.G;
     if (tid <= MG_MAXG) s_spl[tid] = 0;
-    if (tid < MG_MAXG * MG_MAXG) s_cnt[tid / MG_MAXG][tid % MG_MAXG] = 0;
-    // thread t owns bins [64 t, 64 t + 64): global count of its bins
+    // thread t owns bins [64 t, 64 t + 64)
+    const ulonglong2 *h2 = reinterpret_cast<const ulonglong2 *>(p.ghist) + tid * 32;
     unsigned long long mine = 0;
-    for (int s = 0; s < G; ++s) {
-        const uint4 *h4 = reinterpret_cast<const uint4 *>(p.hist_all + (size_t)s * MSD_BINS) + tid * 16;
 #pragma unroll 4
-        for (int k = 0; k < 16; ++k) { const uint4 v = h4[k]; mine += (unsigned long long)v.x + v.y + v.z + v.w; }
-    }
+    for (int k = 0; k < 32; ++k) { const ulonglong2 v = h2[k]; mine += v.x + v.y; }
     unsigned long long incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -64,88 +76,68 @@ __global__ void __launch_bounds__(1024, 1) mgpu_plan_kernel(MgpuPlanParams p) {
     unsigned long long base = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < 32; ++w) { if (w < warp) base += s_w[w]; total += s_w[w]; }
-    const unsigned long long excl0 = base + incl - mine;        // keys in the bins before this thread's first bin
     // spl[b] = number of bins whose exclusive prefix is below the b-th target = first bin with prefix >= b N / G
-    {
-        unsigned long long target[MG_MAXG];
+    unsigned long long target[MG_MAXG];
 #pragma unroll
-        for (int b = 0; b < MG_MAXG; ++b) target[b] = b < G ? (total * (unsigned long long)b) / (unsigned long long)G : ~0ull;
-        unsigned long long run = excl0;
-        unsigned int below[MG_MAXG];
+    for (int b = 0; b < MG_MAXG; ++b) target[b] = b < G ? (total * (unsigned long long)b) / (unsigned long long)G : ~0ull;
+    unsigned long long run = base + incl - mine;
+    unsigned int below[MG_MAXG];
 #pragma unroll
-        for (int b = 0; b < MG_MAXG; ++b) below[b] = 0;
-        for (int k4 = 0; k4 < 16; ++k4) {
-            unsigned long long g[4] = {0, 0, 0, 0};
-            for (int s = 0; s < G; ++s) {
-                const uint4 v = (reinterpret_cast<const uint4 *>(p.hist_all + (size_t)s * MSD_BINS) + tid * 16)[k4];
-                g[0] += v.x; g[1] += v.y; g[2] += v.z; g[3] += v.w;
-            }
+    for (int b = 0; b < MG_MAXG; ++b) below[b] = 0;
+    for (int k = 0; k < 32; ++k) {
+        const ulonglong2 v = h2[k];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+        for (int b = 1; b < MG_MAXG; ++b) below[b] += (b < G && run < target[b]) ? 1u : 0u;
+        run += v.x;
 #pragma unroll
-                for (int b = 1; b < MG_MAXG; ++b) below[b] += (b < G && run < target[b]) ? 1u : 0u;
-                run += g[q];
-            }
-        }
-#pragma unroll
-        for (int b = 1; b < MG_MAXG; ++b)
-            if (b < G && below[b]) atomicAdd(&s_spl[b], below[b]);
+        for (int b = 1; b < MG_MAXG; ++b) below[b] += (b < G && run < target[b]) ? 1u : 0u;
+        run += v.y;
     }
+#pragma unroll
+    for (int b = 1; b < MG_MAXG; ++b)
+        if (b < G && below[b]) atomicAdd(&s_spl[b], below[b]);
     __syncthreads();
-    if (tid == 0) { s_spl[0] = 0; s_spl[G] = MSD_BINS; }
+    if (tid <= MG_MAXG) p.plan->spl[tid] = tid == 0 ? 0u : (tid < G ? s_spl[tid] : (unsigned int)MSD_BINS);
+    if (tid == 0) { p.plan->total = total; p.plan->ticket = 0; p.plan->pad = 0; }
+}
+
+__global__ void __launch_bounds__(1024) mgpu_plan_count_kernel(MgpuPlanParams p) {
+    __shared__ unsigned int s_spl[MG_MAXG + 1];
+    const int G = p.G;
+    if (threadIdx.x <= MG_MAXG) s_spl[threadIdx.x] = p.plan->spl[threadIdx.x];
     __syncthreads();
-    // exact count matrix and the histogram of what this rank receives
-    {
-        const unsigned int lo_r = s_spl[p.rank], hi_r = s_spl[p.rank + 1];
-        int b = 0;
-        unsigned int bin = (unsigned int)tid * 64;
-        while (b + 1 < G && bin >= s_spl[b + 1]) ++b;
-        unsigned long long acc[MG_MAXG];
-#pragma unroll
-        for (int s = 0; s < MG_MAXG; ++s) acc[s] = 0;
-        for (int k4 = 0; k4 < 16; ++k4) {
-            uint4 v[MG_MAXG];
-#pragma unroll
-            for (int s = 0; s < MG_MAXG; ++s)
-                v[s] = s < G ? (reinterpret_cast<const uint4 *>(p.hist_all + (size_t)s * MSD_BINS) + tid * 16)[k4] : make_uint4(0, 0, 0, 0);
-            uint4 out;
-#pragma unroll
-            for (int q = 0; q < 4; ++q, ++bin) {
-                while (b + 1 < G && bin >= s_spl[b + 1]) {          // bucket boundary inside this thread's range
-#pragma unroll
-                    for (int s = 0; s < MG_MAXG; ++s) {
-                        if (s < G && acc[s]) atomicAdd(&s_cnt[s][b], acc[s]);
-                        acc[s] = 0;
-                    }
-                    ++b;
-                }
-                unsigned int g = 0;
-#pragma unroll
-                for (int s = 0; s < MG_MAXG; ++s) {
-                    const unsigned int c = q == 0 ? v[s].x : q == 1 ? v[s].y : q == 2 ? v[s].z : v[s].w;
-                    acc[s] += c;
-                    g += c;
-                }
-                const unsigned int r = (bin >= lo_r && bin < hi_r) ? g : 0u;
-                if (q == 0) out.x = r; else if (q == 1) out.y = r; else if (q == 2) out.z = r; else out.w = r;
-            }
-            (reinterpret_cast<uint4 *>(p.hist_recv) + tid * 16)[k4] = out;
+    const unsigned int bin = blockIdx.x * 1024u + threadIdx.x;
+    unsigned int b = 0;
+    for (int j = 1; j < G; ++j) b += (bin >= s_spl[j]) ? 1u : 0u;
+    p.hist_recv[bin] = b == (unsigned int)p.rank ? (unsigned int)p.ghist[bin] : 0u;
+    const bool same = __all_sync(0xffffffffu, b == __shfl_sync(0xffffffffu, b, 0));
+    for (int s = 0; s < G; ++s) {
+        const unsigned int v = p.hist_all[(size_t)s * MSD_BINS + bin];
+        if (same) {
+            const unsigned int lo = __reduce_add_sync(0xffffffffu, v & 0xFFFFu), hi = __reduce_add_sync(0xffffffffu, v >> 16);
+            const unsigned long long t = (unsigned long long)lo + ((unsigned long long)hi << 16);
+            if ((threadIdx.x & 31) == 0 && t) atomicAdd(&p.cnt[s * MG_MAXG + b], t);
+        } else if (v) {
+            atomicAdd(&p.cnt[s * MG_MAXG + b], (unsigned long long)v);
         }
-#pragma unroll
-        for (int s = 0; s < MG_MAXG; ++s)
-            if (s < G && acc[s]) atomicAdd(&s_cnt[s][b], acc[s]);
     }
-    __syncthreads();
+}
+
+__global__ void mgpu_plan_finish_kernel(MgpuPlanParams p) {
+    const int tid = threadIdx.x, G = p.G;            // one warp
+    auto cnt = [&](int s, int b) { return p.cnt[s * MG_MAXG + b]; };
     if (tid < MG_MAXG) {
         const int b = tid;
         unsigned long long before = 0, recv_b = 0;
         for (int s = 0; s < G; ++s) {
-            if (s < p.rank) before += s_cnt[s][b];
-            recv_b += s_cnt[s][b];
+            if (b < G) {
+                if (s < p.rank) before += cnt(s, b);
+                recv_b += cnt(s, b);
+            }
         }
         p.plan->dst_base[b] = b < G ? before : 0;
-        p.plan->send_count[b] = b < G ? s_cnt[p.rank][b] : 0;
-        p.plan->recv_count[b] = b < G ? s_cnt[b][p.rank] : 0;   // from source b
+        p.plan->send_count[b] = b < G ? cnt(p.rank, b) : 0;
+        p.plan->recv_count[b] = b < G ? cnt(b, p.rank) : 0;   // from source b
         // max over destinations of what they receive
         unsigned long long mx = b < G ? recv_b : 0;
 #pragma unroll
@@ -155,7 +147,7 @@ __global__ void __launch_bounds__(1024, 1) mgpu_plan_kernel(MgpuPlanParams p) {
         }
         // longest shard (source b's keys over all buckets): sizes sortperm's 4-byte tagged index
         unsigned long long len = 0;
-        for (int d = 0; d < G; ++d) len += b < G ? s_cnt[b][d] : 0;
+        for (int d = 0; d < G; ++d) len += b < G ? cnt(b, d) : 0;
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) {
             const unsigned long long other = __shfl_xor_sync(0x0000ffffu, len, o);
@@ -163,16 +155,12 @@ __global__ void __launch_bounds__(1024, 1) mgpu_plan_kernel(MgpuPlanParams p) {
         }
         if (tid == 0) {
             p.plan->max_shard_len = (uint32_t)(len > 0xFFFFFFFFull ? 0xFFFFFFFFull : len);
-            p.plan->pad = 0;
             unsigned long long rt = 0;
-            for (int s = 0; s < G; ++s) rt += s_cnt[s][p.rank];
+            for (int s = 0; s < G; ++s) rt += cnt(s, p.rank);
             p.plan->recv_total = rt;
             p.plan->max_recv_total = mx;
-            p.plan->total = total;
-            p.plan->ticket = 0;
         }
     }
-    if (tid <= MG_MAXG) p.plan->spl[tid] = tid <= G ? s_spl[tid] : MSD_BINS;
 }
 
 // ------------------------------------------------------------------ fused partition + exchange
@@ -355,7 +343,8 @@ extern "C" {
 
 int32_t b200_mgpu_plan_bytes(size_t *bytes) {
     if (!bytes) return B200_INVALID_VALUE;
-    *bytes = b200::align_up(sizeof(b200::MgpuPlan), 256);
+    // the public struct, then scratch for the plan kernels: global histogram (uint64[65536]) + count matrix (uint64[256])
+    *bytes = b200::align_up(sizeof(b200::MgpuPlan), 256) + (size_t)b200::MSD_BINS * 8 + 256 * 8;
     return B200_OK;
 }
 
@@ -398,7 +387,17 @@ int32_t b200_mgpu_plan(const void *hist_all_dev, int32_t nranks, int32_t rank, v
     pp.plan = static_cast<MgpuPlan *>(plan_dev);
     pp.hist_recv = static_cast<unsigned int *>(hist_recv_dev);
     pp.G = nranks; pp.rank = rank;
-    mgpu_plan_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pp);
+    char *scratch = static_cast<char *>(plan_dev) + align_up(sizeof(MgpuPlan), 256);
+    pp.ghist = reinterpret_cast<unsigned long long *>(scratch);
+    pp.cnt = pp.ghist + MSD_BINS;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    mgpu_plan_sum_kernel<<<MSD_BINS / 1024, 1024, 0, st>>>(pp);
+    B200_CHECK_LAUNCH();
+    mgpu_plan_split_kernel<<<1, 1024, 0, st>>>(pp);
+    B200_CHECK_LAUNCH();
+    mgpu_plan_count_kernel<<<MSD_BINS / 1024, 1024, 0, st>>>(pp);
+    B200_CHECK_LAUNCH();
+    mgpu_plan_finish_kernel<<<1, 32, 0, st>>>(pp);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }
