@@ -722,6 +722,9 @@ def run_extras(b, dt, torch, dev, peak):
     fn = lambda: b.sortperm(cV)
     fn(); med, mn = tmin(fn, 3)
     out["sortperm 2^30 Float32"] = {"ms": med, "Gkeys/s": n / med / 1e6}
+    fn = lambda: b.partialsort(cV, n // 2)          # radix select (sampled bracket + one-read compaction), input untouched
+    fn(); med, mn = tmin(fn, 5)
+    out["partialsort(c, n/2) 2^30 Float32"] = {"ms": med, "GB/s_counting_one_read_of_the_input": 4 * n / med / 1e6}
     del V, cV
     torch.cuda.empty_cache()
     U = torch.randint(-2**31, 2**31 - 1, (n,), device=dev, generator=g, dtype=torch.int32)

@@ -153,49 +153,47 @@ __global__ void __launch_bounds__(1024) select_sample_kernel(const K *__restrict
 }
 
 // ONE streaming read: count the keys below the bracket, compact (ordered-key space) the keys inside it.
-// Every warp stages its candidates in its own slice of shared memory (ballot + popc, no atomics, no CTA barrier) and
-// reserves room in the candidate buffer with one global atomic per ~224 keys.  Measured alternatives: one
-// warp-aggregated global atomic per 32 keys — 22 ms for a median bracket of 2^30 keys (30 M serialised L2 atomics on one
-// word); one atomic per CTA tile behind two barriers — 1.9 ms with an empty bracket (barrier-bound).
-constexpr int SEL_STAGE = 256;
+// Every LANE stages its candidates in its own 64-byte stack in shared memory (a predicated store and an add per key:
+// no ballot, no atomic, no barrier); when some lane's stack is half full the warp flushes all 32 stacks with one scan and
+// one global atomic.  Measured alternatives at 2^30 Float32: a warp-aggregated global atomic per 32 keys — 22 ms for a
+// median bracket (30 M serialised L2 atomics on one word); one atomic per CTA tile behind two barriers — 1.9 ms with an
+// empty bracket (barrier-bound); warp-level staging by ballot + popc — 1.35 ms (issue-bound, ~25 instructions per key).
 template <class K>
 __global__ void __launch_bounds__(512) select_filter_kernel(const K *__restrict__ keys, int64_t n, SortXform xf,
                                                             SelectFast *fast, K *__restrict__ cand, unsigned long long cap) {
     constexpr int VN = 16 / (int)sizeof(K);
     constexpr int NW = 512 / 32;
+    constexpr int CAPL = 64 / (int)sizeof(K);                      // entries per lane; one iteration adds at most 2 VN = CAPL / 2
     __shared__ unsigned long long s_below[NW];
-    __shared__ K s_stage[NW][SEL_STAGE];
+    __shared__ K s_stage[CAPL * 512];                              // [slot][thread]: a warp's stores to one slot are consecutive
     const K lo = (K)fast->lo, hi = (K)fast->hi;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned int lt = (1u << lane) - 1u;
-    K *stage = s_stage[warp];
-    unsigned long long below = 0;
-    unsigned int fill = 0;                                         // warp-uniform
+    K *stage = s_stage + threadIdx.x;
+    unsigned int below = 0;
+    unsigned int fill = 0;
     auto flush = [&]() {
-        __syncwarp();
+        unsigned int incl = fill;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&fast->ncand, (unsigned long long)fill);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (unsigned int i = lane; i < fill; i += 32)
-            if (base + i < cap) cand[base + i] = stage[i];
-        __syncwarp();
+        if (lane == 31) base = atomicAdd(&fast->ncand, (unsigned long long)incl);
+        base = __shfl_sync(0xffffffffu, base, 31) + incl - fill;
+        for (unsigned int i = 0; i < fill; ++i)
+            if (base + i < cap) cand[base + i] = stage[i * 512];
         fill = 0;
     };
     auto take = [&](K raw, bool live) {
         const K key = key_encode<K>(raw, xf);
         below += (live && key < lo) ? 1u : 0u;
-        const bool in = live && key >= lo && key <= hi;
-        const unsigned int m = __ballot_sync(0xffffffffu, in);
-        if (m) {                                                   // warp-uniform
-            if (in) stage[fill + __popc(m & lt)] = key;
-            fill += __popc(m);
-            if (fill > SEL_STAGE - 32) flush();
-        }
+        if (live && key >= lo && key <= hi) { stage[fill * 512] = key; ++fill; }
     };
     const bool aligned = (reinterpret_cast<uintptr_t>(keys) % 16) == 0;
     const int64_t nvec = aligned ? n / VN : 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    // every lane of a warp runs the same iterations (the ballots need the whole warp): warp-uniform loop bounds
+    // every lane of a warp runs the same iterations (the flush is a warp operation): warp-uniform loop bounds
     const int64_t warp_v0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane;
     for (int64_t w = warp_v0; w < nvec; w += 2 * stride) {
         const int64_t v = w + lane, v2 = v + stride;
@@ -210,16 +208,19 @@ __global__ void __launch_bounds__(512) select_filter_kernel(const K *__restrict_
         for (int q = 0; q < VN; ++q) take(e[q], l0);
 #pragma unroll
         for (int q = 0; q < VN; ++q) take(e[VN + q], l1);
+        if (__any_sync(0xffffffffu, fill > (unsigned int)(CAPL / 2))) flush();
     }
     for (int64_t w = nvec * VN + warp_v0; w < n; w += stride) {     // unaligned input / tail: one key per thread
         const int64_t i = w + lane;
         const bool live = i < n;
         take(live ? keys[i] : K(0), live);
+        if (__any_sync(0xffffffffu, fill > (unsigned int)(CAPL / 2))) flush();
     }
-    if (fill) flush();
+    if (__any_sync(0xffffffffu, fill != 0)) flush();
+    unsigned long long below64 = below;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
-    if (lane == 0) s_below[warp] = below;
+    for (int o = 16; o > 0; o >>= 1) below64 += __shfl_xor_sync(0xffffffffu, below64, o);
+    if (lane == 0) s_below[warp] = below64;
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long t = 0;

@@ -125,6 +125,11 @@ static int msd_cfg() {
 }
 #endif
 
+static unsigned int leaf8_cap() {
+    static const unsigned int cap = (unsigned int)tune_int("B200_MSD_CAP8", (int)LEAF8_CAP);   // tuning builds: small caps exercise the 16-bit leaf on small inputs
+    return cap;
+}
+
 static bool xform_is_identity(const SortXform &x) { return x.base_enc == 0 && x.fmn == 0 && x.mag_mask == 0 && x.desc == 0; }
 
 struct MsdBuffers {
@@ -155,7 +160,7 @@ static int32_t msd_launch(const SortCall &c, const MsdBuffers &b, uint32_t *alt,
         pp.hist16 = c.hist16_in ? static_cast<const unsigned int *>(c.hist16_in) : b.hist16; pp.seg_start = b.seg_start; pp.seg_list = b.seg_list; pp.l1_tile_start = b.l1_tile_start;
         pp.list16 = b.list16;
         pp.ctl = b.ctl; pp.n = (unsigned int)n; pp.tile2 = MSD_TILE;
-        pp.cap8 = LEAF8_CAP;
+        pp.cap8 = leaf8_cap();
         pp.cap_a = (unsigned int)(n >> 6) > LEAF_MAX_SEG ? (unsigned int)(n >> 6) : LEAF_MAX_SEG;
         static const unsigned int min_avg = (unsigned int)tune_int("B200_MSD_MIN_AVG", (int)MSD_MIN_AVG);
         pp.min_avg = min_avg;
@@ -193,7 +198,7 @@ static int32_t msd_launch(const SortCall &c, const MsdBuffers &b, uint32_t *alt,
     }
     MsdLeafParams lp{};
     lp.keys = static_cast<uint32_t *>(c.keys); lp.seg_start = b.seg_start; lp.seg_list = b.seg_list; lp.ctl = b.ctl; lp.xf = c.xf;
-    lp.list16 = b.list16; lp.spill = b.spill; lp.cap8 = LEAF8_CAP;
+    lp.list16 = b.list16; lp.spill = b.spill; lp.cap8 = leaf8_cap();
     {   // 8-bit bins: segments up to LEAF8_CAP keys without heavy duplicates
         static thread_local KernelSetup ks;
         int per_sm = 1;

@@ -8,6 +8,7 @@
 #   accumulate.jl     CUDACore.scan! methods            (replaces CUDACore/src/accumulate.jl:135)
 #   sorting.jl        Base.sort!/sortperm!/partialsort! (replaces CUDACore/src/sorting.jl:1003-1070)
 #   indexing.jl       Base.findall(::CuArray{Bool})     (replaces CUDACore/src/indexing.jl:26-66)
+#   multigpu.jl       sharded_sort! over the devices of one process (b200_mgpu_*; no reference counterpart)
 #
 # NOTE: no Julia toolchain exists in the build image, so this package has never been
 # executed there; the Python mirror in cuda.jl_b200/ drives the same C ABI in the tests.
@@ -33,6 +34,7 @@ include("mapreduce.jl")
 include("accumulate.jl")
 include("sorting.jl")
 include("indexing.jl")
+include("multigpu.jl")
 
 function __init__()
     CUDACore.functional() || return

@@ -33,6 +33,14 @@ srt = (np.arange(u.size, dtype=np.uint64) * 16000).astype(np.uint32)
 check("sort! presorted UInt32 (uniform-row paths)", np.array_equal(b.Array(b.sort(b.CuArray(srt))), srt))
 dup = (rng.integers(0, 2**16, size=u.size, dtype=np.uint32) * np.uint32(65537))
 check("sort! heavy duplicates (16-bit-bin leaf)", np.array_equal(b.Array(b.sort(b.CuArray(dup))), np.sort(dup)))
+rf = rng.random((1 << 18) + 5, dtype=np.float32)            # uniform [0, 1): half the keys share one top byte -> heavy-digit ranking
+check("sort! Float32 uniform [0,1) (heavy digits, 16-bit leaf with B200_MSD_CAP8)", np.array_equal(b.Array(b.sort(b.CuArray(rf))), np.sort(rf)))
+big = (rng.integers(0, 64, size=1 << 23, dtype=np.uint32) * np.uint32(67108859))      # 64 values x 2^17 copies: spill path of the 16-bit leaf
+check("sort! 64 values x 131072 copies (spill table)", np.array_equal(b.Array(b.sort(b.CuArray(big))), np.sort(big)))
+del big
+ps = rng.standard_normal((1 << 22) + 3).astype(np.float32)
+check("partialsort (sampled bracket) 2^22", b.partialsort(b.CuArray(ps), 1 << 21) == np.sort(ps)[(1 << 21) - 1])
+del ps
 f = rng.standard_normal(200_003).astype(np.float32)
 f[[3, 4, 5]] = [np.nan, -0.0, 0.0]
 check("sort! Float32 (LSD passes)", np.array_equal(b.Array(b.sort(b.CuArray(f))).view(np.uint32), oracle.sort(f).view(np.uint32)))
