@@ -207,19 +207,29 @@ __global__ void __launch_bounds__(MG_NT, 2) mgpu_scatter_kernel(MgpuScatterParam
     if (tid == 0) next_t = atomicAdd(&p.plan->ticket, 1u);
     __syncthreads();
 
-    for (unsigned int it = 0;; ++it) {
-        const unsigned int t = s_tk[it & 1];
-        if (t >= tiles) break;
-        if (tid < NW * MG_MAXG) (&s_whist[0][0])[tid] = 0;
-        __syncthreads();                                                             // (0)
+    // Software-pipelined over tiles like the single-GPU partition passes: once a tile's keys sit in the staging buffer
+    // their registers are dead, so the NEXT tile's loads are issued there, before the look-back and the write-out.
+    uint32_t keys[MG_ITEMS];
+    auto load_tile = [&](unsigned int t) {
         const unsigned int tile_base = t * MG_TILE;
         const int valid = p.n - tile_base > (unsigned int)MG_TILE ? MG_TILE : (int)(p.n - tile_base);
         const uint32_t *kin = p.keys + tile_base + tid;
-        uint32_t keys[MG_ITEMS];
+        if (valid == MG_TILE) {
+#pragma unroll
+            for (int i = 0; i < MG_ITEMS; ++i) keys[i] = ldg_stream(kin + i * MG_NT);
+        } else {
+#pragma unroll
+            for (int i = 0; i < MG_ITEMS; ++i) keys[i] = (i * MG_NT + tid < valid) ? ldg_stream(kin + i * MG_NT) : 0u;
+        }
+    };
+    if (s_tk[0] < tiles) load_tile(s_tk[0]);
+    for (unsigned int it = 0;; ++it) {
+        const unsigned int t = s_tk[it & 1];
+        if (t >= tiles) break;
+        const unsigned int tile_base = t * MG_TILE;
+        const int valid = p.n - tile_base > (unsigned int)MG_TILE ? MG_TILE : (int)(p.n - tile_base);
         unsigned int bk[(MG_ITEMS + 3) / 4];           // bucket ids, 8 bits each
         PackedRanks<MG_ITEMS> ranks;
-#pragma unroll
-        for (int i = 0; i < MG_ITEMS; ++i) keys[i] = (i * MG_NT + tid < valid) ? ldg_stream(kin + i * MG_NT) : 0u;
 #pragma unroll
         for (int i = 0; i < MG_ITEMS; ++i) {
             const uint32_t e = IDENT ? keys[i] : key_encode<uint32_t>(keys[i], p.xf);
@@ -231,40 +241,36 @@ __global__ void __launch_bounds__(MG_NT, 2) mgpu_scatter_kernel(MgpuScatterParam
             if ((i & 3) == 0) bk[i >> 2] = b;
             else bk[i >> 2] |= b << (8 * (i & 3));
         }
-        // Ranks without atomics (G <= 16 buckets: 32 lanes adding to a handful of shared counters would serialise).
-        // Every lane counts its own keys per bucket, one warp scan per bucket turns the counts into a block of ranks
-        // per lane and the warp's bucket totals, and a second sweep hands the ranks out in item order.
-        auto rank_all = [&](auto gp_tag) {
-            constexpr int GP = decltype(gp_tag)::value;
-            unsigned int nxt[GP];
-#pragma unroll
-            for (int g = 0; g < GP; ++g) nxt[g] = 0;
-#pragma unroll
-            for (int i = 0; i < MG_ITEMS; ++i) {
-                const unsigned int b = (bk[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-#pragma unroll
-                for (int g = 0; g < GP; ++g) nxt[g] += (b == (unsigned int)g) ? 1u : 0u;
-            }
-#pragma unroll
-            for (int g = 0; g < GP; ++g) {
-                const unsigned int incl = warp_incl_scan(nxt[g]);
-                if ((tid & 31) == 31) s_whist[warp][g] = incl;
-                nxt[g] = incl - nxt[g];
-            }
+        // Ranks without atomics (G <= 16 buckets: 32 lanes adding to a handful of shared counters would serialise):
+        // a multi-split by ballots.  NB = bits of a bucket id; the NB ballots of an item give every lane the mask of its
+        // peers (same bucket) — its rank is the popcount below it — and lane j, standing in for bucket j, the mask of
+        // bucket j, which it adds to the warp's running count of that bucket (kept in lane j's register, fetched by
+        // shuffle).  ~25 instructions per key whatever G; the lane-private counting sweeps this replaces cost 5 G.
+        auto rank_all = [&](auto nb_tag) {
+            constexpr int NB = decltype(nb_tag)::value;
+            const unsigned int lane = tid & 31, lt = (1u << lane) - 1u;
+            unsigned int run = 0;                               // lane j: keys of bucket j seen so far in this warp
 #pragma unroll
             for (int i = 0; i < MG_ITEMS; ++i) {
                 const unsigned int b = (bk[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-                unsigned int r = 0;
+                const bool live = b != 0xFFu;
+                unsigned int peers = __ballot_sync(0xffffffffu, live), mine = peers;
 #pragma unroll
-                for (int g = 0; g < GP; ++g)
-                    if (b == (unsigned int)g) { r = nxt[g]; nxt[g] += 1u; }
-                ranks.set(i, r);
+                for (int bit = 0; bit < NB; ++bit) {
+                    const unsigned int bal = __ballot_sync(0xffffffffu, (b >> bit) & 1u);
+                    peers &= ((b >> bit) & 1u) ? bal : ~bal;
+                    mine &= ((lane >> bit) & 1u) ? bal : ~bal;
+                }
+                const unsigned int base = __shfl_sync(0xffffffffu, run, b & 31u);
+                ranks.set(i, live ? base + __popc(peers & lt) : 0u);
+                run += (lane < (1u << NB)) ? __popc(mine) : 0u;
             }
+            if (lane < (unsigned int)MG_MAXG) s_whist[warp][lane] = lane < (1u << NB) ? run : 0u;
         };
-        if (G <= 2) rank_all(std::integral_constant<int, 2>{});
-        else if (G <= 4) rank_all(std::integral_constant<int, 4>{});
-        else if (G <= 8) rank_all(std::integral_constant<int, 8>{});
-        else rank_all(std::integral_constant<int, 16>{});
+        if (G <= 2) rank_all(std::integral_constant<int, 1>{});
+        else if (G <= 4) rank_all(std::integral_constant<int, 2>{});
+        else if (G <= 8) rank_all(std::integral_constant<int, 3>{});
+        else rank_all(std::integral_constant<int, 4>{});
         __syncthreads();                                                             // (A)
         // bucket threads: warp offsets inside the bucket, tile count, publish, scan over the buckets
         unsigned int cnt = 0;
@@ -291,7 +297,13 @@ __global__ void __launch_bounds__(MG_NT, 2) mgpu_scatter_kernel(MgpuScatterParam
                 s_bkt[pos] = (unsigned char)b;
             }
         }
-        if (tid == 0 && s_tk[(it + 1) & 1] < tiles) next_t = atomicAdd(&p.plan->ticket, 1u);
+        {
+            const unsigned int tn = s_tk[(it + 1) & 1];        // written before barrier (B)
+            if (tn < tiles) {
+                if (tid == 0) next_t = atomicAdd(&p.plan->ticket, 1u);
+                load_tile(tn);
+            }
+        }
         // look-back per destination
         if (tid < MG_MAXG) {
             unsigned long long excl = 0;
@@ -333,7 +345,8 @@ __global__ void __launch_bounds__(MG_NT, 2) mgpu_scatter_kernel(MgpuScatterParam
                 p.dst[b][s_gbase[b] + (unsigned long long)i] = s_keys[i];
             }
         }
-        // the next iteration's first barrier (0) separates this write-out from the next tile's staging writes
+        // barrier (A) of the next iteration separates this write-out from the next tile's staging writes; its per-warp
+        // counters (s_whist) are rewritten only after barrier (C) above, which every reader has passed
     }
 }
 

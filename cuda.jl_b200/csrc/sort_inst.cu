@@ -320,6 +320,7 @@ int32_t B200_CAT(sort_run_k, B200_KEY_BYTES)(const SortCall &c) {
         else if (msd_cfg() == 3) rc = xform_is_identity(c.xf) ? msd_launch<true, 1024, 10>(c, mb, alt, st) : msd_launch<false, 1024, 10>(c, mb, alt, st);
         else if (msd_cfg() == 4) rc = xform_is_identity(c.xf) ? msd_launch<true, 512, 16>(c, mb, alt, st) : msd_launch<false, 512, 16>(c, mb, alt, st);
         else if (msd_cfg() == 5) rc = xform_is_identity(c.xf) ? msd_launch<true, 512, 12>(c, mb, alt, st) : msd_launch<false, 512, 12>(c, mb, alt, st);
+        else if (msd_cfg() == 6) rc = xform_is_identity(c.xf) ? msd_launch<true, 512, 24>(c, mb, alt, st) : msd_launch<false, 512, 24>(c, mb, alt, st);
         else
 #endif
         rc = xform_is_identity(c.xf) ? msd_launch<true>(c, mb, alt, st) : msd_launch<false>(c, mb, alt, st);

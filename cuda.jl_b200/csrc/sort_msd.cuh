@@ -410,6 +410,10 @@ __global__ void __launch_bounds__(NT, (NT == 512 && ITEMS <= 16) ? 3 : 1024 / NT
     for (unsigned int it = 0;; ++it) {
         const bool full = cur.valid == TILE;
         const bool chain_head = cur.t == cur.first;
+        if (tid == 0) {
+            s_tk[(it + 1) & 1] = next_t;          // the ticket requested during the previous tile has long arrived
+            if constexpr (LEVEL == 2) s_nh[(it + 1) & 1] = 0;     // last read two tiles ago; next written after (C)
+        }
         // first output index of this bucket's digit `tid` (loaded early, used after the look-back)
         unsigned int bin = 0;
         if (dthread) bin = LEVEL == 1 ? p.seg_start[tid * 256] : p.seg_start[cur.seg * 256 + tid];
@@ -497,39 +501,27 @@ __global__ void __launch_bounds__(NT, (NT == 512 && ITEMS <= 16) ? 3 : 1024 / NT
         }
         __syncthreads();                                                                     // (A)
 
-        // ---- per digit: publish the tile's count, exclusive scan over the digits
-        unsigned int cnt = 0;
-        if (dthread) {
+        // ---- per digit: publish the tile's count, exclusive scan over the digits.  No barrier between the warp scans
+        // and the warp bases: every digit warp sums the lower warps' counters itself (<= 7 conflict-free loads per lane
+        // and one warp reduction), which is cheaper than parking 16 warps at a barrier for 8 numbers.
+        unsigned int cnt = 0, doff = 0;
+        if (dthread) {                             // whole warps (tid < 256)
             cnt = s_hist[tid];
-            s_hist[tid] = 0;                       // ready for the next tile's ranking (two barriers away)
             st_relaxed<uint32_t>(p.status + (size_t)cur.t * 256 + tid, (chain_head ? LB::INCLUSIVE : LB::PARTIAL) | cnt);
-        }
-        if (tid == 0) {
-            s_tk[(it + 1) & 1] = next_t;          // the ticket requested during the previous tile has long arrived
-            if constexpr (LEVEL == 2) s_nh[(it + 1) & 1] = 0;     // last read before barrier (A); next written after (C)
-        }
-        unsigned int incl = cnt;
-        if (warp < 8) {
+            const unsigned int incl = warp_incl_scan(cnt);
+            unsigned int lower = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += up;
-            }
-            if (lane == 31) s_wsum[warp] = incl;
-        }
-        __syncthreads();                                                                     // (B)
-        unsigned int doff = 0;
-        if (dthread) {
-            unsigned int wbase = 0;
+            for (int k = 0; k < 7; ++k) lower += (k < warp) ? s_hist[32 * k + lane] : 0u;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) wbase += (w < warp) ? s_wsum[w] : 0u;
-            doff = wbase + incl - cnt;
+            for (int o = 16; o > 0; o >>= 1) lower += __shfl_xor_sync(0xffffffffu, lower, o);
+            doff = lower + incl - cnt;
             s_doff[tid] = doff;
         }
-        const unsigned int tn = s_tk[(it + 1) & 1];
+        const unsigned int tn = s_tk[(it + 1) & 1];       // written before barrier (A)
         const bool have_next = tn < tiles;
         locate(tn, (it + 1) & 1);
         __syncthreads();                                                                     // (C)
+        if (dthread) s_hist[tid] = 0;              // every digit warp has read the counters; the next ranking is behind barrier (D)
 
         // ---- the first look-back round trip is requested before the scatter and consumed after it: the predecessors
         // published their counts before their own scatter, so these words are (at least) PARTIAL when they arrive
