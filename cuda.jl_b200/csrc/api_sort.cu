@@ -295,6 +295,7 @@ static int32_t select_kth_dispatch(void *ws, size_t wsb, const void *keys, int32
 int32_t b200_select_kth_workspace_bytes(int32_t dtype_key, int64_t n, size_t *bytes) {
     if (!bytes || n < 0) return B200_INVALID_VALUE;
     *bytes = 0;
+    if (n > 0xFFFFFFFFLL) return B200_UNSUPPORTED;      // 32-bit histogram bins: the query doubles as the capability probe
     return select_kth_dispatch(nullptr, 0, nullptr, dtype_key, n, 0, 0, nullptr, nullptr, bytes);
 }
 
@@ -302,6 +303,7 @@ int32_t b200_select_kth(void *workspace, size_t workspace_bytes, const void *key
                         int64_t k, int32_t descending, void *out_value, b200_stream_t stream) {
     if (b200::dtype_size(dtype_key) == 0) return B200_UNSUPPORTED;
     if (n <= 0 || k < 0 || k >= n || !keys || !out_value) return B200_INVALID_VALUE;
+    if (n > 0xFFFFFFFFLL) return B200_UNSUPPORTED;      // the per-digit histograms are 32-bit bins (the Julia hook then falls back)
     return select_kth_dispatch(workspace, workspace_bytes, keys, dtype_key, n, k, descending, out_value, stream, nullptr);
 }
 

@@ -170,31 +170,33 @@ static int32_t msd_launch(const SortCall &c, const MsdBuffers &b, uint32_t *alt,
     MsdScatterParams sp{};
     sp.n = (unsigned int)n; sp.seg_start = b.seg_start; sp.l1_tile_start = b.l1_tile_start; sp.ctl = b.ctl; sp.xf = c.xf;
     const size_t ssmem = (size_t)MSD_TILE * 4;
-    {   // P1: keys -> alt by byte 3
-        static thread_local KernelSetup ks;
+    // P1: keys -> alt by byte 3; P2: alt -> keys by byte 2 inside every level-1 bucket.  Each level is launched in both
+    // instantiations; the plan's ctl->heavy bit lets exactly one of them run (the other returns at once).
+    auto launch_level = [&](auto kern, KernelSetup &ks, int64_t tiles) -> int32_t {
         int per_sm = 1;
-        auto kern = msd_scatter_kernel<1, MSD_NT, MSD_ITEMS, IDENT>;
         int32_t rc = setup_kernel(ks, kern, MSD_NT, ssmem, &per_sm);
         if (rc != B200_OK) return rc;
+        int64_t grid = (int64_t)dev.sm_count * per_sm;
+        if (grid > tiles) grid = tiles;
+        kern<<<(unsigned int)grid, MSD_NT, ssmem, st>>>(sp);
+        B200_CHECK_LAUNCH();
+        return B200_OK;
+    };
+    {
+        static thread_local KernelSetup ks_a, ks_b;
         sp.keys_in = static_cast<const uint32_t *>(src); sp.keys_out = alt; sp.status = b.status1;
-        int64_t grid = (int64_t)dev.sm_count * per_sm;
-        const int64_t tiles = cdiv(n, MSD_TILE);
-        if (grid > tiles) grid = tiles;
-        kern<<<(unsigned int)grid, MSD_NT, ssmem, st>>>(sp);
-        B200_CHECK_LAUNCH();
-    }
-    {   // P2: alt -> keys by byte 2 inside every level-1 bucket
-        static thread_local KernelSetup ks;
-        int per_sm = 1;
-        auto kern = msd_scatter_kernel<2, MSD_NT, MSD_ITEMS, IDENT>;
-        int32_t rc = setup_kernel(ks, kern, MSD_NT, ssmem, &per_sm);
+        int32_t rc = launch_level(msd_scatter_kernel<1, MSD_NT, MSD_ITEMS, IDENT, false>, ks_a, cdiv(n, MSD_TILE));
         if (rc != B200_OK) return rc;
+        rc = launch_level(msd_scatter_kernel<1, MSD_NT, MSD_ITEMS, IDENT, true>, ks_b, cdiv(n, MSD_TILE));
+        if (rc != B200_OK) return rc;
+    }
+    {
+        static thread_local KernelSetup ks_a, ks_b;
         sp.keys_in = alt; sp.keys_out = static_cast<uint32_t *>(c.keys); sp.status = b.status2;
-        int64_t grid = (int64_t)dev.sm_count * per_sm;
-        const int64_t tiles = cdiv(n, MSD_TILE) + 256;
-        if (grid > tiles) grid = tiles;
-        kern<<<(unsigned int)grid, MSD_NT, ssmem, st>>>(sp);
-        B200_CHECK_LAUNCH();
+        int32_t rc = launch_level(msd_scatter_kernel<2, MSD_NT, MSD_ITEMS, IDENT, false>, ks_a, cdiv(n, MSD_TILE) + 256);
+        if (rc != B200_OK) return rc;
+        rc = launch_level(msd_scatter_kernel<2, MSD_NT, MSD_ITEMS, IDENT, true>, ks_b, cdiv(n, MSD_TILE) + 256);
+        if (rc != B200_OK) return rc;
     }
     MsdLeafParams lp{};
     lp.keys = static_cast<uint32_t *>(c.keys); lp.seg_start = b.seg_start; lp.seg_list = b.seg_list; lp.ctl = b.ctl; lp.xf = c.xf;

@@ -254,6 +254,26 @@ static __global__ void __launch_bounds__(1024, 1) msd_plan_kernel(MsdPlanParams 
         o4[k] = o;
     }
     if (tid == 1023) p.seg_start[MSD_BINS] = run;
+    if (tid == 0) s_t[0] = 0;                     // reused below as the tile table; first as the heavy-digit flags
+    __syncthreads();
+    {   // heavy digits (same rule as msd_scatter_kernel's `detect`): a digit holding >= 1/8 of a chain of >= 4 tiles
+        const unsigned int b0 = (unsigned int)tid & ~3u;                       // first thread of this thread's level-1 bucket
+        const unsigned int lo1 = s_excl[b0], hi1 = b0 + 4 < 1024 ? s_excl[b0 + 4] : p.n;
+        const unsigned int tot1 = hi1 - lo1;
+        unsigned int flags = 0;
+        if ((tid & 3) == 0 && p.n >= 4u * p.tile2 && tot1 >= (p.n >> 3)) flags |= 1u;
+        if (tot1 >= 4u * p.tile2) {
+            const unsigned int th = tot1 >> 3;
+#pragma unroll 4
+            for (int k = 0; k < 16; ++k) {
+                const uint4 v = h4[k];
+                if (v.x >= th || v.y >= th || v.z >= th || v.w >= th) flags |= 2u;
+            }
+        }
+        if (flags) atomicOr(&s_t[0], flags);
+    }
+    __syncthreads();
+    if (tid == 0) p.ctl->heavy = s_t[0];
     __syncthreads();
     // level-1 bucket b = bins [256 b, 256 b + 256) = threads 4 b .. 4 b + 3
     unsigned int tiles = 0;
@@ -313,7 +333,10 @@ struct MsdTile {
     int valid;                          // keys in the tile
 };
 
-template <int LEVEL, int NT, int ITEMS, bool IDENT>
+// HEAVY: the instantiation that knows about heavy digits (skewed keys, see `detect`); the plan kernel's ctl->heavy bit of
+// this level says which of the two instantiations runs — keeping the extra code out of the common one is worth ~3 %
+// on uniform keys (register allocation of the hot loop).
+template <int LEVEL, int NT, int ITEMS, bool IDENT, bool HEAVY>
 __global__ void __launch_bounds__(NT, (NT == 512 && ITEMS <= 16) ? 3 : 1024 / NT) msd_scatter_kernel(MsdScatterParams p) {
     using LB = LookBits<uint32_t>;
     constexpr int TILE = NT * ITEMS;
@@ -329,10 +352,11 @@ __global__ void __launch_bounds__(NT, (NT == 512 && ITEMS <= 16) ? 3 : 1024 / NT
     __shared__ unsigned int s_seg[2][4];                     // {bucket, first tile, first key, end key} of a ticket
     __shared__ unsigned int s_l1ts[LEVEL == 2 ? 257 : 1];    // first tile of every level-1 bucket (loaded once)
     __shared__ unsigned int s_l1lo[LEVEL == 2 ? 257 : 1];    // first key of every level-1 bucket
-    __shared__ unsigned int s_hv[2][4];                      // heavy digits of the chain a ticket belongs to (see `detect`)
+    __shared__ unsigned int s_hv[HEAVY ? 2 : 1][4];          // heavy digits of the chain a ticket belongs to (see `detect`)
     __shared__ unsigned int s_nh[2];
 
     if (ld_cg_u32(&p.ctl->mode) == 0) return;
+    if ((((ld_cg_u32(&p.ctl->heavy) >> (LEVEL - 1)) & 1u) != 0u) != HEAVY) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool dthread = NT == 256 || tid < 256;
     const unsigned int tiles = LEVEL == 1 ? (p.n + TILE - 1) / TILE : ld_cg_u32(&p.ctl->tiles2);
@@ -386,7 +410,7 @@ __global__ void __launch_bounds__(NT, (NT == 512 && ITEMS <= 16) ? 3 : 1024 / NT
 
     // ---- prologue: tables, first ticket, first tile's loads
     unsigned int next_t = 0;                       // thread 0: ticket after the current one, requested a tile early
-    if (tid == 0) { s_tk[0] = atomicAdd(ticket, 1u); s_nh[0] = 0; s_nh[1] = 0; }
+    if (tid == 0) { s_tk[0] = atomicAdd(ticket, 1u); s_nh[0] = 0; s_nh[1] = 0; }   // s_nh stays 0 in the !HEAVY instantiation
     if constexpr (LEVEL == 2) {
         for (int i = tid; i < 257; i += NT) {
             s_l1ts[i] = p.l1_tile_start[i];
@@ -401,9 +425,11 @@ __global__ void __launch_bounds__(NT, (NT == 512 && ITEMS <= 16) ? 3 : 1024 / NT
     if constexpr (LEVEL == 2) __syncthreads();
     MsdTile cur = describe(s_tk[0], 0);
     load_tile(cur);
-    if (dthread) {
-        if constexpr (LEVEL == 1) detect(0, p.seg_start[(tid + 1) * 256] - p.seg_start[tid * 256], p.n);
-        else detect(0, p.seg_start[cur.seg * 256 + tid + 1] - p.seg_start[cur.seg * 256 + tid], s_seg[0][3] - s_seg[0][2]);
+    if constexpr (HEAVY) {
+        if (dthread) {
+            if constexpr (LEVEL == 1) detect(0, p.seg_start[(tid + 1) * 256] - p.seg_start[tid * 256], p.n);
+            else detect(0, p.seg_start[cur.seg * 256 + tid + 1] - p.seg_start[cur.seg * 256 + tid], s_seg[0][3] - s_seg[0][2]);
+        }
     }
     __syncthreads();
 
@@ -412,7 +438,7 @@ __global__ void __launch_bounds__(NT, (NT == 512 && ITEMS <= 16) ? 3 : 1024 / NT
         const bool chain_head = cur.t == cur.first;
         if (tid == 0) {
             s_tk[(it + 1) & 1] = next_t;          // the ticket requested during the previous tile has long arrived
-            if constexpr (LEVEL == 2) s_nh[(it + 1) & 1] = 0;     // last read two tiles ago; next written after (C)
+            if constexpr (LEVEL == 2 && HEAVY) s_nh[(it + 1) & 1] = 0;     // last read two tiles ago; next written after (C)
         }
         // first output index of this bucket's digit `tid` (loaded early, used after the look-back)
         unsigned int bin = 0;
@@ -448,7 +474,7 @@ __global__ void __launch_bounds__(NT, (NT == 512 && ITEMS <= 16) ? 3 : 1024 / NT
                 }
                 ranks.set(i, r);
             }
-        } else if (full && s_nh[LEVEL == 1 ? 0 : (it & 1)] != 0) {
+        } else if (HEAVY && full && s_nh[LEVEL == 1 ? 0 : (it & 1)] != 0) {
             // heavy digits: no atomic and no ballot per key.  Pass 1: every lane counts its own keys of each heavy digit;
             // one warp scan + ONE atomic per heavy digit reserve a block of ranks per lane; pass 2 hands a lane's ranks
             // out in item order (equal keys are indistinguishable, any unique rank will do).  The other digits keep
@@ -550,7 +576,7 @@ __global__ void __launch_bounds__(NT, (NT == 512 && ITEMS <= 16) ? 3 : 1024 / NT
             if (tid == 0) next_t = atomicAdd(ticket, 1u);
             nxt = describe(tn, (it + 1) & 1);
             load_tile(nxt);
-            if constexpr (LEVEL == 2) {
+            if constexpr (LEVEL == 2 && HEAVY) {
                 if (nxt.seg != cur.seg) {                 // a new chain: its heavy digits
                     if (dthread) {
                         const unsigned int a = p.seg_start[nxt.seg * 256 + tid], b = p.seg_start[nxt.seg * 256 + tid + 1];

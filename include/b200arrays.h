@@ -309,7 +309,10 @@ int32_t b200_partition_scatter(void *workspace, size_t workspace_bytes, const vo
 /* The reference's bitonic partialsort is "full sort, then c[k]".  b200_select_kth writes the
  * element that a stable sort (isless order, `descending` as in b200_sort_keys) would put at
  * 0-based position k to out_value[0] (device, element type of the keys) WITHOUT sorting or
- * modifying `keys`: sizeof(key) streaming reads of the input (MSD radix select). */
+ * modifying `keys`.  n >= 2^22: a sorted sample brackets rank k, ONE streaming read compacts the bracket (n / 8 keys of
+ * workspace) and the MSD byte passes run over the candidates; a bracket that misses falls back, on the device, to
+ * sizeof(key) streaming reads of the input (the path taken for smaller n).  n >= 2^32: B200_UNSUPPORTED (32-bit bins).
+ * Keys-only sort! on floats (b200_sort_keys*) keeps NaN payloads but drops the NaN SIGN bit; select returns the same key. */
 int32_t b200_select_kth_workspace_bytes(int32_t dtype_key, int64_t n, size_t *bytes);
 int32_t b200_select_kth(void *workspace, size_t workspace_bytes, const void *keys, int32_t dtype_key,
                         int64_t n, int64_t k, int32_t descending, void *out_value, b200_stream_t stream);
