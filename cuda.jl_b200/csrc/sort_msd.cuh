@@ -194,7 +194,8 @@ struct MsdPlanParams {
     unsigned int *list16;           // [65536] segments longer than cap8 (the 16-bit leaf's work list), ascending
     MsdCtl *ctl;
     unsigned int n;
-    unsigned int tile2;             // keys per level-2 tile
+    unsigned int tile2;             // keys per level-2 tile of the heavy-digit instantiation (also the unit of the heavy rule)
+    unsigned int tile2_plain;       // keys per level-2 tile of the plain instantiation (no heavy digit at level 2)
     unsigned int cap8;              // longest segment the 8-bit leaf takes
     unsigned int cap_a;             // longest segment admitted at all (one CTA sorts a segment: load balance)
     unsigned int min_avg;           // hybrid only when n / non-empty segments >= min_avg
@@ -273,14 +274,16 @@ static __global__ void __launch_bounds__(1024, 1) msd_plan_kernel(MsdPlanParams 
         if (flags) atomicOr(&s_t[0], flags);
     }
     __syncthreads();
-    if (tid == 0) p.ctl->heavy = s_t[0];
+    const unsigned int heavy_flags = s_t[0];
+    if (tid == 0) p.ctl->heavy = heavy_flags;
+    const unsigned int tile2 = (heavy_flags & 2u) ? p.tile2 : p.tile2_plain;      // the level-2 instantiation that will run
     __syncthreads();
     // level-1 bucket b = bins [256 b, 256 b + 256) = threads 4 b .. 4 b + 3
     unsigned int tiles = 0;
     if (tid < 256) {
         const unsigned int a = s_excl[tid * 4];
         const unsigned int b = tid == 255 ? p.n : s_excl[tid * 4 + 4];
-        tiles = (b - a + p.tile2 - 1) / p.tile2;
+        tiles = (b - a + tile2 - 1) / tile2;
     }
     unsigned int it = tiles;
 #pragma unroll
