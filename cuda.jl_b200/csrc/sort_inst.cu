@@ -138,9 +138,11 @@ struct MsdBuffers {
 };
 
 // MSD_ITEMS: keys per thread of the heavy-digit instantiation of P1 / P2 (its ranking sweeps need the registers);
-// MSD_ITEMS_PLAIN: of the plain one — 24 instead of 20 is 17 % fewer tiles (look-backs, barriers): measured 10.75 ->
-// 10.38 ms at 2^30 uniform keys, while the heavy instantiation lost 4 % with 24 (Float32 rand 11.0 -> 11.5 ms).
-template <bool IDENT, int MSD_NT = 512, int MSD_ITEMS = 20, int MSD_ITEMS_PLAIN = MSD_ITEMS == 20 ? 24 : MSD_ITEMS>
+// MSD_ITEMS_PLAIN: of the plain one — fewer, larger tiles mean fewer look-backs and barriers per key.  Measured at 2^30
+// uniform keys: 20 keys per thread 10.50 ms, 24: 10.21, 28: 9.94 (56 KB of staging per CTA, two CTAs per SM, 24 bytes of
+// spills in P2), 32: 9.91 but presorted input 13.2 ms (spills in the row-uniform path); the heavy instantiation lost 4 %
+// already at 24 (Float32 rand 11.0 -> 11.5 ms).
+template <bool IDENT, int MSD_NT = 512, int MSD_ITEMS = 20, int MSD_ITEMS_PLAIN = MSD_ITEMS == 20 ? 28 : MSD_ITEMS>
 static int32_t msd_launch(const SortCall &c, const MsdBuffers &b, uint32_t *alt, cudaStream_t st) {
     constexpr int MSD_TILE = MSD_NT * MSD_ITEMS;
     constexpr int MSD_TILE_PLAIN = MSD_NT * MSD_ITEMS_PLAIN;
