@@ -166,7 +166,8 @@ struct SortCtl {
     unsigned int nne;           // non-empty 16-bit segments
     unsigned int tiles2;        // level-2 tiles
     unsigned int max_seg;       // longest 16-bit segment (diagnostic)
-    unsigned int heavy, pad2;   // hybrid path: bit 0 / 1 = level 1 / level 2 has digits holding >= 1/8 of their chain (skewed keys)
+    unsigned int heavy, small_cap;   // hybrid path: bit 0 / 1 = level 1 / level 2 has digits holding >= 1/8 of their chain (skewed keys);
+                                     // small_cap: segments of up to this many keys are sorted on chip by msd_leaf_block_kernel (0: none)
     unsigned int ticket1, ticket2, ticket_leaf, n16;   // n16: entries of the 16-bit leaf's work list
     unsigned long long lsd_ticket[8];   // one tile ticket per LSD pass (persistent CTAs, no per-pass memset)
 };

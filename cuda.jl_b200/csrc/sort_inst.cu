@@ -113,7 +113,9 @@ constexpr int LEAF_NT = 512;
 constexpr int LEAF16_NT = 1024;              // the 128 KB table leaves one CTA per SM: make it a full one
 constexpr unsigned int LEAF8_CAP = 1u << 18;  // segments up to this many keys (4 per value on average; a bin holds 255) go to the 8-bit-bin leaf first
 constexpr unsigned int LEAF_MAX_SEG = 65535; // always admitted; beyond it a segment may hold at most n / 64 keys (one CTA sorts it)
-constexpr unsigned int MSD_MIN_AVG = 3072;   // counting leaf: 65536 bins are walked per segment whatever its length
+constexpr unsigned int MSD_MIN_AVG = 768;    // hybrid path: at least this many keys per non-empty 16-bit segment on average
+constexpr unsigned int MSD_DENSE_AVG = 6144; // from this average on: counting leaves only (they walk 65536 bins per segment whatever its
+                                             // length); below it the short segments are sorted on chip (msd_leaf_block_kernel)
 constexpr int64_t MSD_MAX_N = 1LL << 30;     // 32-bit look-back words carry 30-bit counts
 
 #ifdef B200_TUNING
@@ -128,6 +130,16 @@ static int msd_cfg() {
 static unsigned int leaf8_cap() {
     static const unsigned int cap = (unsigned int)tune_int("B200_MSD_CAP8", (int)LEAF8_CAP);   // tuning builds: small caps exercise the 16-bit leaf on small inputs
     return cap;
+}
+
+// Tile of the on-chip leaf for a sort of n keys (0: not used): the smallest instantiation that holds 1.25 x the average
+// segment of keys spread over all 65536 segments.  Segments longer than the tile go to the counting leaves.
+static int block_leaf_tile(int64_t n) {
+    const int64_t want = (n >> 16) + (n >> 18);
+    if (want <= RX_THREADS * 6) return RX_THREADS * 6;
+    if (want <= RX_THREADS * 12) return RX_THREADS * 12;
+    if (want <= RX_THREADS * 20) return RX_THREADS * 20;
+    return 0;
 }
 
 static bool xform_is_identity(const SortXform &x) { return x.base_enc == 0 && x.fmn == 0 && x.mag_mask == 0 && x.desc == 0; }
@@ -169,7 +181,10 @@ static int32_t msd_launch(const SortCall &c, const MsdBuffers &b, uint32_t *alt,
         pp.cap8 = leaf8_cap();
         pp.cap_a = (unsigned int)(n >> 6) > LEAF_MAX_SEG ? (unsigned int)(n >> 6) : LEAF_MAX_SEG;
         static const unsigned int min_avg = (unsigned int)tune_int("B200_MSD_MIN_AVG", (int)MSD_MIN_AVG);
+        static const unsigned int dense_avg = (unsigned int)tune_int("B200_MSD_DENSE_AVG", (int)MSD_DENSE_AVG);
         pp.min_avg = min_avg;
+        pp.dense_avg = dense_avg;
+        pp.small_cap = (unsigned int)block_leaf_tile(n);
         msd_plan_kernel<<<1, 1024, 0, st>>>(pp);
         B200_CHECK_LAUNCH();
     }
@@ -207,6 +222,21 @@ static int32_t msd_launch(const SortCall &c, const MsdBuffers &b, uint32_t *alt,
     MsdLeafParams lp{};
     lp.keys = static_cast<uint32_t *>(c.keys); lp.seg_start = b.seg_start; lp.seg_list = b.seg_list; lp.ctl = b.ctl; lp.xf = c.xf;
     lp.list16 = b.list16; lp.spill = b.spill; lp.cap8 = leaf8_cap();
+    if (const int bt = block_leaf_tile(n)) {   // short segments of inputs that are sparse at 16 bits (gated on ctl->small_cap)
+        auto go = [&](auto kern, KernelSetup &ks) -> int32_t {
+            const size_t smem = (size_t)RX_WARPS * RX_RADIX * 4 + (size_t)bt * 4;
+            int per_sm = 1;
+            int32_t rc = setup_kernel(ks, kern, RX_THREADS, smem, &per_sm);
+            if (rc != B200_OK) return rc;
+            kern<<<(unsigned int)(dev.sm_count * per_sm), RX_THREADS, smem, st>>>(lp);
+            B200_CHECK_LAUNCH();
+            return B200_OK;
+        };
+        static thread_local KernelSetup ks6, ks12, ks20;
+        int32_t rc = bt == RX_THREADS * 6 ? go(msd_leaf_block_kernel<6, IDENT>, ks6)
+                   : bt == RX_THREADS * 12 ? go(msd_leaf_block_kernel<12, IDENT>, ks12) : go(msd_leaf_block_kernel<20, IDENT>, ks20);
+        if (rc != B200_OK) return rc;
+    }
     {   // 8-bit bins: segments up to LEAF8_CAP keys without heavy duplicates
         static thread_local KernelSetup ks;
         int per_sm = 1;

@@ -199,6 +199,8 @@ struct MsdPlanParams {
     unsigned int cap8;              // longest segment the 8-bit leaf takes
     unsigned int cap_a;             // longest segment admitted at all (one CTA sorts a segment: load balance)
     unsigned int min_avg;           // hybrid only when n / non-empty segments >= min_avg
+    unsigned int dense_avg;         // below this many keys per non-empty segment the short segments are sorted on chip ...
+    unsigned int small_cap;         // ... those of at most small_cap keys (msd_leaf_block_kernel)
 };
 
 static __global__ void __launch_bounds__(1024, 1) msd_plan_kernel(MsdPlanParams p) {
@@ -307,6 +309,7 @@ static __global__ void __launch_bounds__(1024, 1) msd_plan_kernel(MsdPlanParams 
         if (tot_ne == 0 || (unsigned long long)p.n < (unsigned long long)p.min_avg * tot_ne) mode = 0;
         p.ctl->nne = tot_ne;
         p.ctl->n16 = tot_nb;             // the 8-bit leaf appends the segments it gives up on
+        p.ctl->small_cap = (mode && (unsigned long long)p.n < (unsigned long long)p.dense_avg * tot_ne) ? p.small_cap : 0u;
         p.ctl->max_seg = gmx;
         p.ctl->mode = mode;
     }
@@ -701,6 +704,7 @@ __global__ void __launch_bounds__(NT, 3) msd_leaf_kernel(MsdLeafParams p) {
     if (ld_cg_u32(&p.ctl->mode) == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int nne = ld_cg_u32(&p.ctl->nne);
+    const int small_cap = (int)ld_cg_u32(&p.ctl->small_cap);       // segments up to here were sorted by msd_leaf_block_kernel
     for (int i = tid; i < WORDS / 4; i += NT) reinterpret_cast<uint4 *>(s_bins)[i] = make_uint4(0, 0, 0, 0);
 
     // Segments are dealt round-robin to the persistent CTAs (independent work: no ticket).  Bounds of the next segment
@@ -720,7 +724,7 @@ __global__ void __launch_bounds__(NT, 3) msd_leaf_kernel(MsdLeafParams p) {
         if (k + G < nne) { nlo = __ldg(p.seg_start + seg_n1); nhi = __ldg(p.seg_start + seg_n1 + 1); }
         if (k + 2 * G < nne) seg_n2 = __ldg(p.seg_list + k + 2 * G);
         const int m = (int)(hi - lo);
-        if (m <= (int)p.cap8) {                              // uniform over the CTA (longer ones: the plan kernel listed them)
+        if (m <= (int)p.cap8 && m > small_cap) {             // uniform over the CTA (longer ones: the plan kernel listed them)
             uint32_t *base = p.keys + lo;
             // ---- count: one shared atomic per key.  Loads go out CH at a time (a load -> atomic -> load chain would
             // expose one memory round trip per key).  The add needs no return value and no per-key overflow test — a
@@ -825,6 +829,116 @@ __global__ void __launch_bounds__(NT, 3) msd_leaf_kernel(MsdLeafParams p) {
                 }
             }
             __syncthreads();        // table clean / list16 written before the next segment's atomics
+        }
+        lo = nlo; hi = nhi; seg = seg_n1; seg_n1 = seg_n2;
+    }
+}
+
+// ------------------------------------------------------------------ L (sparse): short segments sorted on chip
+// The counting leaves walk 65536 bins per segment whatever its length — 2^32 bins per sort, i.e. 4 per key at 2^30 keys
+// but 32 per key at 2^27.  When the input is sparse at 16 bits (fewer than dense_avg keys per non-empty segment), the
+// segments of up to `small_cap` keys are instead sorted by ONE CTA entirely in shared memory: two stable radix-256
+// passes over the low 16 key bits with the ballot ranking of the block sort (sort_block.cuh, radix_block_sort_kernel —
+// the same code path the sort!(A; dims) tests exercise), keys already in ordered-key space, decoded on the way out.
+// Stable ranking makes duplicates a non-issue; padding keys (all ones) sort behind every real key.
+template <int ITEMS, bool IDENT>
+__global__ void __launch_bounds__(RX_THREADS, ITEMS > 12 ? 3 : 4) msd_leaf_block_kernel(MsdLeafParams p) {
+    constexpr int TILE = RX_THREADS * ITEMS;
+    constexpr int WARP_ITEMS = 32 * ITEMS;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    unsigned int *s_whist = reinterpret_cast<unsigned int *>(s_raw);                 // [8][256]
+    uint32_t *s_keys = reinterpret_cast<uint32_t *>(s_whist + RX_WARPS * RX_RADIX);  // [TILE]
+    __shared__ unsigned int s_wsum[RX_WARPS];
+    if (ld_cg_u32(&p.ctl->mode) == 0) return;
+    int small_cap = (int)ld_cg_u32(&p.ctl->small_cap);
+    if (small_cap == 0) return;
+    if (small_cap > TILE) small_cap = TILE;                    // (the host passes small_cap == TILE)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int nne = ld_cg_u32(&p.ctl->nne);
+    const unsigned int G = gridDim.x;
+    unsigned int k = blockIdx.x;
+    if (k >= nne) return;
+    unsigned int seg = __ldg(p.seg_list + k), lo = __ldg(p.seg_start + seg), hi = __ldg(p.seg_start + seg + 1), seg_n1 = 0;
+    if (k + G < nne) seg_n1 = __ldg(p.seg_list + k + G);
+    uint32_t *const kall = p.keys;
+    const int idx0 = warp * WARP_ITEMS + lane;
+    unsigned int *whist = s_whist + warp * RX_RADIX;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    const int d = tid;
+    for (; k < nne; k += G) {
+        unsigned int nlo = 0, nhi = 0, seg_n2 = 0;
+        if (k + G < nne) { nlo = __ldg(p.seg_start + seg_n1); nhi = __ldg(p.seg_start + seg_n1 + 1); }
+        if (k + 2 * G < nne) seg_n2 = __ldg(p.seg_list + k + 2 * G);
+        const int m = (int)(hi - lo);
+        if (m <= small_cap) {                                  // uniform over the CTA
+            uint32_t keys[ITEMS];
+#pragma unroll
+            for (int it = 0; it < ITEMS; ++it) {
+                const int idx = idx0 + it * 32;
+                keys[it] = idx < m ? ld_coh(kall + lo + idx) : 0xFFFFFFFFu;
+            }
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                const int shift = 8 * pass;
+#pragma unroll
+                for (int q = 0; q < RX_RADIX / 32; ++q) whist[q * 32 + lane] = 0;
+                __syncwarp();
+                unsigned short ranks[ITEMS];
+#pragma unroll
+                for (int it = 0; it < ITEMS; ++it) {
+                    const unsigned int digit = (keys[it] >> shift) & 0xFFu;
+                    unsigned int differ = 0;
+#pragma unroll
+                    for (int bit = 0; bit < 8; ++bit) {
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t.reg .b32 t, bal, ext;\n\t"
+                            "and.b32 t, %1, %2;\n\t"
+                            "setp.ne.u32 p, t, 0;\n\t"
+                            "vote.sync.ballot.b32 bal, p, 0xffffffff;\n\t"
+                            "selp.b32 ext, 0xffffffff, 0, p;\n\t"
+                            "lop3.b32 %0, %0, bal, ext, 0xF6;\n\t}"
+                            : "+r"(differ) : "r"(digit), "r"(1u << bit));
+                    }
+                    const unsigned int peers = ~differ;
+                    const unsigned int lower = peers & lt_mask;
+                    volatile unsigned int *ctr = whist + digit;
+                    const unsigned int old = *ctr;
+                    __syncwarp();
+                    if (lower == 0u) *ctr = old + __popc(peers);
+                    __syncwarp();
+                    ranks[it] = (unsigned short)(old + __popc(lower));
+                }
+                __syncthreads();
+                // per digit: offsets of each warp inside the digit run, then the run's start
+                unsigned int tile_count = 0;
+#pragma unroll
+                for (int w = 0; w < RX_WARPS; ++w) {
+                    const unsigned int c = s_whist[w * RX_RADIX + d];
+                    s_whist[w * RX_RADIX + d] = tile_count;
+                    tile_count += c;
+                }
+                const unsigned int incl = warp_incl_scan(tile_count);
+                if (lane == 31) s_wsum[warp] = incl;
+                __syncthreads();
+                unsigned int wbase = 0;
+#pragma unroll
+                for (int w = 0; w < RX_WARPS; ++w) wbase += (w < warp) ? s_wsum[w] : 0u;
+                const unsigned int doff = wbase + incl - tile_count;
+#pragma unroll
+                for (int w = 0; w < RX_WARPS; ++w) s_whist[w * RX_RADIX + d] += doff;
+                __syncthreads();
+#pragma unroll
+                for (int it = 0; it < ITEMS; ++it) s_keys[whist[(keys[it] >> shift) & 0xFFu] + ranks[it]] = keys[it];
+                __syncthreads();
+                if (pass == 0) {
+#pragma unroll
+                    for (int it = 0; it < ITEMS; ++it) keys[it] = s_keys[idx0 + it * 32];
+                    __syncthreads();   // everyone has reloaded before the next pass rewrites s_whist / s_keys
+                }
+            }
+            // padding (all-ones keys) sorted last: positions >= m
+            for (int idx = tid; idx < m; idx += RX_THREADS) kall[lo + idx] = IDENT ? s_keys[idx] : key_decode<uint32_t>(s_keys[idx], p.xf);
+            __syncthreads();                                   // s_keys is rewritten by the next segment's first pass
         }
         lo = nlo; hi = nhi; seg = seg_n1; seg_n1 = seg_n2;
     }
