@@ -534,12 +534,6 @@ def _fused_available(shard, ops):
         return False
 
 
-def _sample_unsorted(c, group):
-    """S regular samples of an unsorted shard (a random sample for shuffled data; for presorted
-    data regular positions are exactly the regular-sampling choice)."""
-    return c
-
-
 def dist_sort(shard, rev=False, group=None, ops=None):
     """Distributed sample sort of the concatenation of all shards.  Returns this rank's slice of
     the globally sorted sequence (slices are in rank order; their sizes are data dependent) and
