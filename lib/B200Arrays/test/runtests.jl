@@ -19,4 +19,17 @@ include(joinpath(CUDA_TEST, "setup.jl"))
     @test Array(sortperm(x)) == p_graft
     @test Array(cumsum(x)) ≈ c_graft
     B200Arrays.enable!(true)
+    # large keys-only sorts: the hybrid MSD path (n >= 2^27) on uniform and skewed keys, against Base on the host
+    for gen in (() -> CUDA.rand(UInt32, 1 << 27), () -> CUDA.rand(Float32, 1 << 27), () -> CUDA.randn(Float32, 1 << 27))
+        y = gen()
+        @test Array(sort(y)) == sort(Array(y))
+        @test partialsort(y, 1 << 26) == sort(Array(y))[1 << 26]          # sampled radix select (n >= 2^22)
+    end
+    # sharded sort over every visible device (multigpu.jl): concatenated slices == Base's sort of the concatenation
+    if length(CUDA.devices()) >= 2
+        shards = [CUDA.device!(d) do; CUDA.rand(UInt32, 1 << 22); end for d in CUDA.devices()]
+        host = reduce(vcat, Array.(shards))
+        out = B200Arrays.sharded_sort!(shards)
+        @test reduce(vcat, Array.(out)) == sort(host)
+    end
 end
