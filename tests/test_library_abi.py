@@ -26,6 +26,25 @@ def test_header_symbols_exported():
     assert set(b._lib.SIGNATURES) == set(syms)
 
 
+def test_artifact_is_shippable_and_env_free():
+    """Round-1 verdict: a 202 MB library with getenv knobs in product code is not a JLL artifact.  The product build
+    compresses its fatbins and reads no environment variable (tuning knobs exist only in -DB200_TUNING builds)."""
+    import b200arrays as b
+    path = b._lib.LIB_PATH
+    if os.environ.get("B200ARRAYS_LIB"):
+        pytest.skip("a variant library was selected through B200ARRAYS_LIB")
+    assert os.path.getsize(path) < 40 * 1024 * 1024, f"{path} is {os.path.getsize(path) >> 20} MB"
+    blob = open(path, "rb").read()
+    for knob in (b"B200_SORT_HYBRID", b"B200_MSD_MIN_LOG2N", b"B200_SCAN_CHAIN", b"B200_SELECT_FAST"):
+        assert knob not in blob, f"{knob.decode()} is read by the product library"
+    # the size queries of the workspaces the Julia layer asks for answer without a GPU
+    n = ctypes.c_size_t(0)
+    lib = b._lib.load()
+    assert lib.b200_sort_workspace_bytes(6, -1, 1 << 30, 1, ctypes.byref(n)) == 0 and (4 << 30) < n.value < (5 << 30)
+    assert lib.b200_select_kth_workspace_bytes(2, 1 << 30, ctypes.byref(n)) == 0 and n.value < (1 << 30)
+    assert lib.b200_select_kth_workspace_bytes(2, 1 << 33, ctypes.byref(n)) == 2        # 32-bit bins: UNSUPPORTED
+
+
 def test_host_only_entry_points():
     import b200arrays as b
     lib = b._lib.load()
