@@ -1,4 +1,4 @@
-// sort_msd.cuh — hybrid MSD radix sort for DENSE 32-bit keys (keys-only `sort!`), sm_100a.
+// sort_msd.cuh — hybrid MSD radix sort for 32-bit keys (keys-only `sort!`, 2^27 keys and more), sm_100a.
 //
 // Why: an LSD radix pass must rank stably, and a stable warp rank costs ~37 issue slots per key row
 // (8 ballots) — three such passes put `sort!` at ~290 instructions per key (profiles/r1_sort_opcode_mix.md).
@@ -8,20 +8,29 @@
 //   H   msd_hist16_kernel   one read of the keys -> histogram of the top 16 key bits (65536 bins, packed 16-bit
 //                           shared-memory counters, flushed to global before a field can overflow)
 //   PL  msd_plan_kernel     exclusive scan of the histogram = start of every 16-bit segment; list of non-empty
-//                           segments; tile table of the 256 level-1 buckets; decides whether the data is dense
-//                           enough (largest segment fits the leaf's shared memory, segments long enough for a
-//                           counting leaf) — otherwise `mode` stays 0, every kernel below returns at once and the
-//                           LSD passes of sort.cuh (gated on the same word) run instead
+//                           segments; work list of the 16-bit leaf; tile table of the 256 level-1 buckets; flags for
+//                           heavy digits (skewed keys); decides whether the path runs at all (largest segment at most
+//                           max(65535, n / 64) keys — one CTA sorts a segment —, at least min_avg keys per non-empty
+//                           segment) — otherwise `mode` stays 0, every kernel below returns at once and the LSD passes
+//                           of sort.cuh (gated on the same word) run instead
 //   P1  msd_scatter_kernel<1>  partition by key byte 3 (atomic rank inside the tile, decoupled look-back over
 //                           the tiles, digit runs written from shared memory) : keys -> alt
 //   P2  msd_scatter_kernel<2>  the same inside each level-1 bucket by key byte 2 (tiles never straddle a bucket,
 //                           the look-back chain restarts at a bucket's first tile)       : alt -> keys
-//   L   msd_leaf_kernel     persistent CTAs take one 16-bit segment at a time: histogram of its low 16 bits in a packed
-//                           shared-memory table (one atomic per key), then the table is walked in value order and
-//                           every value written `count` times, in place (a keys-only sort of a 16-bit residue IS
-//                           its histogram)
+//                           Both levels exist in two instantiations: plain (28 keys per thread) and heavy-digit-aware
+//                           (20 keys per thread; digits holding >= 1/8 of their chain are ranked lane-privately, without
+//                           atomics); the plan's flag bits let exactly one of them run.
+//   LB  msd_leaf_block_kernel  inputs that are sparse at 16 bits: segments of up to 1536 / 3072 / 5120 keys sorted by one
+//                           CTA in shared memory (two stable radix-256 passes over the low 16 bits)
+//   L8  msd_leaf_kernel     persistent CTAs take one 16-bit segment (up to 2^18 keys) at a time: histogram of its low 16
+//                           bits in a packed 8-bit-bin shared-memory table (one atomic per key), then the table is walked
+//                           in value order and every value written `count` times, in place (a keys-only sort of a 16-bit
+//                           residue IS its histogram)
+//   L16 msd_leaf16_kernel   the same with 16-bit bins for longer segments (any length, one ticket each) and for heavy
+//                           duplicates; values with more than 32767 copies spill into a per-CTA table in global memory
 //
-// ~125 instructions per key in total instead of ~290, three passes over HBM plus the histogram read.
+// ~170 instructions per key in total instead of ~290, three passes over HBM plus the histogram read: 2^30 UInt32 keys in
+// 9.9 ms (108 Gkeys/s), Float32 `rand` keys in 10.9 ms (profiles/r2_sort_final.md).
 // Replaces (for this input class) CUDACore/src/sorting.jl:909-974 `bitonic_sort!`; keys keep Julia's `isless`
 // order through key_encode / key_decode exactly as in the LSD path.
 #pragma once
